@@ -1,0 +1,116 @@
+/* starflate_b200 — C ABI of the B200-native raw-DEFLATE decompressor.
+ *
+ * This is the drop-in boundary for the one hot path of garymm/starflate:
+ *   starflate::decompress(std::span<const std::byte>, std::span<std::byte>) -> DecompressStatus
+ *   (reference: src/decompress.hpp:63-64, src/decompress.cpp:402-461)
+ * The reference has no FFI/plugin registry; its C++ free function *is* the interface.  The
+ * C++23 mirror of that interface lives in starflate_b200/cpp/ (g++), and reaches the CUDA
+ * kernels (nvcc, C++20) only through the functions declared here — plain pointers and sizes,
+ * no C++ or torch types.  INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Two kinds of result:
+ *   - the return value of every function is an *infrastructure* code (sfb200_rc): 0 on success,
+ *     non-zero for CUDA / argument failures.  There is no CPU fallback: without a usable CUDA
+ *     device every entry point fails with SFB200_RC_NO_DEVICE.
+ *   - per-stream results are starflate::DecompressStatus values (src/decompress.hpp:13-23),
+ *     one uint8_t per stream, bit-identical to what the reference returns for that stream, plus
+ *     `written` (bytes produced) — an extension the reference cannot report.
+ */
+#ifndef STARFLATE_B200_H
+#define STARFLATE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SFB200_ABI_VERSION 1
+
+/* starflate::DecompressStatus, numeric values preserved (src/decompress.hpp:13-23). */
+enum sfb200_status {
+  SFB200_SUCCESS = 0,
+  SFB200_ERROR = 1, /* never produced by the reference; used here only for streams that
+                       violate the batch preconditions (sizes >= 4 GiB, see below) */
+  SFB200_INVALID_BLOCK_HEADER = 2,
+  SFB200_NO_COMPRESSION_LEN_MISMATCH = 3,
+  SFB200_DST_TOO_SMALL = 4,
+  SFB200_SRC_TOO_SMALL = 5,
+  SFB200_INVALID_LIT_OR_LEN = 6,
+  SFB200_INVALID_DISTANCE = 7
+};
+
+/* infrastructure return codes */
+enum sfb200_rc {
+  SFB200_RC_OK = 0,
+  SFB200_RC_NO_DEVICE = 1,    /* no CUDA device / driver: the product has no CPU path */
+  SFB200_RC_BAD_ARGUMENT = 2,
+  SFB200_RC_CUDA_ERROR = 3,   /* see sfb200_last_error() */
+  SFB200_RC_OUT_OF_MEMORY = 4
+};
+
+typedef struct sfb200_ctx sfb200_ctx;
+
+/* Create / destroy a context bound to one CUDA device (one per process-rank; streams of a
+ * batch are independent, so multi-GPU use is one context per GPU with no communication). */
+int sfb200_create(int device, sfb200_ctx** out);
+void sfb200_destroy(sfb200_ctx* ctx);
+const char* sfb200_last_error(const sfb200_ctx* ctx);
+int sfb200_abi_version(void);
+
+/* Batched decompress, everything resident in device memory (the metric's path).
+ *
+ * Stream i reads  src_base[src_off[i] .. src_off[i]+src_len[i])  and writes
+ *                 dst_base[dst_off[i] .. dst_off[i]+dst_cap[i]);
+ * status[i] receives the DecompressStatus, written[i] (may be NULL) the bytes produced.
+ * All six arrays are DEVICE pointers; regions of different streams must not overlap.
+ * Replaces one reference call per stream: decompress(src_i, dst_i) (src/decompress.cpp:402).
+ * Semantics preserved per stream: first error wins, bytes already produced stay in dst,
+ * dst beyond `written` is never touched, trailing src bytes after the final block are ignored.
+ * Precondition: src_len[i], dst_cap[i] < 2^32 - 16 (else status[i] = SFB200_ERROR).
+ * `cuda_stream` is a cudaStream_t (NULL = default stream); the call is asynchronous. */
+int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
+                                   const uint64_t* src_off, const uint64_t* src_len,
+                                   uint8_t* dst_base, const uint64_t* dst_off,
+                                   const uint64_t* dst_cap, uint8_t* status,
+                                   uint64_t* written, uint64_t n, void* cuda_stream);
+
+/* Same batch, HOST buffers: stages src to the device, runs the kernel, copies dst/status/
+ * written back, synchronises.  `src_bytes` / `dst_bytes` are the sizes of the two flat
+ * buffers.  dst is copied to the device first so that bytes the decoder leaves untouched
+ * keep their caller-provided value (reference contract). */
+int sfb200_decompress_batch_host(sfb200_ctx* ctx, const uint8_t* src, uint64_t src_bytes,
+                                 const uint64_t* src_off, const uint64_t* src_len,
+                                 uint8_t* dst, uint64_t dst_bytes, const uint64_t* dst_off,
+                                 const uint64_t* dst_cap, uint8_t* status, uint64_t* written,
+                                 uint64_t n);
+
+/* Single stream, host buffers: the exact shape of the reference entry point
+ * decompress(span src, span dst) (src/decompress.hpp:63-64).  *status receives the
+ * DecompressStatus; *written (may be NULL) the bytes produced. */
+int sfb200_decompress(sfb200_ctx* ctx, const uint8_t* src, size_t src_len, uint8_t* dst,
+                      size_t dst_cap, uint8_t* status, uint64_t* written);
+
+/* Position-weighted 64-bit checksum of each stream's output region [0, len[i]) computed on the
+ * device (used by tests/bench to verify multi-GiB outputs without a device->host copy):
+ *   sum_j (byte_j + 1) * (0x9E3779B97F4A7C15 * (j + 1) | 1)   mod 2^64. */
+int sfb200_checksum_batch_device(sfb200_ctx* ctx, const uint8_t* base, const uint64_t* off,
+                                 const uint64_t* len, uint64_t* out, uint64_t n,
+                                 void* cuda_stream);
+
+/* Tuning / introspection (bench harness only; not part of the reference surface). */
+typedef struct sfb200_launch_info {
+  int sm_count;
+  int warps_per_cta;
+  int ctas_per_sm;
+  int smem_bytes_per_cta;
+  int regs_per_thread;
+  uint64_t kernel_launches; /* kernels launched by this context so far */
+} sfb200_launch_info;
+int sfb200_get_launch_info(sfb200_ctx* ctx, sfb200_launch_info* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STARFLATE_B200_H */

@@ -1,0 +1,73 @@
+// TEST INFRASTRUCTURE ONLY — CPU emulation of the CUDA kernel's lane logic (see cuda_shim.h).
+#define SFB_CPU_EMU 1
+#include "cuda_shim.h"
+
+#include <vector>
+
+// the kernel's dynamic shared memory: one emulated lane, laid out exactly as on the device
+static thread_local uint16_t* emu_smem = nullptr;
+#define SFB_EMU_SMEM emu_smem
+static unsigned long long emu_stat_tokens = 0, emu_stat_slow_tokens = 0;
+#define SFB_STAT(name) (++emu_stat_##name)
+#include "../../starflate_b200/csrc/inflate_lanes.cuh"
+
+using EmuCfg = sfb::Cfg<SFB_EMU_ROOT_LIT, SFB_EMU_ROOT_DIST, SFB_EMU_POOL, 1>;
+
+// Each stream is run in private, padded copies of its src/dst regions that keep the original
+// address alignment (mod 16).  The kernel's aligned word accesses may legitimately touch the
+// padding of src (reads) but must never modify anything outside [dst, dst+cap): the canaries
+// around dst are verified.  Returns 0, or 1000+i if stream i wrote out of bounds.
+extern "C" int emu_decompress_batch(const uint8_t* src, const uint64_t* src_off,
+                                    const uint64_t* src_len, uint8_t* dst,
+                                    const uint64_t* dst_off, const uint64_t* dst_cap,
+                                    uint8_t* status, uint64_t* written, uint64_t n)
+{
+  std::vector<uint16_t> smem(EmuCfg::SMEM_BYTES / 2 + 64, 0xDEAD);
+  emu_smem = smem.data();
+  blockDim.x = 1;  // one emulated lane
+  gridDim.x = 1;
+  constexpr size_t PAD = 64;
+  for (uint64_t i = 0; i < n; ++i) {
+    const uint8_t* s = src + src_off[i];
+    uint8_t* d = dst + dst_off[i];
+    std::vector<uint8_t> sbuf(src_len[i] + 2 * PAD + 16, 0xEE);
+    std::vector<uint8_t> dbuf(dst_cap[i] + 2 * PAD + 16, 0xC3);
+    auto place = [](std::vector<uint8_t>& v, const void* like) {
+      uint8_t* p = v.data() + PAD;
+      while ((reinterpret_cast<uintptr_t>(p) & 15u) != (reinterpret_cast<uintptr_t>(like) & 15u)) ++p;
+      return p;
+    };
+    uint8_t* sp = place(sbuf, s);
+    uint8_t* dp = place(dbuf, d);
+    if (src_len[i]) std::memcpy(sp, s, src_len[i]);
+    if (dst_cap[i]) std::memcpy(dp, d, dst_cap[i]);
+    unsigned long long counter = 0;
+    const uint64_t zero = 0;
+    sfb::BatchArgs a;
+    a.src_base = sp;
+    a.src_off = &zero;
+    a.src_len = &src_len[i];
+    a.dst_base = dp;
+    a.dst_off = &zero;
+    a.dst_cap = &dst_cap[i];
+    a.status = &status[i];
+    a.written = written ? &written[i] : nullptr;
+    a.n = 1;
+    a.group_counter = &counter;
+    threadIdx.x = 0;
+    blockIdx.x = 0;
+    sfb::inflate_lanes_kernel<EmuCfg>(a);
+    for (uint8_t* q = dbuf.data(); q < dp; ++q)
+      if (*q != 0xC3) return 1000 + static_cast<int>(i);
+    for (uint8_t* q = dp + dst_cap[i]; q < dbuf.data() + dbuf.size(); ++q)
+      if (*q != 0xC3) return 1000 + static_cast<int>(i);
+    if (dst_cap[i]) std::memcpy(d, dp, dst_cap[i]);
+  }
+  return 0;
+}
+
+extern "C" void emu_stats(unsigned long long* out)
+{
+  out[0] = emu_stat_tokens;
+  out[1] = emu_stat_slow_tokens;
+}

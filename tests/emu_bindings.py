@@ -1,0 +1,48 @@
+"""TEST INFRASTRUCTURE ONLY: builds/loads tests/cpu_emu (the kernel's lane logic compiled for the
+host, one emulated lane per stream; see tests/cpu_emu/cuda_shim.h).  Not a fallback: nothing in
+the product package can reach this."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+_u8p = C.POINTER(C.c_uint8)
+_u64p = C.POINTER(C.c_uint64)
+
+
+def build(root_lit=9, root_dist=6, pool=192) -> str:
+    out = os.path.join(HERE, "cpu_emu", f"libemu_{root_lit}_{root_dist}_{pool}.so")
+    srcs = [os.path.join(HERE, "cpu_emu", "emu.cpp"), os.path.join(HERE, "cpu_emu", "cuda_shim.h"),
+            os.path.join(ROOT, "starflate_b200", "csrc", "inflate_lanes.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
+        subprocess.check_call(["g++", "-std=c++20", "-O2", "-fPIC", "-shared",
+                               f"-DSFB_EMU_ROOT_LIT={root_lit}", f"-DSFB_EMU_ROOT_DIST={root_dist}",
+                               f"-DSFB_EMU_POOL={pool}", "-o", out, srcs[0]])
+    return out
+
+
+class Emu:
+    def __init__(self, **kw):
+        self.lib = C.CDLL(build(**kw))
+        self.lib.emu_decompress_batch.argtypes = [_u8p, _u64p, _u64p, _u8p, _u64p, _u64p, _u8p,
+                                                  _u64p, C.c_uint64]
+
+    def decompress_batch(self, b, dst):
+        st = np.zeros(b.n, np.uint8)
+        wr = np.zeros(b.n, np.uint64)
+        p = lambda a, t: a.ctypes.data_as(t)
+        rc = self.lib.emu_decompress_batch(p(b.src, _u8p), p(b.src_off, _u64p), p(b.src_len, _u64p),
+                                           p(dst, _u8p), p(b.dst_off, _u64p), p(b.dst_cap, _u64p),
+                                           p(st, _u8p), p(wr, _u64p), b.n)
+        assert rc == 0, f"emulated kernel wrote outside a dst region (code {rc})"
+        return st, wr
+
+    def stats(self):
+        out = (C.c_ulonglong * 2)()
+        self.lib.emu_stats(out)
+        return {"tokens": out[0], "slow_tokens": out[1]}

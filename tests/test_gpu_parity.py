@@ -1,0 +1,172 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the golden fixtures (the
+reference's own results), the oracle on seeded batches, and size-independent properties at
+BASELINE.json's full sizes.  Integer/byte work: the bar is bit-exact (bytes, status, written)."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from tests import deflate_tools as T
+from tests import gpu_util
+from tests import known_answers as K
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_family(ctx, oracle, golden, name, dst_align=1, src_align=1):
+    cases = golden.cases(name)
+    b = T.Batch([c[1] for c in cases], [c[2] for c in cases], dst_align=dst_align,
+                src_align=src_align)
+    st, wr, dst = gpu_util.run_device(ctx, b)
+    bad = []
+    for k, (i, src, cap) in enumerate(cases):
+        want_st, want_wr, want_hash, cls = golden.expected(name, i)
+        got_hash = "%016x" % oracle.fnv1a64(b.dst_slice(dst, k).tobytes())
+        if (int(st[k]), int(wr[k]), got_hash) != (want_st, want_wr, want_hash):
+            bad.append((i, cls, int(st[k]), int(wr[k]), want_st, want_wr))
+    assert not bad, (name, len(bad), bad[:5])
+    # nothing outside the per-stream regions may change (gaps keep the fill value)
+    mask = np.ones(b.dst_total, dtype=bool)
+    for k in range(b.n):
+        o = int(b.dst_off[k])
+        mask[o:o + int(b.dst_cap[k])] = False
+    assert (dst[mask] == 0xA5).all()
+
+
+def test_golden_families_bit_exact(ctx, oracle, golden):
+    """All 25k committed cases: status, written and every dst byte (incl. untouched tail)."""
+    for name in golden.families:
+        _check_family(ctx, oracle, golden, name)
+
+
+@pytest.mark.parametrize("dst_align,src_align", [(8, 4), (256, 16), (3, 5)])
+def test_golden_alignment_variants(ctx, oracle, golden, dst_align, src_align):
+    for name in ("known_answers", "cut1_multiblock_12000", "cap_dynamic_4096",
+                 "cap_stored_4096", "crafted_dynamic_headers", "flip_repetitive_70000"):
+        _check_family(ctx, oracle, golden, name, dst_align, src_align)
+
+
+@pytest.mark.parametrize("name,hx,cap,status,prefix,cls", K.KNOWN, ids=[k[0] for k in K.KNOWN])
+def test_known_answers_single_stream_host_api(ctx, name, hx, cap, status, prefix, cls):
+    """sfb200_decompress: the reference entry point's shape, host buffers."""
+    st, dst, written = ctx.decompress(bytes.fromhex(hx), cap, fill=0xA5)
+    assert st == status
+    if prefix is not None:
+        assert dst[:written].hex() == prefix
+    assert dst[written:] == bytes([0xA5]) * (cap - written)
+
+
+def test_starfleet_roundtrip(ctx, golden):
+    # /root/reference/src/test/decompress_test.cpp:136-174
+    for base in ("starfleet_fixed", "starfleet_dynamic"):
+        st, dst, written = ctx.decompress(golden.bases[base], K.STARFLEET_LEN)
+        assert (st, written) == (0, K.STARFLEET_LEN)
+        assert hashlib.md5(dst).hexdigest() == K.STARFLEET_MD5
+
+
+def test_mixed_batch_vs_oracle(ctx, oracle):
+    """Seeded ragged batch (all block types, truncations, short dst) — every byte vs the oracle."""
+    rng = np.random.default_rng(77)
+    streams, caps = [], []
+    kinds = ["dynamic", "fixed", "stored", "multiblock", "repetitive"]
+    for i in range(1500):
+        size = int(rng.choice([1, 17, 300, 4096, 20000, 65536, 150000]))
+        plain, comp = T.make_stream(kinds[i % 5], size, 5000 + i)
+        if i % 11 == 0:
+            comp = comp[: int(rng.integers(0, len(comp) + 1))]
+        cap = len(plain)
+        if i % 13 == 0:
+            cap = max(0, cap - int(rng.integers(1, 300)))
+        if i % 17 == 0:
+            cap += int(rng.integers(1, 50))
+        streams.append(comp)
+        caps.append(cap)
+    streams.append(b"")  # empty source
+    caps.append(0)
+    b = T.Batch(streams, caps)
+    st, wr, dst = gpu_util.run_device(ctx, b)
+    dst_o = b.new_dst()
+    ost, owr, _ = oracle.decompress_batch(b.src, b.src_off, b.src_len, dst_o, b.dst_off, b.dst_cap, 8)
+    assert (st == ost).all(), np.nonzero(st != ost)[0][:10]
+    assert (wr == owr).all()
+    assert (dst == dst_o).all()
+    assert set(np.unique(ost)) >= {0, 4, 6}  # the batch really contains failures too
+
+
+def test_host_batch_api_matches_device_api(ctx, oracle):
+    streams, caps = [], []
+    for i in range(200):
+        plain, comp = T.make_stream(["dynamic", "fixed", "stored"][i % 3], 100 + 37 * i, i)
+        streams.append(comp)
+        caps.append(len(plain) - (i % 5 == 0) * 3 + (i % 7 == 0) * 9)
+    b = T.Batch(streams, caps, dst_align=1)
+    dst = b.new_dst()
+    st, wr = ctx.decompress_batch_host(b.src, b.src_off, b.src_len, dst, b.dst_off, b.dst_cap)
+    dst_o = b.new_dst()
+    ost, owr, _ = oracle.decompress_batch(b.src, b.src_off, b.src_len, dst_o, b.dst_off, b.dst_cap)
+    assert (st == ost).all() and (wr == owr).all() and (dst == dst_o).all()
+
+
+def test_one_bad_stream_does_not_affect_neighbours(ctx, oracle):
+    plain, comp = T.make_stream("dynamic", 30000, 1)
+    streams = [comp, comp[:100], comp, b"\x07", comp]
+    b = T.Batch(streams, [len(plain)] * 5)
+    st, wr, dst = gpu_util.run_device(ctx, b)
+    assert list(st) == [oracle.decompress(s, len(plain))[0] for s in streams]
+    assert st[0] == 0 and st[1] != 0 and st[3] == 2
+    for k in (0, 2, 4):
+        assert b.dst_slice(dst, k).tobytes() == plain
+
+
+def _replicated_batch(unique, copies, dev):
+    """`copies` x the unique streams: repeated src offsets, distinct dst regions (full-size runs
+    without generating hundreds of thousands of unique inputs in the test)."""
+    plains = [u[0] for u in unique]
+    b = T.Batch([u[1] for u in unique], [len(p) for p in plains], dst_align=1)
+    n_u = len(unique)
+    sel = np.tile(np.arange(n_u), copies)
+    src_off = b.src_off[sel]
+    src_len = b.src_len[sel]
+    cap = b.dst_cap[sel]
+    dst_off = np.concatenate([[0], np.cumsum(cap)[:-1]]).astype(np.uint64)
+    total = int(cap.sum())
+    t = lambda a: torch.from_numpy(a.view(np.int64)).to(dev)
+    return (torch.from_numpy(b.src).to(dev), t(src_off), t(src_len), t(dst_off), t(cap), total, sel,
+            [gpu_util.host_checksum(p) for p in plains])
+
+
+@pytest.mark.parametrize("shape", ["C2", "C3", "C4"])
+def test_full_size_checksum_of_checksums(ctx, shape):
+    """BASELINE.json configs at full size; verified through the device-side position-weighted
+    checksum of every output region against the checksum of the known plaintext."""
+    dev = torch.device("cuda", ctx.device)
+    if shape == "C2":    # 65,536 x 64 KiB dynamic level 6
+        unique = [T.make_stream("dynamic", 65536, 100 + i) for i in range(256)]
+        copies = 256
+    elif shape == "C3":  # 1,048,576 x 4 KiB mixed stored/fixed/dynamic
+        unique = [T.make_stream(["stored", "fixed", "dynamic"][i % 3], 4096, 300 + i)
+                  for i in range(1536)]
+        copies = 1048576 // 1536 + 1
+    else:                # 16,384 x 1 MiB level 9 repetitive
+        unique = [T.make_stream("repetitive", 1 << 20, 700 + i) for i in range(32)]
+        copies = 512
+    src, src_off, src_len, dst_off, cap, total, sel, sums = _replicated_batch(unique, copies, dev)
+    n = src_off.numel()
+    dst = torch.zeros(total + 64, dtype=torch.uint8, device=dev)
+    status = torch.full((n,), 0xEE, dtype=torch.uint8, device=dev)
+    written = torch.zeros(n, dtype=torch.int64, device=dev)
+    ctx.decompress_batch_device(src, src_off, src_len, dst, dst_off, cap, status, written)
+    out = torch.zeros(n, dtype=torch.int64, device=dev)
+    ctx.checksum_batch_device(dst, dst_off, written, out)
+    torch.cuda.synchronize(dev)
+    assert int(status.max()) == 0
+    assert torch.equal(written, cap)
+    want = np.array(sums, dtype=np.uint64)[sel]
+    got = out.cpu().numpy().view(np.uint64)
+    assert (got == want).all()
+    # idempotence: a second run over the same dst gives the same bytes
+    ctx.decompress_batch_device(src, src_off, src_len, dst, dst_off, cap, status, written)
+    ctx.checksum_batch_device(dst, dst_off, written, out)
+    torch.cuda.synchronize(dev)
+    assert (out.cpu().numpy().view(np.uint64) == want).all()

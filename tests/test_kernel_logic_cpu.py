@@ -1,0 +1,62 @@
+"""CPU: the CUDA kernel's lane-local logic (starflate_b200/csrc/inflate_lanes.cuh compiled for
+the host by tests/cpu_emu) against the golden fixtures and the oracle.  This is a unit test of
+the decoder state machine, bit reader, LUT builder and write-combining output window in the
+GPU-less container; the real parity tests are the `-m gpu` ones through the C ABI."""
+import numpy as np
+import pytest
+
+from tests import deflate_tools as T
+from tests import emu_bindings
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return emu_bindings.Emu()
+
+
+def _check_family(emu, oracle, golden, name, stride):
+    cases = golden.cases(name, stride)
+    b = T.Batch([c[1] for c in cases], [c[2] for c in cases])   # packed, arbitrary alignments
+    dst = b.new_dst()
+    st, wr = emu.decompress_batch(b, dst)
+    for k, (i, src, cap) in enumerate(cases):
+        want_st, want_wr, want_hash, cls = golden.expected(name, i)
+        assert (int(st[k]), int(wr[k])) == (want_st, want_wr), (name, i, cls)
+        assert "%016x" % oracle.fnv1a64(b.dst_slice(dst, k).tobytes()) == want_hash, (name, i, cls)
+
+
+def test_golden_families(emu, oracle, golden):
+    for name, fam in golden.families.items():
+        _check_family(emu, oracle, golden, name, 11 if len(fam["params"]) > 3000 else 2)
+    s = emu.stats()
+    assert s["tokens"] > 1_000_000 and s["slow_tokens"] < s["tokens"] // 20  # fast path exercised
+
+
+@pytest.mark.parametrize("cfg", [dict(root_lit=8, root_dist=5, pool=128),
+                                 dict(root_lit=10, root_dist=8, pool=512)])
+def test_other_lut_geometries(oracle, golden, cfg):
+    """Small pools force the E_SLOW (pool exhausted) path on valid streams; results must not change."""
+    e = emu_bindings.Emu(**cfg)
+    for name in ("known_answers", "crafted_dynamic_headers", "cut1_multiblock_12000",
+                 "flip_dynamic_4096", "cap_repetitive_70000"):
+        _check_family(e, oracle, golden, name, 3)
+    _check_family(e, oracle, golden, "cut7_starfleet_dynamic", 97)
+
+
+def test_random_batches_vs_oracle(emu, oracle):
+    rng = np.random.default_rng(5)
+    streams, caps = [], []
+    for i in range(120):
+        kind = ["dynamic", "fixed", "stored", "multiblock", "repetitive"][i % 5]
+        plain, comp = T.make_stream(kind, int(rng.integers(1, 9000)), 1000 + i)
+        if i % 7 == 0:
+            comp = comp[: int(rng.integers(0, len(comp)))]
+        caps.append(len(plain) + int(rng.integers(-3, 4)) if i % 3 else len(plain))
+        streams.append(comp)
+    caps = [max(c, 0) for c in caps]
+    b = T.Batch(streams, caps)
+    dst_e, dst_o = b.new_dst(), b.new_dst()
+    st, wr = emu.decompress_batch(b, dst_e)
+    ost, owr, _ = oracle.decompress_batch(b.src, b.src_off, b.src_len, dst_o, b.dst_off, b.dst_cap)
+    assert (st == ost).all() and (wr == owr).all()
+    assert (dst_e == dst_o).all()
