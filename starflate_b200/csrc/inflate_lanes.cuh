@@ -74,18 +74,24 @@ struct Cfg {
   static constexpr int WORK_U16 = 32;               // count[16], next[16] during table build
   static constexpr int LANE_U16 = LUT_U16 + LENS_U16 + WORK_U16;
   static constexpr int WARP_U16 = LANE_U16 * 32;
-  static constexpr int INFO_WORDS = 64;             // shared length / distance info tables
+  static constexpr int INFO_WORDS = 32;             // shared distance info table
   static constexpr int SMEM_BYTES = WARPS * WARP_U16 * 2 + INFO_WORDS * 4;
-  static_assert(POOL_OFF + POOL <= 2048, "sub-table offsets are 11 bits");
+  static_assert(POOL <= 510, "sub-table offsets are 9 bits");
   static_assert(POOL >= 128, "the 128-entry CL LUT (one byte per u16 slot) is overlaid on the pool");
 };
 
-// LUT entry (u16):
-//   0x0000                       no code here
-//   bit15 = 0: bits 0-3 code length (1..15), bits 4-12 symbol
-//   bit15 = 1: bits 0-3 sub-table index bits (1..6), bits 4-14 sub-table offset;
-//              0x8000 (index bits 0) = "not representable, use slow_token()"
-constexpr uint32_t E_SLOW = 0x8000u;
+// LUT entry (u16).  bits 0-3 = code length L (1..15); L == 0 marks a special entry.
+//   L != 0, literal/length table:
+//     bit 15 = 1   length code: bits 4-11 = base - 3, bits 12-14 = number of extra bits
+//     bit 15 = 0   bits 12-14 kind: 0 literal (bits 4-11 = byte), 1 end of block,
+//                  3 symbol 286/287 (rejected by the reference -> slow_token())
+//   L != 0, distance table: bits 4-8 = distance symbol (0..31)
+//   L == 0: 0x0000 no code here; E_SLOW "not representable, use slow_token()";
+//           otherwise a sub-table pointer: bits 4-12 offset from the pool start,
+//           bits 13-15 sub-table index bits (1..7)
+constexpr uint32_t E_SLOW = 0xFFF0u;
+constexpr uint32_t E_KIND_EOB = 0x1000u;
+constexpr uint32_t E_KIND_BAD = 0x3000u;
 
 // RFC 1951 §3.2.5 (reference: src/decompress.cpp:52-84).  info = base | extra << 16
 __constant__ uint32_t c_len_info[32] = {
@@ -125,38 +131,50 @@ struct BitReader {
   int cnt;
   int phantom;
   uint32_t nextw;
-  const uint8_t* p;      // address of nextw's word (4-byte aligned)
-  const uint8_t* begin;  // first byte of the stream
-  const uint8_t* pend;   // one past the last byte
+  uint32_t ip;          // byte offset (from base) of nextw's word; multiple of 4
+  uint32_t iend;        // byte offset (from base) one past the last stream byte
+  uint32_t lead0;       // begin - base (0..3)
+  const uint8_t* base;  // stream start rounded down to 4 bytes
 
-  __device__ __forceinline__ uint32_t fetch(const uint8_t* a, int& ph) const
+  __device__ __forceinline__ const uint8_t* begin() const { return base + lead0; }
+
+  // general fetch (any position); the hot loop inlines the in-range case in refill()
+  __device__ __forceinline__ uint32_t fetch(uint32_t at, int& ph) const
   {
-    if (a + 4 <= pend) {
+    if (at + 4 <= iend) {
       ph = 0;
-      return *reinterpret_cast<const uint32_t*>(a);
+      return *reinterpret_cast<const uint32_t*>(base + at);
     }
-    if (a < pend) {
-      const unsigned k = static_cast<unsigned>(pend - a);  // 1..3 valid bytes
+    if (at < iend) {
+      const unsigned k = iend - at;  // 1..3 valid bytes
       ph = 32 - 8 * static_cast<int>(k);
-      return *reinterpret_cast<const uint32_t*>(a) & ((1u << (8 * k)) - 1u);
+      return *reinterpret_cast<const uint32_t*>(base + at) & ((1u << (8 * k)) - 1u);
     }
     ph = 32;
     return 0;
   }
 
-  // start reading at byte `at` (begin <= at <= pend), skipping `skip_bits` (0..7) more bits
-  __device__ void init_at(const uint8_t* at, unsigned skip_bits)
+  __device__ void open(const uint8_t* begin_, uint32_t len)
   {
-    const unsigned lead = static_cast<unsigned>(reinterpret_cast<uintptr_t>(at) & 3u);
-    const uint8_t* a0 = at - lead;
+    lead0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(begin_) & 3u);
+    base = begin_ - lead0;
+    iend = lead0 + len;
+    init_at(lead0, 0);
+  }
+
+  // start reading at byte offset `at` from base (lead0 <= at <= iend), then skip 0..7 bits
+  __device__ void init_at(uint32_t at, unsigned skip_bits)
+  {
+    const uint32_t lead = at & 3u;
+    const uint32_t a0 = at - lead;
     int ph0 = 32, ph1 = 32;
     uint32_t w0 = 0;
-    if (at < pend) w0 = fetch(a0, ph0);
+    if (at < iend) w0 = fetch(a0, ph0);
     buf = static_cast<uint64_t>(w0 >> (8 * lead));
     cnt = 32 - 8 * static_cast<int>(lead);
     if (ph0 > cnt) ph0 = cnt;  // stream shorter than the rest of this word
-    p = a0 + 4;
-    nextw = fetch(p, ph1);
+    ip = a0 + 4;
+    nextw = fetch(ip, ph1);
     phantom = ph0 + ph1;
     refill();
     buf >>= skip_bits;
@@ -168,32 +186,36 @@ struct BitReader {
     if (cnt <= 32) {
       buf |= static_cast<uint64_t>(nextw) << cnt;
       cnt += 32;
-      p += 4;
-      int ph;
-      nextw = fetch(p, ph);
-      phantom += ph;
+      ip += 4;
+      if (ip + 4 <= iend) {
+        nextw = *reinterpret_cast<const uint32_t*>(base + ip);
+      } else {
+        int ph;
+        nextw = fetch(ip, ph);
+        phantom += ph;
+      }
     }
   }
-  __device__ __forceinline__ void drop(int n)
+  __device__ __forceinline__ void drop(uint32_t n)
   {
     buf >>= n;
-    cnt -= n;
+    cnt -= static_cast<int>(n);
   }
   __device__ __forceinline__ uint32_t peek32() const { return static_cast<uint32_t>(buf); }
   // real bits among the fetched, unconsumed ones (negative after an overrun)
   __device__ __forceinline__ int real_left() const { return cnt + 32 - phantom; }
-  // absolute bit position of the next unread bit, relative to `begin`
+  // absolute bit position of the next unread bit, relative to the stream start
   __device__ __forceinline__ uint64_t bitpos() const
   {
-    return 8ull * static_cast<uint64_t>(p - begin) - static_cast<uint64_t>(cnt);
+    return 8ull * static_cast<uint64_t>(ip - lead0) - static_cast<uint64_t>(cnt);
   }
   __device__ __forceinline__ uint64_t total_bits() const
   {
-    return 8ull * static_cast<uint64_t>(pend - begin);
+    return 8ull * static_cast<uint64_t>(iend - lead0);
   }
   __device__ void seek_bit(uint64_t bit)
   {
-    init_at(begin + (bit >> 3), static_cast<unsigned>(bit & 7));
+    init_at(lead0 + static_cast<uint32_t>(bit >> 3), static_cast<unsigned>(bit & 7));
   }
 };
 
@@ -346,7 +368,19 @@ __device__ __noinline__ SlowToken slow_token(const LaneMem& m, int n_lit, int n_
 // huffman::table::canonicalize (huffman/src/table.hpp:177-216).  Length sets the reference
 // accepts but a prefix LUT cannot represent exactly (over-subscribed: some code value reaches
 // 2^len, "shortest code wins") get E_SLOW in every root slot.
-template <int ROOT>
+// LITLEN selects the entry payload (see the entry format above).
+template <bool LITLEN>
+__device__ __forceinline__ uint16_t make_entry(uint32_t s, uint32_t L)
+{
+  if (!LITLEN) return static_cast<uint16_t>((s << 4) | L);
+  if (s < 256) return static_cast<uint16_t>((s << 4) | L);
+  if (s == 256) return static_cast<uint16_t>(E_KIND_EOB | L);
+  if (s > 285) return static_cast<uint16_t>(E_KIND_BAD | L);
+  const uint32_t info = c_len_info[s - 257];
+  return static_cast<uint16_t>(0x8000u | ((info >> 16) << 12) | (((info & 0xffffu) - 3u) << 4) | L);
+}
+
+template <int ROOT, bool LITLEN, int POOL_OFF>
 __device__ void build_lut(const LaneMem& m, int s0, int n, int root_off, int pool_end,
                           int& pool_at)
 {
@@ -378,7 +412,7 @@ __device__ void build_lut(const LaneMem& m, int s0, int n, int root_off, int poo
   }
 #pragma unroll 1
   for (int j = 0; j < (1 << ROOT); ++j) lut[(root_off + j) * 32] = 0;
-  // pass A: direct entries; long codes leave (0x8000 | max length) in their root slot
+  // pass A: direct entries; long codes leave (0xF000 | max length) in their root slot
   uint32_t pmin = 1u << ROOT, pmax = 0;
 #pragma unroll 1
   for (int s = 0; s < n; ++s) {
@@ -386,14 +420,14 @@ __device__ void build_lut(const LaneMem& m, int s0, int n, int root_off, int poo
     if (!L) continue;
     const uint32_t code = next[L * 32]++;
     if (L <= static_cast<uint32_t>(ROOT)) {
-      const uint16_t e = static_cast<uint16_t>((static_cast<uint32_t>(s) << 4) | L);
+      const uint16_t e = make_entry<LITLEN>(static_cast<uint32_t>(s), L);
       for (uint32_t j = bitrev(code, static_cast<int>(L)); j < (1u << ROOT); j += 1u << L)
         lut[(root_off + j) * 32] = e;
     } else {
       const uint32_t pfx = code >> (L - ROOT);
       uint16_t& slot = lut[(root_off + bitrev(pfx, ROOT)) * 32];
       const uint32_t prev = slot & 15u;
-      slot = static_cast<uint16_t>(0x8000u | (L > prev ? L : prev));
+      slot = static_cast<uint16_t>(0xF000u | (L > prev ? L : prev));
       pmin = pfx < pmin ? pfx : pmin;
       pmax = pfx > pmax ? pfx : pmax;
     }
@@ -404,11 +438,12 @@ __device__ void build_lut(const LaneMem& m, int s0, int n, int root_off, int poo
   for (uint32_t pfx = pmin; pfx <= pmax; ++pfx) {
     uint16_t& slot = lut[(root_off + bitrev(pfx, ROOT)) * 32];
     const uint32_t e = slot;
-    if (!(e & 0x8000u)) continue;
+    if ((e & 0xF000u) != 0xF000u) continue;
     const int sb = static_cast<int>(e & 15u) - ROOT;
     const int size = 1 << sb;
-    if (pool_at + size <= pool_end) {
-      slot = static_cast<uint16_t>(0x8000u | (static_cast<uint32_t>(pool_at) << 4) | static_cast<uint32_t>(sb));
+    if (sb <= 7 && pool_at + size <= pool_end) {
+      slot = static_cast<uint16_t>((static_cast<uint32_t>(sb) << 13) |
+                                   (static_cast<uint32_t>(pool_at - POOL_OFF) << 4));
       for (int j = 0; j < size; ++j) lut[(pool_at + j) * 32] = 0;
       pool_at += size;
     } else {
@@ -432,23 +467,23 @@ __device__ void build_lut(const LaneMem& m, int s0, int n, int root_off, int poo
     const uint32_t rest = L - ROOT;
     const uint32_t e = lut[(root_off + bitrev(code >> rest, ROOT)) * 32];
     if (e == E_SLOW) continue;
-    const uint32_t sb = e & 15u;
-    const uint32_t off = (e >> 4) & 0x7ffu;
-    const uint16_t v = static_cast<uint16_t>((static_cast<uint32_t>(s) << 4) | L);
+    const uint32_t sb = e >> 13;
+    const uint32_t off = POOL_OFF + ((e >> 4) & 0x1ffu);
+    const uint16_t v = make_entry<LITLEN>(static_cast<uint32_t>(s), L);
     for (uint32_t j = bitrev(code & ((1u << rest) - 1u), static_cast<int>(rest)); j < (1u << sb);
          j += 1u << rest)
       lut[(off + j) * 32] = v;
   }
 }
 
-// LUT lookup.  Returns the raw entry (0 = no code, E_SLOW = ask slow_token()).
-template <int ROOT>
+// LUT lookup.  Returns a direct entry (L != 0), 0 (no code) or E_SLOW (ask slow_token()).
+template <int ROOT, int POOL_OFF>
 __device__ __forceinline__ uint32_t lut_lookup(const uint16_t* lut, int root_off, uint32_t bits)
 {
   uint32_t e = lut[(root_off + static_cast<int>(bits & ((1u << ROOT) - 1u))) * 32];
-  if (e > E_SLOW) {
-    const uint32_t sb = e & 15u;
-    const uint32_t off = (e >> 4) & 0x7ffu;
+  if ((e & 15u) == 0 && e != 0 && e != E_SLOW) {  // sub-table pointer (codes longer than ROOT)
+    const uint32_t sb = e >> 13;
+    const uint32_t off = POOL_OFF + ((e >> 4) & 0x1ffu);
     e = lut[(off + ((bits >> ROOT) & ((1u << sb) - 1u))) * 32];
   }
   return e;
@@ -456,38 +491,42 @@ __device__ __forceinline__ uint32_t lut_lookup(const uint16_t* lut, int root_off
 
 // ---------------------------------------------------------------------------------------------
 // Per-lane output window: 8-byte write combining over the stream's dst region.
+// Invariant: bytes [vpos & ~7, vpos) of the output live in the low bytes of `obuf` (its
+// higher bytes are unspecified); everything below vpos & ~7 is in memory.
 struct OutWin {
   uint8_t* al;      // 8-byte aligned address of virtual position 0
   uint32_t lead;    // dst start within the first word (0..7): virtual position of byte 0
   uint32_t vpos;    // virtual position of the next byte to produce
   uint32_t vend;    // virtual position one past the capacity
-  uint64_t obuf;    // bytes [vpos & ~7, vpos) not yet in memory
+  uint64_t obuf;
 
   __device__ __forceinline__ uint32_t written() const { return vpos - lead; }
   __device__ __forceinline__ uint32_t room() const { return vend - vpos; }
 
-  // word of the output at 8-aligned virtual position wv (wv <= vpos & ~7)
+  // word of the output at 8-aligned virtual position wv (general case, may be the open word)
   __device__ __forceinline__ uint64_t word_at(uint32_t wv) const
   {
     const uint32_t cur = vpos & ~7u;
-    if (wv == cur) return obuf;
     if (wv < cur) return *reinterpret_cast<const uint64_t*>(al + wv);
-    return 0;
+    return wv == cur ? obuf : 0;
   }
 
-  // append n (1..8) bytes, `chunk` zero above byte n
+  // append n (1..8) bytes from the low bytes of `chunk` (bytes above n are ignored)
   __device__ __forceinline__ void append(uint64_t chunk, uint32_t n)
   {
     const uint32_t k = vpos & 7u;
-    obuf |= chunk << (8 * k);
+    const uint32_t sh = 8 * k;
+    const uint64_t merged = (obuf & ((1ull << sh) - 1ull)) | (chunk << sh);
     if (k + n >= 8) {
       const uint32_t wv = vpos & ~7u;
       if (wv >= lead) {
-        *reinterpret_cast<uint64_t*>(al + wv) = obuf;
+        *reinterpret_cast<uint64_t*>(al + wv) = merged;
       } else {  // first word of an unaligned dst: bytes before `lead` are not ours
-        for (uint32_t b = lead; b < 8; ++b) al[b] = static_cast<uint8_t>(obuf >> (8 * b));
+        for (uint32_t b = lead; b < 8; ++b) al[b] = static_cast<uint8_t>(merged >> (8 * b));
       }
-      obuf = shr64(chunk, 8 * (8 - k));
+      obuf = chunk >> ((64 - sh) & 63);  // k == 0: no byte is carried over, any value will do
+    } else {
+      obuf = merged;
     }
     vpos += n;
   }
@@ -554,7 +593,7 @@ __device__ int parse_block_header(BitReader& br, const LaneMem& m, OutWin& ow, b
       *status = ST_DST_TOO_SMALL;
       return S_DONE;
     }
-    copy_src = br.begin + (pos >> 3);
+    copy_src = br.begin() + (pos >> 3);
     copy_left = len;
     if (len == 0) {
       if (final_block) {
@@ -692,12 +731,23 @@ __device__ int parse_block_header(BitReader& br, const LaneMem& m, OutWin& ow, b
     }
   }
   int pool_at = C::POOL_OFF;
-  build_lut<C::ROOT_LIT>(m, 0, n_lit, C::LIT_OFF, C::POOL_OFF + C::POOL, pool_at);
-  build_lut<C::ROOT_DIST>(m, n_lit, n_dist, C::DIST_OFF, C::POOL_OFF + C::POOL, pool_at);
+  build_lut<C::ROOT_LIT, true, C::POOL_OFF>(m, 0, n_lit, C::LIT_OFF, C::POOL_OFF + C::POOL, pool_at);
+  build_lut<C::ROOT_DIST, false, C::POOL_OFF>(m, n_lit, n_dist, C::DIST_OFF, C::POOL_OFF + C::POOL,
+                                              pool_at);
   return S_DECODE;
 }
 
 // ---------------------------------------------------------------------------------------------
+// The batch kernel.  One lane per stream, 32 streams per warp, warps pull groups of 32
+// consecutive streams from a global counter.
+//
+// Control structure (kept free of `break`s so that the warp reconverges after every stage):
+//   rounds:  lanes that need a block header parse it (lock-step when several do), then
+//   tokens:  while any lane is inside a block, every iteration runs three converged stages
+//              1. decode   lanes in S_DECODE decode one token (literal | end of block | match)
+//              2. source   lanes in S_MATCH / S_STORED fetch <= 8 source bytes
+//              3. append   lanes with bytes merge them into their write-combining word
+//            lanes waiting for the next header (or finished) idle until the round ends.
 template <class C>
 __global__ void __launch_bounds__(C::WARPS * 32)
 inflate_lanes_kernel(const BatchArgs a)
@@ -707,14 +757,11 @@ inflate_lanes_kernel(const BatchArgs a)
 #else
   extern __shared__ __align__(16) uint16_t smem[];
 #endif
+  constexpr unsigned FULL = 0xffffffffu;
   const int lane = static_cast<int>(threadIdx.x & 31u);
   const int warp = static_cast<int>(threadIdx.x >> 5);
-  uint32_t* const s_len_info = reinterpret_cast<uint32_t*>(smem + C::WARPS * C::WARP_U16);
-  uint32_t* const s_dist_info = s_len_info + 32;
-  for (unsigned t = threadIdx.x; t < 32; t += blockDim.x) {
-    s_len_info[t] = c_len_info[t];
-    s_dist_info[t] = c_dist_info[t];
-  }
+  uint32_t* const s_dist_info = reinterpret_cast<uint32_t*>(smem + C::WARPS * C::WARP_U16);
+  for (unsigned t = threadIdx.x; t < 32; t += blockDim.x) s_dist_info[t] = c_dist_info[t];
   __syncthreads();
 
   LaneMem m;
@@ -727,7 +774,7 @@ inflate_lanes_kernel(const BatchArgs a)
   for (;;) {
     unsigned long long g = 0;
     if (lane == 0) g = atomicAdd(a.group_counter, 1ull);
-    g = __shfl_sync(0xffffffffu, g, 0);
+    g = __shfl_sync(FULL, g, 0);
     if (g >= n_groups) break;
     const uint64_t idx = g * 32 + static_cast<uint64_t>(lane);
 
@@ -749,9 +796,7 @@ inflate_lanes_kernel(const BatchArgs a)
         if (a.written) a.written[idx] = 0;
         live = false;
       } else {
-        br.begin = a.src_base + a.src_off[idx];
-        br.pend = br.begin + slen;
-        br.init_at(br.begin, 0);
+        br.open(a.src_base + a.src_off[idx], static_cast<uint32_t>(slen));
         uint8_t* d = a.dst_base + a.dst_off[idx];
         ow.lead = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(d) & 7u);
         ow.al = d - ow.lead;
@@ -762,117 +807,119 @@ inflate_lanes_kernel(const BatchArgs a)
       }
     }
 
-    while (__any_sync(0xffffffffu, state != S_DONE)) {
+    while (__any_sync(FULL, state != S_DONE)) {
       if (state == S_HEADER) {
         state = parse_block_header<C>(br, m, ow, final_block, n_lit, n_dist, copy_src, copy_left,
                                       &status);
       }
-      // ---- token / copy iterations ---------------------------------------------------------
-      while (state <= S_STORED) {
+      // ---- token / copy iterations (all 32 lanes stay in this loop together) ----------------
+      while (__any_sync(FULL, state <= S_STORED)) {
         uint64_t chunk = 0;
         uint32_t n = 0;
+        // ---- stage 1: decode one token ------------------------------------------------------
         if (state == S_DECODE) {
           br.refill();
           SFB_STAT(tokens);
-          const uint64_t tok_pos = br.bitpos();
-          bool slow = false;
-          int kind = 0;  // 0 literal, 1 end of block, 2 match
+          const uint32_t ip0 = br.ip;   // token start = 8*(ip0 - lead0) - cnt0 (slow path only)
+          const int cnt0 = br.cnt;
+          bool slow = false, is_match = false, eob = false;
           uint32_t value = 0, dist = 0;
-          uint32_t e = lut_lookup<C::ROOT_LIT>(lut, C::LIT_OFF, br.peek32());
+          uint32_t e = lut_lookup<C::ROOT_LIT, C::POOL_OFF>(lut, C::LIT_OFF, br.peek32());
           uint32_t L = e & 15u;
-          if (e >= E_SLOW || L == 0) {
-            slow = true;
-          } else {
-            br.drop(static_cast<int>(L));
-            const uint32_t sym = e >> 4;
-            if (sym < 256) {
-              value = sym;
-            } else if (sym == 256) {
-              kind = 1;
-            } else if (sym > 285) {
-              slow = true;
-            } else {
-              kind = 2;
-              const uint32_t info = s_len_info[sym - 257];
-              const uint32_t xb = info >> 16;
-              value = (info & 0xffffu) + (br.peek32() & ((1u << xb) - 1u));
-              br.drop(static_cast<int>(xb));
-              br.refill();
-              e = lut_lookup<C::ROOT_DIST>(lut, C::DIST_OFF, br.peek32());
-              L = e & 15u;
-              const uint32_t dsym = e >> 4;
-              if (e >= E_SLOW || L == 0 || dsym >= 30) {
-                slow = true;
-              } else {
-                br.drop(static_cast<int>(L));
+          slow = (L == 0);
+          br.drop(L);
+          if (e & 0xF000u) {            // not a literal: end of block, length code, or oddity
+            if (e & 0x8000u) {
+              if (L) {
+                is_match = true;
+                const uint32_t xb = (e >> 12) & 7u;
+                value = 3u + ((e >> 4) & 0xffu) + (br.peek32() & ((1u << xb) - 1u));
+                br.drop(xb);
+                br.refill();
+                const uint32_t de = lut_lookup<C::ROOT_DIST, C::POOL_OFF>(lut, C::DIST_OFF, br.peek32());
+                const uint32_t dL = de & 15u;
+                const uint32_t dsym = (de >> 4) & 31u;
+                slow = (dL == 0) | (dsym >= 30u);
+                br.drop(dL);
                 const uint32_t dinfo = s_dist_info[dsym];
                 const uint32_t dxb = dinfo >> 16;
                 dist = (dinfo & 0xffffu) + (br.peek32() & ((1u << dxb) - 1u));
-                br.drop(static_cast<int>(dxb));
+                br.drop(dxb);
               }
+            } else if ((e & 0xF000u) == E_KIND_EOB) {
+              eob = true;
+            } else {
+              slow = true;              // symbols 286 / 287
             }
+          } else {
+            value = (e >> 4) & 0xffu;
           }
-          if (slow || br.real_left() < 0) {
+          if (slow | (br.real_left() < 0)) {
             // anything the fast path cannot vouch for: redo this token exactly
             SFB_STAT(slow_tokens);
-            const SlowToken t = slow_token(m, n_lit, n_dist, br.begin, tok_pos, br.total_bits());
+            const uint64_t tok_pos = 8ull * static_cast<uint64_t>(ip0 - br.lead0) - static_cast<uint64_t>(cnt0);
+            const SlowToken t = slow_token(m, n_lit, n_dist, br.begin(), tok_pos, br.total_bits());
             if (t.status != ST_SUCCESS) {
               status = t.status;
               state = S_DONE;
-              break;
+            } else {
+              is_match = t.kind == 2;
+              eob = t.kind == 1;
+              value = static_cast<uint32_t>(t.value);
+              dist = static_cast<uint32_t>(t.dist);
+              br.seek_bit(t.next);
             }
-            kind = t.kind;
-            value = static_cast<uint32_t>(t.value);
-            dist = static_cast<uint32_t>(t.dist);
-            br.seek_bit(t.next);
           }
-          if (kind == 0) {
-            if (ow.room() < 1) {  // decompress_literal, src/decompress.cpp:150-152
-              status = ST_DST_TOO_SMALL;
-              state = S_DONE;
-              break;
-            }
-            chunk = value;
-            n = 1;
-          } else if (kind == 1) {
-            if (final_block) {
+          if (state == S_DECODE) {
+            if (eob) {
               status = ST_SUCCESS;
+              state = final_block ? S_DONE : S_HEADER;
+            } else if (is_match) {
+              if (dist > ow.written()) {          // src/decompress.cpp:178-180
+                status = ST_INVALID_DISTANCE;
+                state = S_DONE;
+              } else if (ow.room() < value) {     // :181-183 (no partial copy)
+                status = ST_DST_TOO_SMALL;
+                state = S_DONE;
+              } else {
+                mlen = value;
+                mdist = dist;
+                state = S_MATCH;
+              }
+            } else if (ow.room() < 1) {           // decompress_literal, :150-152
+              status = ST_DST_TOO_SMALL;
               state = S_DONE;
             } else {
-              state = S_HEADER;
+              chunk = value;
+              n = 1;
             }
-            break;
-          } else {
-            if (dist > ow.written()) {  // src/decompress.cpp:178-180
-              status = ST_INVALID_DISTANCE;
-              state = S_DONE;
-              break;
-            }
-            if (ow.room() < value) {  // :181-183 (no partial copy)
-              status = ST_DST_TOO_SMALL;
-              state = S_DONE;
-              break;
-            }
-            mlen = value;
-            mdist = dist;
-            state = S_MATCH;
           }
         }
+        __syncwarp();
+        // ---- stage 2: up to 8 source bytes for lanes that are copying ------------------------
         if (state == S_MATCH) {
           // copy_from_before (src/decompress.cpp:388-398), <= 8 bytes per iteration
           const uint32_t vs = ow.vpos - mdist;
           const uint32_t wv = vs & ~7u;
           const uint32_t sh = 8 * (vs & 7u);
-          uint64_t s8 = ow.word_at(wv) >> sh;
-          if (sh) s8 |= ow.word_at(wv + 8) << (64 - sh);
-          if (mdist < 8) {  // overlapping: replicate the mdist-byte period
-            s8 &= low_bytes_mask(mdist);
-            s8 |= shl64(s8, 8 * mdist);
-            s8 |= shl64(s8, 16 * mdist);
-            s8 |= shl64(s8, 32 * mdist);
+          uint64_t s8;
+          if (mdist >= 15) {
+            // both source words are already in memory (strictly below the open word)
+            const uint64_t w0 = *reinterpret_cast<const uint64_t*>(ow.al + wv);
+            const uint64_t w1 = *reinterpret_cast<const uint64_t*>(ow.al + wv + 8);
+            s8 = (w0 >> sh) | ((w1 << 1) << (63 - sh));
+          } else {
+            s8 = ow.word_at(wv) >> sh;
+            if (sh) s8 |= ow.word_at(wv + 8) << (64 - sh);
+            if (mdist < 8) {  // overlapping: replicate the mdist-byte period
+              s8 &= low_bytes_mask(mdist);
+              s8 |= shl64(s8, 8 * mdist);
+              s8 |= shl64(s8, 16 * mdist);
+              s8 |= shl64(s8, 32 * mdist);
+            }
           }
           n = mlen < 8 ? mlen : 8;
-          chunk = s8 & low_bytes_mask(n);
+          chunk = s8;
           mlen -= n;
           if (mlen == 0) state = S_DECODE;
         } else if (state == S_STORED) {
@@ -882,19 +929,17 @@ inflate_lanes_kernel(const BatchArgs a)
           uint64_t s8 = *reinterpret_cast<const uint64_t*>(wa) >> (8 * k);
           n = copy_left < 8 ? copy_left : 8;
           if (k && n > 8 - k) s8 |= *reinterpret_cast<const uint64_t*>(wa + 8) << (64 - 8 * k);
-          chunk = s8 & low_bytes_mask(n);
+          chunk = s8;
           copy_src += n;
           copy_left -= n;
           if (copy_left == 0) {
-            br.init_at(copy_src, 0);
-            if (final_block) {
-              status = ST_SUCCESS;
-              state = S_DONE;
-            } else {
-              state = S_HEADER;
-            }
+            br.init_at(static_cast<uint32_t>(copy_src - br.base), 0);
+            status = ST_SUCCESS;
+            state = final_block ? S_DONE : S_HEADER;
           }
         }
+        __syncwarp();
+        // ---- stage 3: merge into the write-combining word ------------------------------------
         if (n) ow.append(chunk, n);
       }
       if (state == S_DONE && live) {

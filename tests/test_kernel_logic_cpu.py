@@ -33,7 +33,7 @@ def test_golden_families(emu, oracle, golden):
 
 
 @pytest.mark.parametrize("cfg", [dict(root_lit=8, root_dist=5, pool=128),
-                                 dict(root_lit=10, root_dist=8, pool=512)])
+                                 dict(root_lit=10, root_dist=8, pool=448)])
 def test_other_lut_geometries(oracle, golden, cfg):
     """Small pools force the E_SLOW (pool exhausted) path on valid streams; results must not change."""
     e = emu_bindings.Emu(**cfg)
