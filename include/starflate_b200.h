@@ -68,7 +68,7 @@ int sfb200_abi_version(void);
  * Replaces one reference call per stream: decompress(src_i, dst_i) (src/decompress.cpp:402).
  * Semantics preserved per stream: first error wins, bytes already produced stay in dst,
  * dst beyond `written` is never touched, trailing src bytes after the final block are ignored.
- * Precondition: src_len[i], dst_cap[i] < 2^32 - 16 (else status[i] = SFB200_ERROR).
+ * Precondition: src_len[i], dst_cap[i] < 2^32 - 256 (else status[i] = SFB200_ERROR).
  * `cuda_stream` is a cudaStream_t (NULL = default stream); the call is asynchronous. */
 int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
                                    const uint64_t* src_off, const uint64_t* src_len,

@@ -11,7 +11,13 @@
 
 namespace {
 
-using LaneCfg = sfb::Cfg</*ROOT_LIT=*/9, /*ROOT_DIST=*/6, /*POOL=*/192, /*WARPS=*/1>;
+#ifndef SFB_ROOT_LIT
+#define SFB_ROOT_LIT 8
+#define SFB_ROOT_DIST 6
+#define SFB_POOL 128
+#define SFB_WARPS 4
+#endif
+using LaneCfg = sfb::Cfg<SFB_ROOT_LIT, SFB_ROOT_DIST, SFB_POOL, SFB_WARPS>;
 
 }  // namespace
 
@@ -21,6 +27,7 @@ struct sfb200_ctx {
   int ctas_per_sm = 0;
   int regs_per_thread = 0;
   unsigned long long* d_counter = nullptr;
+  uint32_t* d_lens = nullptr;  // per-resident-lane code-length scratch
   uint64_t launches = 0;
   std::string err;
   // staging for the host-buffer entry points (grown on demand)
@@ -102,6 +109,12 @@ int sfb200_create(int device, sfb200_ctx** out)
   if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_counter), sizeof(unsigned long long)) !=
       cudaSuccess)
     return bail(SFB200_RC_OUT_OF_MEMORY);
+  const size_t lens_bytes = static_cast<size_t>(ctx->sm_count) * static_cast<size_t>(per_sm) *
+                            LaneCfg::WARPS * sfb::SCRATCH_WORDS * 32 * sizeof(uint32_t);
+  if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_lens), lens_bytes) != cudaSuccess) {
+    cudaFree(ctx->d_counter);
+    return bail(SFB200_RC_OUT_OF_MEMORY);
+  }
   *out = ctx;
   return SFB200_RC_OK;
 }
@@ -111,6 +124,7 @@ void sfb200_destroy(sfb200_ctx* ctx)
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaFree(ctx->d_counter);
+  cudaFree(ctx->d_lens);
   cudaFree(ctx->d_src);
   cudaFree(ctx->d_dst);
   cudaFree(ctx->d_meta);
@@ -154,6 +168,7 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
   a.written = written;
   a.n = n;
   a.group_counter = ctx->d_counter;
+  a.lens_scratch = ctx->d_lens;
   const uint64_t groups = (n + 31) / 32;
   const uint64_t want = (groups + LaneCfg::WARPS - 1) / LaneCfg::WARPS;
   const uint64_t resident = static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->ctas_per_sm);

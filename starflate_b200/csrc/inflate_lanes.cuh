@@ -9,12 +9,15 @@
 // Why a lane and not a warp per stream: Huffman decode of one stream is a serial dependency
 // chain.  A warp per stream spends one issue slot per instruction on ONE token; a lane per
 // stream retires up to 32 tokens per issued instruction.  Each lane owns
-//   * a register bit buffer (64-bit window + one prefetched 32-bit word),
+//   * a register bit window (two 32-bit words + one prefetched word, funnel-shift peeks),
 //   * a two-level decode LUT in shared memory, interleaved so that element j of lane l sits at
 //     u16 index j*32+l (lane pairs share a bank: at most 2-way conflicts on random lookups),
 //   * an 8-byte write-combining register for its output window in HBM.
 // The token loop is a small state machine (decode | match-copy | stored-copy) so that lanes
 // stay converged: every iteration each lane either decodes one token or moves <= 8 bytes.
+// The code lengths of the current block live in a per-lane slice of a global scratch buffer
+// (written once per block, read sequentially by the table builder and the slow path), which
+// keeps the shared-memory footprint at the LUT alone: 896 B per lane -> 8 warps per SM.
 //
 // Exactness: the fast path only handles tokens that decode cleanly with input to spare.
 // Anything unusual (code not in the LUT, LUT pool overflow marker, over-subscribed code set,
@@ -45,6 +48,13 @@ enum : uint8_t {
   ST_INVALID_DISTANCE = 7,
 };
 
+// Per-lane slice of the global scratch (u32 words; word j of lane l at g[j*32 + l]):
+constexpr int LENS_WORDS = 40;      // [0,40)    320 code lengths as nibbles
+constexpr int SCR_FIRST = 40;       // [40,72)   first code per length: lit/len [40,56), distance [56,72)
+constexpr int SCR_COUNT = 72;       // [72,104)  count | offset << 16 per length (same split)
+constexpr int SCR_SORTED = 104;     // [104,264) symbols in canonical order as u16: lit/len 0..287, distance 288..319
+constexpr int SCRATCH_WORDS = 264;
+
 struct BatchArgs {
   const uint8_t* src_base;
   const uint64_t* src_off;
@@ -56,6 +66,7 @@ struct BatchArgs {
   uint64_t* written;  // may be null
   uint64_t n;
   unsigned long long* group_counter;  // dynamic work distribution (zeroed before launch)
+  uint32_t* lens_scratch;             // gridDim.x * WARPS * SCRATCH_WORDS * 32 words
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -69,15 +80,12 @@ struct Cfg {
   static constexpr int LIT_OFF = 0;
   static constexpr int DIST_OFF = 1 << ROOT_LIT;
   static constexpr int POOL_OFF = DIST_OFF + (1 << ROOT_DIST);
-  static constexpr int LUT_U16 = POOL_OFF + POOL;   // decode LUT entries per lane
-  static constexpr int LENS_U16 = 80;               // 320 code lengths as nibbles
-  static constexpr int WORK_U16 = 32;               // count[16], next[16] during table build
-  static constexpr int LANE_U16 = LUT_U16 + LENS_U16 + WORK_U16;
+  static constexpr int LANE_U16 = POOL_OFF + POOL;  // decode LUT entries per lane
   static constexpr int WARP_U16 = LANE_U16 * 32;
   static constexpr int INFO_WORDS = 32;             // shared distance info table
   static constexpr int SMEM_BYTES = WARPS * WARP_U16 * 2 + INFO_WORDS * 4;
   static_assert(POOL <= 510, "sub-table offsets are 9 bits");
-  static_assert(POOL >= 128, "the 128-entry CL LUT (one byte per u16 slot) is overlaid on the pool");
+  static_assert(POOL >= 64, "the 128-entry CL LUT (one byte each) is overlaid on the pool");
 };
 
 // LUT entry (u16).  bits 0-3 = code length L (1..15); L == 0 marks a special entry.
@@ -114,47 +122,58 @@ __constant__ uint32_t c_dist_info[32] = {
 __constant__ uint8_t c_cl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
 __device__ __forceinline__ uint64_t shl64(uint64_t x, unsigned s) { return s >= 64 ? 0 : x << s; }
-__device__ __forceinline__ uint64_t shr64(uint64_t x, unsigned s) { return s >= 64 ? 0 : x >> s; }
 __device__ __forceinline__ uint64_t low_bytes_mask(unsigned n)  // n in 0..8
 {
   return n >= 8 ? ~0ull : ((1ull << (8 * n)) - 1);
 }
 __device__ __forceinline__ uint32_t bitrev(uint32_t v, int n) { return __brev(v) >> (32 - n); }
+// bits [s, s+32) of the 64-bit value hi:lo, 0 <= s < 32
+__device__ __forceinline__ uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s)
+{
+#ifdef SFB_CPU_EMU
+  return static_cast<uint32_t>(((static_cast<uint64_t>(hi) << 32) | lo) >> (s & 31u));
+#else
+  return __funnelshift_r(lo, hi, s);
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------
 // Bit reader (replaces huffman::bit_span, huffman/src/bit_span.hpp).  Bits are consumed LSB
-// first.  `buf` holds `cnt` bits, `nextw` is the already-fetched following word.  Words past
-// the end of the stream are fetched as zeros and counted in `phantom`, so the window always
-// looks full; real_left() tells how many fetched-but-unconsumed bits are real.
+// first.  w0:w1 is a 64-bit window over the stream, w2 the already-fetched following word,
+// `bo` the offset of the next unread bit inside w0 (kept < 32 by norm()).  Words at or past
+// the end of the stream are fetched as zeros and raise `tail`; while `tail` is clear no
+// consumer can have run past the end, so the hot loop only checks overrun() in tail mode.
+// word at byte offset `at` when it is not entirely inside the stream (rare): zero-filled
+__device__ __noinline__ uint32_t fetch_tail_word(const uint8_t* base, uint32_t at, uint32_t iend)
+{
+  if (at < iend) {
+    const unsigned k = iend - at;  // 1..3 valid bytes
+    return *reinterpret_cast<const uint32_t*>(base + at) & ((1u << (8 * k)) - 1u);
+  }
+  return 0;
+}
+
 struct BitReader {
-  uint64_t buf;
-  int cnt;
-  int phantom;
-  uint32_t nextw;
-  uint32_t ip;          // byte offset (from base) of nextw's word; multiple of 4
+  uint32_t w0, w1, w2;
+  uint32_t bo;
+  uint32_t ip;          // byte offset (from base) of the next word to fetch (w2 sits at ip-4)
+  uint32_t tail;        // some fetched word was not entirely inside the stream
   uint32_t iend;        // byte offset (from base) one past the last stream byte
-  uint32_t lead0;       // begin - base (0..3)
+  uint32_t lead0;       // stream start - base (0..3)
   const uint8_t* base;  // stream start rounded down to 4 bytes
 
   __device__ __forceinline__ const uint8_t* begin() const { return base + lead0; }
 
-  // general fetch (any position); the hot loop inlines the in-range case in refill()
-  __device__ __forceinline__ uint32_t fetch(uint32_t at, int& ph) const
+  // (fetches near / past the end of the stream go through the free function fetch_tail_word:
+  //  a non-inlined *member* would force this struct out of registers into local memory)
+  __device__ __forceinline__ uint32_t fetch(uint32_t at)
   {
-    if (at + 4 <= iend) {
-      ph = 0;
-      return *reinterpret_cast<const uint32_t*>(base + at);
-    }
-    if (at < iend) {
-      const unsigned k = iend - at;  // 1..3 valid bytes
-      ph = 32 - 8 * static_cast<int>(k);
-      return *reinterpret_cast<const uint32_t*>(base + at) & ((1u << (8 * k)) - 1u);
-    }
-    ph = 32;
-    return 0;
+    if (at + 4 <= iend) return *reinterpret_cast<const uint32_t*>(base + at);
+    tail = 1;
+    return fetch_tail_word(base, at, iend);
   }
 
-  __device__ void open(const uint8_t* begin_, uint32_t len)
+  __device__ __forceinline__ void open(const uint8_t* begin_, uint32_t len)
   {
     lead0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(begin_) & 3u);
     base = begin_ - lead0;
@@ -163,57 +182,51 @@ struct BitReader {
   }
 
   // start reading at byte offset `at` from base (lead0 <= at <= iend), then skip 0..7 bits
-  __device__ void init_at(uint32_t at, unsigned skip_bits)
+  __device__ __forceinline__ void init_at(uint32_t at, unsigned skip_bits)
   {
-    const uint32_t lead = at & 3u;
-    const uint32_t a0 = at - lead;
-    int ph0 = 32, ph1 = 32;
-    uint32_t w0 = 0;
-    if (at < iend) w0 = fetch(a0, ph0);
-    buf = static_cast<uint64_t>(w0 >> (8 * lead));
-    cnt = 32 - 8 * static_cast<int>(lead);
-    if (ph0 > cnt) ph0 = cnt;  // stream shorter than the rest of this word
-    ip = a0 + 4;
-    nextw = fetch(ip, ph1);
-    phantom = ph0 + ph1;
-    refill();
-    buf >>= skip_bits;
-    cnt -= static_cast<int>(skip_bits);
+    const uint32_t a0 = at & ~3u;
+    tail = 0;
+    w0 = fetch(a0);
+    w1 = fetch(a0 + 4);
+    w2 = fetch(a0 + 8);
+    ip = a0 + 12;
+    bo = 8 * (at & 3u) + skip_bits;
+    norm();
   }
 
-  __device__ __forceinline__ void refill()
+  // make bo < 32 again (bo < 64 on entry): slide the window by one word
+  __device__ __forceinline__ void norm()
   {
-    if (cnt <= 32) {
-      buf |= static_cast<uint64_t>(nextw) << cnt;
-      cnt += 32;
+    if (bo >= 32) {
+      w0 = w1;
+      w1 = w2;
+      w2 = fetch(ip);
       ip += 4;
-      if (ip + 4 <= iend) {
-        nextw = *reinterpret_cast<const uint32_t*>(base + ip);
-      } else {
-        int ph;
-        nextw = fetch(ip, ph);
-        phantom += ph;
-      }
+      bo -= 32;
     }
   }
-  __device__ __forceinline__ void drop(uint32_t n)
-  {
-    buf >>= n;
-    cnt -= static_cast<int>(n);
-  }
-  __device__ __forceinline__ uint32_t peek32() const { return static_cast<uint32_t>(buf); }
-  // real bits among the fetched, unconsumed ones (negative after an overrun)
-  __device__ __forceinline__ int real_left() const { return cnt + 32 - phantom; }
+  // next 32 bits (requires bo < 32)
+  __device__ __forceinline__ uint32_t peek() const { return funnel_r(w0, w1, bo); }
+  __device__ __forceinline__ void skip(uint32_t n) { bo += n; }
+
   // absolute bit position of the next unread bit, relative to the stream start
   __device__ __forceinline__ uint64_t bitpos() const
   {
-    return 8ull * static_cast<uint64_t>(ip - lead0) - static_cast<uint64_t>(cnt);
+    // (the window may start before the stream: ip - 12 < lead0 right after init_at)
+    return static_cast<uint64_t>(8ll * (static_cast<int64_t>(ip) - 12 - static_cast<int64_t>(lead0)) +
+                                 static_cast<int64_t>(bo));
   }
   __device__ __forceinline__ uint64_t total_bits() const
   {
     return 8ull * static_cast<uint64_t>(iend - lead0);
   }
-  __device__ void seek_bit(uint64_t bit)
+  // real (inside the stream) bits from the next unread bit on; negative after an overrun
+  __device__ __forceinline__ int64_t real_left() const
+  {
+    return static_cast<int64_t>(total_bits()) - static_cast<int64_t>(bitpos());
+  }
+  __device__ __forceinline__ bool overrun() const { return real_left() < 0; }
+  __device__ __forceinline__ void seek_bit(uint64_t bit)
   {
     init_at(lead0 + static_cast<uint32_t>(bit >> 3), static_cast<unsigned>(bit & 7));
   }
@@ -226,62 +239,80 @@ __device__ __forceinline__ uint32_t bit_at(const uint8_t* begin, uint64_t i)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Lane-interleaved shared memory views.
-struct LaneMem {
-  uint16_t* lut;   // element j at lut[j*32]
-  uint16_t* lens;  // nibble s at (lens[(s>>2)*32] >> 4*(s&3)) & 15
-  uint16_t* work;  // count[L] at work[L*32], next[L] at work[(16+L)*32]
-
-  __device__ __forceinline__ uint32_t len_of(int s) const
+// Code lengths of the current block: 320 nibbles per lane in global scratch, lane-interleaved
+// (word j of lane l at g[j*32 + l], so lanes working in lock-step coalesce).  Lit/len lengths
+// occupy nibbles [0, n_lit), distance lengths follow at [n_lit, n_lit + n_dist).
+struct LensWriter {
+  uint32_t* g;
+  uint32_t acc;
+  int k;
+  __device__ __forceinline__ explicit LensWriter(uint32_t* g_) : g(g_), acc(0), k(0) {}
+  __device__ __forceinline__ void put(uint32_t v)
   {
-    return (lens[(s >> 2) * 32] >> ((s & 3) * 4)) & 15u;
+    acc |= v << (4 * (k & 7));
+    ++k;
+    if ((k & 7) == 0) {
+      g[((k >> 3) - 1) * 32] = acc;
+      acc = 0;
+    }
   }
-  __device__ __forceinline__ void set_len(int s, uint32_t v) const
+  __device__ __forceinline__ void finish()
   {
-    uint16_t& w = lens[(s >> 2) * 32];
-    const int sh = (s & 3) * 4;
-    w = static_cast<uint16_t>((w & ~(15u << sh)) | (v << sh));
+    if (k & 7) g[(k >> 3) * 32] = acc;
   }
 };
 
+// Sequential reader of `count` nibbles starting at nibble `start`.
+struct LensReader {
+  const uint32_t* g;
+  uint32_t w;
+  int s, end;
+  __device__ __forceinline__ LensReader(const uint32_t* g_, int start, int count)
+      : g(g_), w(0), s(start), end(start + count)
+  {
+    if (count > 0) w = g[(start >> 3) * 32] >> (4 * (start & 7));
+  }
+  __device__ __forceinline__ uint32_t next()
+  {
+    const uint32_t v = w & 15u;
+    ++s;
+    w >>= 4;
+    if ((s & 7) == 0 && s < end) w = g[(s >> 3) * 32];
+    return v;
+  }
+};
+
+struct LaneMem {
+  uint16_t* lut;       // element j at lut[j*32]
+  uint32_t* lens;      // this lane's slice of the global code-length scratch
+};
+
 // ---------------------------------------------------------------------------------------------
-// Exact canonical decode of one symbol, bit-serial, straight from the code lengths.
+// Exact canonical decode of one symbol, bit-serial, from the per-length first-code / count
+// arrays and the canonical symbol order that build_lut() leaves in the lane's scratch.
 // Restates huffman::decode_one + table::find (huffman/src/decode.hpp:83-102,
-// huffman/src/table.hpp:426-452) over the table that huffman::table(symbol_bitsize, ...) +
-// canonicalize() would build (table.hpp:177-216,360-376) for lengths lens[s0 .. s0+n).
-// Returns the code length (0 = not found: unassigned code, or input exhausted first).
-__device__ __noinline__ int canon_decode(const LaneMem& m, int s0, int n, const uint8_t* begin,
+// huffman/src/table.hpp:426-452): after each bit a code of the current bitsize matches iff
+// (value - first[len]) <u count[len]; the shortest match wins; "not found" when the input is
+// exhausted or the bitsize passes the longest code.  Valid for ANY length set the reference
+// accepts (incomplete, over-subscribed).  `which` = 0 lit/len, 1 distance.
+// Returns the code length (0 = not found).
+__device__ __noinline__ int canon_decode(const uint32_t* scratch, int which, const uint8_t* begin,
                                          uint64_t pos, uint64_t end, int* symbol)
 {
-  uint16_t cnt[16];
-#pragma unroll
-  for (int L = 0; L < 16; ++L) cnt[L] = 0;
-  int maxlen = 0;
-  for (int s = 0; s < n; ++s) {
-    const int L = static_cast<int>(m.len_of(s0 + s));
-    if (L) {
-      cnt[L]++;
-      if (L > maxlen) maxlen = L;
-    }
-  }
-  uint32_t code = 0, first = 0;
-  for (int L = 1; L <= maxlen; ++L) {
-    if (pos + static_cast<uint64_t>(L - 1) >= end) return 0;  // ran out of input
-    code = (code << 1) | bit_at(begin, pos + static_cast<uint64_t>(L - 1));
-    first = (first + (L > 1 ? cnt[L - 1] : 0u)) << 1;
-    const uint32_t k = code - first;
-    if (cnt[L] && k < cnt[L]) {
-      // k-th symbol (ascending symbol order) among those of length L
-      uint32_t seen = 0;
-      for (int s = 0; s < n; ++s) {
-        if (static_cast<int>(m.len_of(s0 + s)) == L) {
-          if (seen == k) {
-            *symbol = s;
-            return L;
-          }
-          ++seen;
-        }
-      }
+  const uint32_t* first = scratch + (SCR_FIRST + 16 * which) * 32;
+  const uint32_t* cnt_off = scratch + (SCR_COUNT + 16 * which) * 32;
+  const uint32_t maxlen = first[0];  // slot 0 holds the longest code length of the table
+  uint32_t code = 0;
+  for (uint32_t L = 1; L <= maxlen; ++L) {
+    if (pos + (L - 1) >= end) return 0;  // ran out of input
+    code = (code << 1) | bit_at(begin, pos + (L - 1));
+    const uint32_t co = cnt_off[L * 32];
+    const uint32_t k = code - first[L * 32];
+    if (k < (co & 0xffffu)) {
+      const uint32_t i = (which ? 288u : 0u) + (co >> 16) + k;
+      const uint32_t w = scratch[(SCR_SORTED + (i >> 1)) * 32];
+      *symbol = static_cast<int>((i & 1u) ? (w >> 16) : (w & 0xffffu));
+      return static_cast<int>(L);
     }
   }
   return 0;
@@ -299,16 +330,17 @@ struct SlowToken {
 // (src/decompress.cpp:206-240 with decode_lit_or_len :122-144 and
 // decompress_length_distance :157-177), bit-serially.  Output-side checks
 // (distance > written, room) stay with the caller.
-__device__ __noinline__ SlowToken slow_token(const LaneMem& m, int n_lit, int n_dist,
-                                             const uint8_t* begin, uint64_t pos, uint64_t end)
+__device__ __noinline__ SlowToken slow_token(const uint32_t* lens, const uint8_t* begin,
+                                             uint64_t pos, uint64_t end)
 {
   SlowToken t;
   t.status = ST_SUCCESS;
   t.kind = 0;
   t.value = 0;
   t.dist = 0;
+  t.next = pos;
   int sym = 0;
-  int used = canon_decode(m, 0, n_lit, begin, pos, end, &sym);
+  int used = canon_decode(lens, 0, begin, pos, end, &sym);
   if (!used) {
     t.status = ST_INVALID_LIT_OR_LEN;
     return t;
@@ -339,7 +371,7 @@ __device__ __noinline__ SlowToken slow_token(const LaneMem& m, int n_lit, int n_
   for (int i = 0; i < extra; ++i) v |= static_cast<int>(bit_at(begin, pos + i)) << i;
   pos += static_cast<uint64_t>(extra);
   t.value = static_cast<int>(info & 0xffffu) + v;
-  used = canon_decode(m, n_lit, n_dist, begin, pos, end, &sym);
+  used = canon_decode(lens, 1, begin, pos, end, &sym);
   if (!used) {
     t.status = ST_INVALID_DISTANCE;
     return t;
@@ -364,7 +396,7 @@ __device__ __noinline__ SlowToken slow_token(const LaneMem& m, int n_lit, int n_
 }
 
 // ---------------------------------------------------------------------------------------------
-// Build one two-level LUT from code lengths lens[s0 .. s0+n).  Canonical code assignment as in
+// Build one two-level LUT from code lengths [s0, s0+n).  Canonical code assignment as in
 // huffman::table::canonicalize (huffman/src/table.hpp:177-216).  Length sets the reference
 // accepts but a prefix LUT cannot represent exactly (over-subscribed: some code value reaches
 // 2^len, "shortest code wins") get E_SLOW in every root slot.
@@ -381,55 +413,71 @@ __device__ __forceinline__ uint16_t make_entry(uint32_t s, uint32_t L)
 }
 
 template <int ROOT, bool LITLEN, int POOL_OFF>
-__device__ void build_lut(const LaneMem& m, int s0, int n, int root_off, int pool_end,
+__device__ __forceinline__ void build_lut(const LaneMem& m, int s0, int n, int root_off, int pool_end,
                           int& pool_at)
 {
   uint16_t* const lut = m.lut;
-  uint16_t* const count = m.work;
-  uint16_t* const next = m.work + 16 * 32;
+  uint32_t* const g_first = m.lens + (SCR_FIRST + (LITLEN ? 0 : 16)) * 32;
+  uint32_t* const g_count = m.lens + (SCR_COUNT + (LITLEN ? 0 : 16)) * 32;
+  uint16_t* const g_sorted = reinterpret_cast<uint16_t*>(m.lens + SCR_SORTED * 32);
+  constexpr uint32_t SORT0 = LITLEN ? 0u : 288u;
+  uint16_t count[16], offset[16];
+  uint32_t next[16];
+#pragma unroll
+  for (int L = 0; L < 16; ++L) count[L] = 0;
+  {
+    LensReader r(m.lens, s0, n);
 #pragma unroll 1
-  for (int L = 0; L < 16; ++L) count[L * 32] = 0;
-#pragma unroll 1
-  for (int s = 0; s < n; ++s) {
-    const uint32_t L = m.len_of(s0 + s);
-    count[L * 32]++;
+    for (int s = 0; s < n; ++s) count[r.next()]++;
   }
   count[0] = 0;
   bool over = false;
   {
-    uint32_t code = 0;
-#pragma unroll 1
+    uint32_t code = 0, off = 0, maxlen = 0;
+#pragma unroll
     for (int L = 1; L < 16; ++L) {
-      code = (code + count[(L - 1) * 32]) << 1;
-      next[L * 32] = static_cast<uint16_t>(code);
-      if (code + count[L * 32] > (1u << L)) over = true;
+      code = (code + count[L - 1]) << 1;
+      next[L] = code;
+      offset[L] = static_cast<uint16_t>(off);
+      g_first[L * 32] = code;
+      g_count[L * 32] = count[L] | (off << 16);
+      off += count[L];
+      if (count[L]) maxlen = L;
+      if (code + count[L] > (1u << L)) over = true;
     }
-  }
-  if (over) {
-#pragma unroll 1
-    for (int j = 0; j < (1 << ROOT); ++j) lut[(root_off + j) * 32] = static_cast<uint16_t>(E_SLOW);
-    return;
+    g_first[0] = maxlen;
   }
 #pragma unroll 1
-  for (int j = 0; j < (1 << ROOT); ++j) lut[(root_off + j) * 32] = 0;
-  // pass A: direct entries; long codes leave (0xF000 | max length) in their root slot
+  for (int j = 0; j < (1 << ROOT); ++j)
+    lut[(root_off + j) * 32] = over ? static_cast<uint16_t>(E_SLOW) : static_cast<uint16_t>(0);
+  // pass A: canonical symbol order for canon_decode(); direct LUT entries; long codes leave
+  // (0xF000 | max length) in their root slot
   uint32_t pmin = 1u << ROOT, pmax = 0;
+  {
+    LensReader r(m.lens, s0, n);
 #pragma unroll 1
-  for (int s = 0; s < n; ++s) {
-    const uint32_t L = m.len_of(s0 + s);
-    if (!L) continue;
-    const uint32_t code = next[L * 32]++;
-    if (L <= static_cast<uint32_t>(ROOT)) {
-      const uint16_t e = make_entry<LITLEN>(static_cast<uint32_t>(s), L);
-      for (uint32_t j = bitrev(code, static_cast<int>(L)); j < (1u << ROOT); j += 1u << L)
-        lut[(root_off + j) * 32] = e;
-    } else {
-      const uint32_t pfx = code >> (L - ROOT);
-      uint16_t& slot = lut[(root_off + bitrev(pfx, ROOT)) * 32];
-      const uint32_t prev = slot & 15u;
-      slot = static_cast<uint16_t>(0xF000u | (L > prev ? L : prev));
-      pmin = pfx < pmin ? pfx : pmin;
-      pmax = pfx > pmax ? pfx : pmax;
+    for (int s = 0; s < n; ++s) {
+      const uint32_t L = r.next();
+      if (!L) continue;
+      const uint32_t code = next[L]++;
+      {
+        // rank within the length = symbols of this length seen so far
+        const uint32_t i = SORT0 + offset[L]++;
+        g_sorted[(i >> 1) * 64 + (i & 1u)] = static_cast<uint16_t>(s);
+      }
+      if (over) continue;
+      if (L <= static_cast<uint32_t>(ROOT)) {
+        const uint16_t e = make_entry<LITLEN>(static_cast<uint32_t>(s), L);
+        for (uint32_t j = bitrev(code, static_cast<int>(L)); j < (1u << ROOT); j += 1u << L)
+          lut[(root_off + j) * 32] = e;
+      } else {
+        const uint32_t pfx = code >> (L - ROOT);
+        uint16_t& slot = lut[(root_off + bitrev(pfx, ROOT)) * 32];
+        const uint32_t prev = slot & 15u;
+        slot = static_cast<uint16_t>(0xF000u | (L > prev ? L : prev));
+        pmin = pfx < pmin ? pfx : pmin;
+        pmax = pfx > pmax ? pfx : pmax;
+      }
     }
   }
   if (pmax < pmin) return;  // no long codes
@@ -453,26 +501,29 @@ __device__ void build_lut(const LaneMem& m, int s0, int n, int root_off, int poo
   // pass C: fill sub-tables
   {
     uint32_t code = 0;
-#pragma unroll 1
+#pragma unroll
     for (int L = 1; L < 16; ++L) {
-      code = (code + count[(L - 1) * 32]) << 1;
-      next[L * 32] = static_cast<uint16_t>(code);
+      code = (code + count[L - 1]) << 1;
+      next[L] = code;
     }
   }
+  {
+    LensReader r(m.lens, s0, n);
 #pragma unroll 1
-  for (int s = 0; s < n; ++s) {
-    const uint32_t L = m.len_of(s0 + s);
-    if (L <= static_cast<uint32_t>(ROOT)) continue;
-    const uint32_t code = next[L * 32]++;
-    const uint32_t rest = L - ROOT;
-    const uint32_t e = lut[(root_off + bitrev(code >> rest, ROOT)) * 32];
-    if (e == E_SLOW) continue;
-    const uint32_t sb = e >> 13;
-    const uint32_t off = POOL_OFF + ((e >> 4) & 0x1ffu);
-    const uint16_t v = make_entry<LITLEN>(static_cast<uint32_t>(s), L);
-    for (uint32_t j = bitrev(code & ((1u << rest) - 1u), static_cast<int>(rest)); j < (1u << sb);
-         j += 1u << rest)
-      lut[(off + j) * 32] = v;
+    for (int s = 0; s < n; ++s) {
+      const uint32_t L = r.next();
+      if (L <= static_cast<uint32_t>(ROOT)) continue;  // next[] of short lengths is not needed
+      const uint32_t code = next[L]++;
+      const uint32_t rest = L - ROOT;
+      const uint32_t e = lut[(root_off + bitrev(code >> rest, ROOT)) * 32];
+      if (e == E_SLOW) continue;
+      const uint32_t sb = e >> 13;
+      const uint32_t off = POOL_OFF + ((e >> 4) & 0x1ffu);
+      const uint16_t v = make_entry<LITLEN>(static_cast<uint32_t>(s), L);
+      for (uint32_t j = bitrev(code & ((1u << rest) - 1u), static_cast<int>(rest)); j < (1u << sb);
+           j += 1u << rest)
+        lut[(off + j) * 32] = v;
+    }
   }
 }
 
@@ -532,7 +583,7 @@ struct OutWin {
   }
 
   // write the unflushed tail (called once, when the stream ends for any reason)
-  __device__ void flush_tail()
+  __device__ __forceinline__ void flush_tail()
   {
     const uint32_t wv = vpos & ~7u;
     uint32_t b = wv < lead ? lead : wv;
@@ -551,34 +602,35 @@ enum : int { S_DECODE = 0, S_MATCH = 1, S_STORED = 2, S_HEADER = 3, S_DONE = 4 }
 // of this repository apply (SrcTooSmall; InvalidLitOrLen for malformed repeats).
 // Returns the next lane state; *status is set when the state is S_DONE.
 template <class C>
-__device__ int parse_block_header(BitReader& br, const LaneMem& m, OutWin& ow, bool& final_block,
+__device__ __forceinline__ int parse_block_header(BitReader& br, const LaneMem& m, OutWin& ow, uint32_t& final_block,
                                   int& n_lit, int& n_dist, const uint8_t*& copy_src,
                                   uint32_t& copy_left, int* status)
 {
-  br.refill();
+  br.norm();
   if (br.real_left() < 3) {
     *status = ST_INVALID_BLOCK_HEADER;
     return S_DONE;
   }
-  const uint32_t hdr = br.peek32() & 7u;
+  const uint32_t hdr = br.peek() & 7u;
   const uint32_t type = hdr >> 1;
   if (type == 3) {
     *status = ST_INVALID_BLOCK_HEADER;
     return S_DONE;
   }
-  final_block = (hdr & 1u) != 0;
-  br.drop(3);
+  final_block = hdr & 1u;
+  br.skip(3);
 
   if (type == 0) {
-    // stored block
-    br.drop(br.cnt & 7);  // phantom words are whole bytes, so cnt mod 8 is the stream's phase
-    br.refill();
+    // stored block: skip to the byte boundary (the window words are byte-aligned with the
+    // stream, so the phase of `bo` is the phase of the stream)
+    br.skip((8u - (br.bo & 7u)) & 7u);
+    br.norm();
     if (br.real_left() < 32) {
       *status = ST_SRC_TOO_SMALL;  // reference: pop_16 past the end (class U)
       return S_DONE;
     }
-    const uint32_t w = br.peek32();
-    br.drop(32);
+    const uint32_t w = br.peek();
+    br.skip(32);
     const uint32_t len = w & 0xffffu, nlen = w >> 16;
     if (len != ((~nlen) & 0xffffu)) {
       *status = ST_LEN_MISMATCH;
@@ -596,6 +648,7 @@ __device__ int parse_block_header(BitReader& br, const LaneMem& m, OutWin& ow, b
     copy_src = br.begin() + (pos >> 3);
     copy_left = len;
     if (len == 0) {
+      br.norm();
       if (final_block) {
         *status = ST_SUCCESS;
         return S_DONE;
@@ -610,43 +663,44 @@ __device__ int parse_block_header(BitReader& br, const LaneMem& m, OutWin& ow, b
     n_lit = 288;
     n_dist = 32;
 #pragma unroll 1
-    for (int j = 0; j < 80; ++j) {
-      const int s = j * 4;
+    for (int j = 0; j < LENS_WORDS; ++j) {
+      const int s = j * 8;
       uint32_t v;
-      if (s < 144) v = 0x8888u;
-      else if (s < 256) v = 0x9999u;
-      else if (s < 280) v = 0x7777u;
-      else if (s < 288) v = 0x8888u;
-      else v = 0x5555u;
-      m.lens[j * 32] = static_cast<uint16_t>(v);
+      if (s < 144) v = 0x88888888u;
+      else if (s < 256) v = 0x99999999u;
+      else if (s < 280) v = 0x77777777u;
+      else if (s < 288) v = 0x88888888u;
+      else v = 0x55555555u;
+      m.lens[j * 32] = v;
     }
   } else {
     // dynamic codes
-    br.refill();
+    br.norm();
     if (br.real_left() < 14) {
       *status = ST_SRC_TOO_SMALL;
       return S_DONE;
     }
-    uint32_t w = br.peek32();
+    uint32_t w = br.peek();
     n_lit = 257 + static_cast<int>(w & 31u);
     n_dist = 1 + static_cast<int>((w >> 5) & 31u);
     const int n_cl = 4 + static_cast<int>((w >> 10) & 15u);
-    br.drop(14);
+    br.skip(14);
     uint64_t cl_lens = 0;  // 19 x 3 bits, indexed by CL symbol
 #pragma unroll 1
     for (int i = 0; i < n_cl; ++i) {
-      br.refill();
+      br.norm();
       if (br.real_left() < 3) {
         *status = ST_SRC_TOO_SMALL;
         return S_DONE;
       }
-      cl_lens |= static_cast<uint64_t>(br.peek32() & 7u) << (3 * c_cl_order[i]);
-      br.drop(3);
+      cl_lens |= static_cast<uint64_t>(br.peek() & 7u) << (3 * c_cl_order[i]);
+      br.skip(3);
     }
-    // code-length code: 7-bit LUT of bytes (sym << 3 | len), overlaid on the pool region.
+    // code-length code: 7-bit LUT of bytes (sym << 3 | len), overlaid on the pool region
+    // (two bytes per u16 slot: byte j of this lane lives in slot j >> 1).
     // Filled from the longest length down so that, for over-subscribed sets, the shortest
     // matching code wins exactly as the reference's bit-serial search does.
-    uint8_t* cl_lut = reinterpret_cast<uint8_t*>(m.lut + C::POOL_OFF * 32);  // byte j at [j*64]
+    uint8_t* cl_lut = reinterpret_cast<uint8_t*>(m.lut + C::POOL_OFF * 32);
     {
       uint32_t cnt[8];
 #pragma unroll
@@ -665,7 +719,7 @@ __device__ int parse_block_header(BitReader& br, const LaneMem& m, OutWin& ow, b
         }
       }
 #pragma unroll 1
-      for (int j = 0; j < 128; ++j) cl_lut[j * 64] = 0;
+      for (int j = 0; j < 128; ++j) cl_lut[(j >> 1) * 64 + (j & 1)] = 0;
 #pragma unroll 1
       for (int L = 7; L >= 1; --L) {
         uint32_t code = first[L];
@@ -674,7 +728,7 @@ __device__ int parse_block_header(BitReader& br, const LaneMem& m, OutWin& ow, b
           if (static_cast<int>((cl_lens >> (3 * s)) & 7u) != L) continue;
           if (code < (1u << L)) {
             for (uint32_t j = bitrev(code, L); j < 128u; j += 1u << L)
-              cl_lut[j * 64] = static_cast<uint8_t>((s << 3) | L);
+              cl_lut[(j >> 1) * 64 + (j & 1)] = static_cast<uint8_t>((s << 3) | L);
           }
           ++code;
         }
@@ -682,58 +736,65 @@ __device__ int parse_block_header(BitReader& br, const LaneMem& m, OutWin& ow, b
     }
     // the two independent runs of code lengths (src/decompress.cpp:353-360)
     const int total = n_lit + n_dist;
-#pragma unroll 1
-    for (int j = 0; j < 80; ++j) m.lens[j * 32] = 0;
+    LensWriter lw(m.lens);
     int run_begin = 0, run_end = n_lit;
+    uint32_t prev = 0;
 #pragma unroll 1
     for (int i = 0; i < total;) {
       if (i == run_end) {
         run_begin = n_lit;
         run_end = total;
       }
-      br.refill();
-      const uint32_t e = cl_lut[(br.peek32() & 127u) * 64];
-      const int L = static_cast<int>(e & 7u);
-      if (L == 0 || L > br.real_left()) {
+      br.norm();
+      const uint32_t bits = br.peek();
+      const uint32_t j = bits & 127u;
+      const uint32_t e = cl_lut[(j >> 1) * 64 + (j & 1)];
+      const uint32_t L = e & 7u;
+      const int64_t left = br.real_left();
+      if (L == 0 || static_cast<int64_t>(L) > left) {
         *status = ST_INVALID_LIT_OR_LEN;  // src/decompress.cpp:265-267
         return S_DONE;
       }
-      br.drop(L);
+      br.skip(L);
       const uint32_t sym = e >> 3;
       if (sym < 16) {
-        if (sym) m.set_len(i, sym);
+        lw.put(sym);
+        prev = sym;
         ++i;
         continue;
       }
-      const int xbits = sym == 16 ? 2 : sym == 17 ? 3 : 7;
-      if (br.real_left() < xbits) {
+      const uint32_t xbits = sym == 16 ? 2u : sym == 17 ? 3u : 7u;
+      if (left - static_cast<int64_t>(L) < static_cast<int64_t>(xbits)) {
         *status = ST_SRC_TOO_SMALL;  // reference: unchecked pop_bits (class U)
         return S_DONE;
       }
-      int repeat = static_cast<int>(br.peek32() & ((1u << xbits) - 1u)) + (sym == 18 ? 11 : 3);
-      br.drop(xbits);
+      // L + xbits <= 14 bits: still inside the peeked word
+      const int repeat = static_cast<int>((bits >> L) & ((1u << xbits) - 1u)) + (sym == 18 ? 11 : 3);
+      br.skip(xbits);
       uint32_t v = 0;
       if (sym == 16) {
         if (i == run_begin) {
           *status = ST_INVALID_LIT_OR_LEN;  // reference reads code_bitsizes[-1] (class U)
           return S_DONE;
         }
-        v = m.len_of(i - 1);
+        v = prev;
       }
       if (i + repeat > run_end) {
         *status = ST_INVALID_LIT_OR_LEN;  // reference writes past code_bitsizes (class U)
         return S_DONE;
       }
-      if (v) {
-        for (int j = 0; j < repeat; ++j) m.set_len(i + j, v);
-      }
+#pragma unroll 1
+      for (int r = 0; r < repeat; ++r) lw.put(v);
+      prev = v;
       i += repeat;
     }
+    lw.finish();
   }
   int pool_at = C::POOL_OFF;
   build_lut<C::ROOT_LIT, true, C::POOL_OFF>(m, 0, n_lit, C::LIT_OFF, C::POOL_OFF + C::POOL, pool_at);
   build_lut<C::ROOT_DIST, false, C::POOL_OFF>(m, n_lit, n_dist, C::DIST_OFF, C::POOL_OFF + C::POOL,
                                               pool_at);
+  br.norm();
   return S_DECODE;
 }
 
@@ -766,8 +827,9 @@ inflate_lanes_kernel(const BatchArgs a)
 
   LaneMem m;
   m.lut = smem + warp * C::WARP_U16 + lane;
-  m.lens = m.lut + C::LUT_U16 * 32;
-  m.work = m.lens + C::LENS_U16 * 32;
+  m.lens = a.lens_scratch +
+           (static_cast<size_t>(blockIdx.x) * C::WARPS + static_cast<size_t>(warp)) * (SCRATCH_WORDS * 32) +
+           lane;
   const uint16_t* const lut = m.lut;
 
   const uint64_t n_groups = (a.n + 31) / 32;
@@ -782,7 +844,7 @@ inflate_lanes_kernel(const BatchArgs a)
     int status = ST_SUCCESS;
     BitReader br;
     OutWin ow;
-    bool final_block = false;
+    uint32_t final_block = 0;
     int n_lit = 0, n_dist = 0;
     uint32_t mlen = 0, mdist = 0;
     const uint8_t* copy_src = nullptr;
@@ -791,7 +853,7 @@ inflate_lanes_kernel(const BatchArgs a)
     if (live) {
       const uint64_t slen = a.src_len[idx];
       const uint64_t cap = a.dst_cap[idx];
-      if (slen >= 0xfffffff0ull || cap >= 0xfffffff0ull) {
+      if (slen >= 0xffffff00ull || cap >= 0xffffff00ull) {
         a.status[idx] = ST_ERROR;  // outside the batch precondition
         if (a.written) a.written[idx] = 0;
         live = false;
@@ -818,47 +880,52 @@ inflate_lanes_kernel(const BatchArgs a)
         uint32_t n = 0;
         // ---- stage 1: decode one token ------------------------------------------------------
         if (state == S_DECODE) {
-          br.refill();
           SFB_STAT(tokens);
-          const uint32_t ip0 = br.ip;   // token start = 8*(ip0 - lead0) - cnt0 (slow path only)
-          const int cnt0 = br.cnt;
-          bool slow = false, is_match = false, eob = false;
-          uint32_t value = 0, dist = 0;
-          uint32_t e = lut_lookup<C::ROOT_LIT, C::POOL_OFF>(lut, C::LIT_OFF, br.peek32());
-          uint32_t L = e & 15u;
+          // br.bo < 32 here (norm() ran at the end of the previous token)
+          const uint32_t ip0 = br.ip;   // token start (slow path only)
+          const uint32_t bo0 = br.bo;
+          uint32_t slow, is_match = 0, eob = 0;
+          uint32_t value, dist = 0;
+          uint32_t bits = br.peek();
+          const uint32_t e = lut_lookup<C::ROOT_LIT, C::POOL_OFF>(lut, C::LIT_OFF, bits);
+          const uint32_t L = e & 15u;
           slow = (L == 0);
-          br.drop(L);
+          bits >>= L;
+          value = (e >> 4) & 0xffu;
+          uint32_t used = L;
           if (e & 0xF000u) {            // not a literal: end of block, length code, or oddity
             if (e & 0x8000u) {
               if (L) {
-                is_match = true;
+                is_match = 1;
                 const uint32_t xb = (e >> 12) & 7u;
-                value = 3u + ((e >> 4) & 0xffu) + (br.peek32() & ((1u << xb) - 1u));
-                br.drop(xb);
-                br.refill();
-                const uint32_t de = lut_lookup<C::ROOT_DIST, C::POOL_OFF>(lut, C::DIST_OFF, br.peek32());
+                value += 3u + (bits & ((1u << xb) - 1u));
+                br.skip(L + xb);
+                br.norm();
+                bits = br.peek();
+                const uint32_t de = lut_lookup<C::ROOT_DIST, C::POOL_OFF>(lut, C::DIST_OFF, bits);
                 const uint32_t dL = de & 15u;
                 const uint32_t dsym = (de >> 4) & 31u;
                 slow = (dL == 0) | (dsym >= 30u);
-                br.drop(dL);
                 const uint32_t dinfo = s_dist_info[dsym];
                 const uint32_t dxb = dinfo >> 16;
-                dist = (dinfo & 0xffffu) + (br.peek32() & ((1u << dxb) - 1u));
-                br.drop(dxb);
+                dist = (dinfo & 0xffffu) + ((bits >> dL) & ((1u << dxb) - 1u));
+                used = dL + dxb;
               }
             } else if ((e & 0xF000u) == E_KIND_EOB) {
-              eob = true;
+              eob = 1;
             } else {
-              slow = true;              // symbols 286 / 287
+              slow = 1;                 // symbols 286 / 287
             }
-          } else {
-            value = (e >> 4) & 0xffu;
           }
-          if (slow | (br.real_left() < 0)) {
+          br.skip(used);
+          br.norm();
+          if (br.tail) slow |= br.overrun();
+          if (slow) {
             // anything the fast path cannot vouch for: redo this token exactly
             SFB_STAT(slow_tokens);
-            const uint64_t tok_pos = 8ull * static_cast<uint64_t>(ip0 - br.lead0) - static_cast<uint64_t>(cnt0);
-            const SlowToken t = slow_token(m, n_lit, n_dist, br.begin(), tok_pos, br.total_bits());
+            const uint64_t tok_pos = static_cast<uint64_t>(
+                8ll * (static_cast<int64_t>(ip0) - 12 - static_cast<int64_t>(br.lead0)) + bo0);
+            const SlowToken t = slow_token(m.lens, br.begin(), tok_pos, br.total_bits());
             if (t.status != ST_SUCCESS) {
               status = t.status;
               state = S_DONE;

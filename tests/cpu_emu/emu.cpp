@@ -23,6 +23,7 @@ extern "C" int emu_decompress_batch(const uint8_t* src, const uint64_t* src_off,
                                     uint8_t* status, uint64_t* written, uint64_t n)
 {
   std::vector<uint16_t> smem(EmuCfg::SMEM_BYTES / 2 + 64, 0xDEAD);
+  std::vector<uint32_t> lens(sfb::SCRATCH_WORDS * 32, 0xDEADBEEFu);
   emu_smem = smem.data();
   blockDim.x = 1;  // one emulated lane
   gridDim.x = 1;
@@ -54,6 +55,7 @@ extern "C" int emu_decompress_batch(const uint8_t* src, const uint64_t* src_off,
     a.written = written ? &written[i] : nullptr;
     a.n = 1;
     a.group_counter = &counter;
+    a.lens_scratch = lens.data();
     threadIdx.x = 0;
     blockIdx.x = 0;
     sfb::inflate_lanes_kernel<EmuCfg>(a);

@@ -15,7 +15,7 @@ _u8p = C.POINTER(C.c_uint8)
 _u64p = C.POINTER(C.c_uint64)
 
 
-def build(root_lit=9, root_dist=6, pool=192) -> str:
+def build(root_lit=8, root_dist=6, pool=128) -> str:
     out = os.path.join(HERE, "cpu_emu", f"libemu_{root_lit}_{root_dist}_{pool}.so")
     srcs = [os.path.join(HERE, "cpu_emu", "emu.cpp"), os.path.join(HERE, "cpu_emu", "cuda_shim.h"),
             os.path.join(ROOT, "starflate_b200", "csrc", "inflate_lanes.cuh")]

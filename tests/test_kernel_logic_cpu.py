@@ -32,7 +32,8 @@ def test_golden_families(emu, oracle, golden):
     assert s["tokens"] > 1_000_000 and s["slow_tokens"] < s["tokens"] // 20  # fast path exercised
 
 
-@pytest.mark.parametrize("cfg", [dict(root_lit=8, root_dist=5, pool=128),
+@pytest.mark.parametrize("cfg", [dict(root_lit=7, root_dist=5, pool=64),
+                                 dict(root_lit=9, root_dist=6, pool=192),
                                  dict(root_lit=10, root_dist=8, pool=448)])
 def test_other_lut_geometries(oracle, golden, cfg):
     """Small pools force the E_SLOW (pool exhausted) path on valid streams; results must not change."""
