@@ -97,7 +97,7 @@ struct Cfg {
 //   L == 0: 0x0000 no code here; E_SLOW "not representable, use slow_token()";
 //           otherwise a sub-table pointer: bits 4-12 offset from the pool start,
 //           bits 13-15 sub-table index bits (1..7)
-constexpr uint32_t E_SLOW = 0xFFF0u;
+constexpr uint32_t E_SLOW = 0xFFF0u;   // (sub-table of 2^7 entries at pool offset 511: never allocated)
 constexpr uint32_t E_KIND_EOB = 0x1000u;
 constexpr uint32_t E_KIND_BAD = 0x3000u;
 
@@ -139,10 +139,15 @@ __device__ __forceinline__ uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t 
 
 // ---------------------------------------------------------------------------------------------
 // Bit reader (replaces huffman::bit_span, huffman/src/bit_span.hpp).  Bits are consumed LSB
-// first.  w0:w1 is a 64-bit window over the stream, w2 the already-fetched following word,
-// `bo` the offset of the next unread bit inside w0 (kept < 32 by norm()).  Words at or past
-// the end of the stream are fetched as zeros and raise `tail`; while `tail` is clear no
-// consumer can have run past the end, so the hot loop only checks overrun() in tail mode.
+// first.  w0:w1:w2 is a 96-bit window over the stream, w3 and w4 are the two already-fetched
+// following words, `bo` the offset of the next unread bit inside the window.  With bo < 32 at
+// the start of a token the window holds >= 65 unread bits, more than the longest token
+// (15 + 5 + 15 + 13 = 48), so a token is decoded with two funnel-shift peeks and the window
+// slides once per token (norm2(): by 0, 1 or 2 words, branch-free; the words loaded there are
+// first consumed a whole token later, which hides their latency).  Words at or past the end of
+// the stream are fetched as zeros and raise `tail`; while `tail` is clear no consumer can have
+// run past the end, so the hot loop only checks overrun() in tail mode.
+
 // word at byte offset `at` when it is not entirely inside the stream (rare): zero-filled
 __device__ __noinline__ uint32_t fetch_tail_word(const uint8_t* base, uint32_t at, uint32_t iend)
 {
@@ -154,9 +159,9 @@ __device__ __noinline__ uint32_t fetch_tail_word(const uint8_t* base, uint32_t a
 }
 
 struct BitReader {
-  uint32_t w0, w1, w2;
+  uint32_t w0, w1, w2, w3, w4;
   uint32_t bo;
-  uint32_t ip;          // byte offset (from base) of the next word to fetch (w2 sits at ip-4)
+  uint32_t ip;          // byte offset (from base) of the next word to fetch (w4 sits at ip-4)
   uint32_t tail;        // some fetched word was not entirely inside the stream
   uint32_t iend;        // byte offset (from base) one past the last stream byte
   uint32_t lead0;       // stream start - base (0..3)
@@ -164,8 +169,8 @@ struct BitReader {
 
   __device__ __forceinline__ const uint8_t* begin() const { return base + lead0; }
 
-  // (fetches near / past the end of the stream go through the free function fetch_tail_word:
-  //  a non-inlined *member* would force this struct out of registers into local memory)
+  // (a non-inlined *member* would force this struct out of registers into local memory,
+  //  hence the free function for the rare case)
   __device__ __forceinline__ uint32_t fetch(uint32_t at)
   {
     if (at + 4 <= iend) return *reinterpret_cast<const uint32_t*>(base + at);
@@ -189,31 +194,66 @@ struct BitReader {
     w0 = fetch(a0);
     w1 = fetch(a0 + 4);
     w2 = fetch(a0 + 8);
-    ip = a0 + 12;
+    w3 = fetch(a0 + 12);
+    w4 = fetch(a0 + 16);
+    ip = a0 + 20;
     bo = 8 * (at & 3u) + skip_bits;
     norm();
   }
 
-  // make bo < 32 again (bo < 64 on entry): slide the window by one word
+  // slide by one word
+  __device__ __forceinline__ void slide1()
+  {
+    w0 = w1;
+    w1 = w2;
+    w2 = w3;
+    w3 = w4;
+    w4 = fetch(ip);
+    ip += 4;
+    bo -= 32;
+  }
+  // make bo < 32 again, any bo (header parsing)
   __device__ __forceinline__ void norm()
   {
-    if (bo >= 32) {
-      w0 = w1;
-      w1 = w2;
-      w2 = fetch(ip);
-      ip += 4;
-      bo -= 32;
+    while (bo >= 32) slide1();
+  }
+  // make bo < 32 again for bo < 96, branch-free in the common case (token loop)
+  __device__ __forceinline__ void norm2()
+  {
+    const bool p1 = bo >= 32, p2 = bo >= 64;
+    uint32_t n0 = 0, n1 = 0;
+    if (p1) {
+      if (ip + 8 <= iend) {
+        n0 = *reinterpret_cast<const uint32_t*>(base + ip);
+        if (p2) n1 = *reinterpret_cast<const uint32_t*>(base + ip + 4);
+      } else {
+        n0 = fetch(ip);
+        if (p2) n1 = fetch(ip + 4);
+      }
     }
+    w0 = p2 ? w2 : (p1 ? w1 : w0);
+    w1 = p2 ? w3 : (p1 ? w2 : w1);
+    w2 = p2 ? w4 : (p1 ? w3 : w2);
+    w3 = p2 ? n0 : (p1 ? w4 : w3);
+    w4 = p2 ? n1 : (p1 ? n0 : w4);
+    ip += p2 ? 8u : (p1 ? 4u : 0u);
+    bo &= 31u;
+  }
+  // 32 bits starting `off` bits into the window (off < 64)
+  __device__ __forceinline__ uint32_t peek_at(uint32_t off) const
+  {
+    const bool hi = off >= 32;
+    return funnel_r(hi ? w1 : w0, hi ? w2 : w1, off);
   }
   // next 32 bits (requires bo < 32)
   __device__ __forceinline__ uint32_t peek() const { return funnel_r(w0, w1, bo); }
   __device__ __forceinline__ void skip(uint32_t n) { bo += n; }
 
   // absolute bit position of the next unread bit, relative to the stream start
+  // (the window may start before the stream: ip - 20 < lead0 right after init_at)
   __device__ __forceinline__ uint64_t bitpos() const
   {
-    // (the window may start before the stream: ip - 12 < lead0 right after init_at)
-    return static_cast<uint64_t>(8ll * (static_cast<int64_t>(ip) - 12 - static_cast<int64_t>(lead0)) +
+    return static_cast<uint64_t>(8ll * (static_cast<int64_t>(ip) - 20 - static_cast<int64_t>(lead0)) +
                                  static_cast<int64_t>(bo));
   }
   __device__ __forceinline__ uint64_t total_bits() const
@@ -528,14 +568,16 @@ __device__ __forceinline__ void build_lut(const LaneMem& m, int s0, int n, int r
 }
 
 // LUT lookup.  Returns a direct entry (L != 0), 0 (no code) or E_SLOW (ask slow_token()).
-template <int ROOT, int POOL_OFF>
+template <int ROOT, int POOL_OFF, uint32_t POOL>
 __device__ __forceinline__ uint32_t lut_lookup(const uint16_t* lut, int root_off, uint32_t bits)
 {
   uint32_t e = lut[(root_off + static_cast<int>(bits & ((1u << ROOT) - 1u))) * 32];
   if ((e & 15u) == 0 && e != 0 && e != E_SLOW) {  // sub-table pointer (codes longer than ROOT)
+    // (lanes that are not decoding run this on stale table contents and discard the result:
+    //  the clamp keeps even a garbage pointer inside this lane's slice)
     const uint32_t sb = e >> 13;
-    const uint32_t off = POOL_OFF + ((e >> 4) & 0x1ffu);
-    e = lut[(off + ((bits >> ROOT) & ((1u << sb) - 1u))) * 32];
+    const uint32_t idx = ((e >> 4) & 0x1ffu) + ((bits >> ROOT) & ((1u << sb) - 1u));
+    e = lut[(POOL_OFF + (idx < POOL ? idx : POOL - 1u)) * 32];
   }
   return e;
 }
@@ -844,6 +886,14 @@ inflate_lanes_kernel(const BatchArgs a)
     int status = ST_SUCCESS;
     BitReader br;
     OutWin ow;
+    // lanes without a stream still run the (predicated-off) token stages: give them a window
+    // that never slides and never loads
+    br.w0 = br.w1 = br.w2 = br.w3 = br.w4 = 0;
+    br.bo = br.ip = br.tail = br.iend = br.lead0 = 0;
+    br.base = nullptr;
+    ow.al = nullptr;
+    ow.lead = ow.vpos = ow.vend = 0;
+    ow.obuf = 0;
     uint32_t final_block = 0;
     int n_lit = 0, n_dist = 0;
     uint32_t mlen = 0, mdist = 0;
@@ -869,114 +919,112 @@ inflate_lanes_kernel(const BatchArgs a)
       }
     }
 
+    // pending output chunk (software pipeline): the bytes decided in iteration j are merged
+    // into the output window in iteration j+1, after the next token has been decoded, so the
+    // loads of a match source overlap a whole decode stage.
+    //   chunk = (pw0 >> psh) | (pw1 << (64 - psh)), pn bytes (0 = nothing pending)
+    uint64_t pw0 = 0, pw1 = 0;
+    uint32_t psh = 0, pn = 0;
+
     while (__any_sync(FULL, state != S_DONE)) {
       if (state == S_HEADER) {
         state = parse_block_header<C>(br, m, ow, final_block, n_lit, n_dist, copy_src, copy_left,
                                       &status);
       }
       // ---- token / copy iterations (all 32 lanes stay in this loop together) ----------------
-      while (__any_sync(FULL, state <= S_STORED)) {
-        uint64_t chunk = 0;
-        uint32_t n = 0;
-        // ---- stage 1: decode one token ------------------------------------------------------
+      while (__any_sync(FULL, (state <= S_STORED) | (pn != 0))) {
+        // ---- stage 1: decode one token (straight-line; results are only used by lanes in
+        //      S_DECODE, the others compute on garbage and discard) ---------------------------
+        const bool dec = state == S_DECODE;
+        SFB_STAT(tokens);
+        const uint32_t ip0 = br.ip;   // token start (slow path only)
+        const uint32_t bo0 = br.bo;   // < 32
+        const uint32_t bits = br.peek();
+        const uint32_t e = lut_lookup<C::ROOT_LIT, C::POOL_OFF, C::POOL>(lut, C::LIT_OFF, bits);
+        const uint32_t L = e & 15u;
+        const bool is_len = (e & 0x8000u) != 0;           // (L != 0 for every direct entry)
+        const uint32_t xb = is_len ? ((e >> 12) & 7u) : 0u;
+        uint32_t value = ((e >> 4) & 0xffu) + (is_len ? 3u + ((bits >> L) & ((1u << xb) - 1u)) : 0u);
+        const uint32_t used1 = L + xb;
+        const uint32_t dbits = br.peek_at(bo0 + used1);   // bo0 + used1 <= 31 + 20
+        const uint32_t de = lut_lookup<C::ROOT_DIST, C::POOL_OFF, C::POOL>(lut, C::DIST_OFF, dbits);
+        const uint32_t dL = de & 15u;
+        const uint32_t dsym = (de >> 4) & 31u;
+        const uint32_t dinfo = s_dist_info[dsym];
+        const uint32_t dxb = dinfo >> 16;
+        uint32_t dist = (dinfo & 0xffffu) + ((dbits >> dL) & ((1u << dxb) - 1u));
+        // kinds: literal (bits 12-15 clear), end of block, length; everything else is "slow"
+        bool eob = (e & 0xF000u) == E_KIND_EOB;
+        bool slow = (L == 0) | ((e & 0xB000u) == E_KIND_BAD) |       // no code / 286,287
+                    (is_len & ((dL == 0) | (dsym >= 30u)));          // no distance code / 30,31
+        if (dec) br.skip(used1 + (is_len ? dL + dxb : 0u));
+        br.norm2();
+        if (br.tail) slow |= br.overrun();
+        bool is_match = is_len;
+        if (dec & slow) {
+          // anything the fast path cannot vouch for: redo this token exactly
+          SFB_STAT(slow_tokens);
+          const uint64_t tok_pos = static_cast<uint64_t>(
+              8ll * (static_cast<int64_t>(ip0) - 20 - static_cast<int64_t>(br.lead0)) + bo0);
+          const SlowToken t = slow_token(m.lens, br.begin(), tok_pos, br.total_bits());
+          if (t.status != ST_SUCCESS) {
+            status = t.status;
+            state = S_DONE;
+          } else {
+            is_match = t.kind == 2;
+            eob = t.kind == 1;
+            value = static_cast<uint32_t>(t.value);
+            dist = static_cast<uint32_t>(t.dist);
+            br.seek_bit(t.next);
+          }
+        }
+        // ---- stage 2: merge the chunk decided in the previous iteration ----------------------
+        if (pn) {
+          const uint64_t s8 = (pw0 >> psh) | ((pw1 << 1) << (63 - psh));
+          ow.append(s8, pn);
+          pn = 0;
+        }
+        // ---- stage 3: act on the token (the output position is up to date now) ---------------
         if (state == S_DECODE) {
-          SFB_STAT(tokens);
-          // br.bo < 32 here (norm() ran at the end of the previous token)
-          const uint32_t ip0 = br.ip;   // token start (slow path only)
-          const uint32_t bo0 = br.bo;
-          uint32_t slow, is_match = 0, eob = 0;
-          uint32_t value, dist = 0;
-          uint32_t bits = br.peek();
-          const uint32_t e = lut_lookup<C::ROOT_LIT, C::POOL_OFF>(lut, C::LIT_OFF, bits);
-          const uint32_t L = e & 15u;
-          slow = (L == 0);
-          bits >>= L;
-          value = (e >> 4) & 0xffu;
-          uint32_t used = L;
-          if (e & 0xF000u) {            // not a literal: end of block, length code, or oddity
-            if (e & 0x8000u) {
-              if (L) {
-                is_match = 1;
-                const uint32_t xb = (e >> 12) & 7u;
-                value += 3u + (bits & ((1u << xb) - 1u));
-                br.skip(L + xb);
-                br.norm();
-                bits = br.peek();
-                const uint32_t de = lut_lookup<C::ROOT_DIST, C::POOL_OFF>(lut, C::DIST_OFF, bits);
-                const uint32_t dL = de & 15u;
-                const uint32_t dsym = (de >> 4) & 31u;
-                slow = (dL == 0) | (dsym >= 30u);
-                const uint32_t dinfo = s_dist_info[dsym];
-                const uint32_t dxb = dinfo >> 16;
-                dist = (dinfo & 0xffffu) + ((bits >> dL) & ((1u << dxb) - 1u));
-                used = dL + dxb;
-              }
-            } else if ((e & 0xF000u) == E_KIND_EOB) {
-              eob = 1;
-            } else {
-              slow = 1;                 // symbols 286 / 287
-            }
-          }
-          br.skip(used);
-          br.norm();
-          if (br.tail) slow |= br.overrun();
-          if (slow) {
-            // anything the fast path cannot vouch for: redo this token exactly
-            SFB_STAT(slow_tokens);
-            const uint64_t tok_pos = static_cast<uint64_t>(
-                8ll * (static_cast<int64_t>(ip0) - 12 - static_cast<int64_t>(br.lead0)) + bo0);
-            const SlowToken t = slow_token(m.lens, br.begin(), tok_pos, br.total_bits());
-            if (t.status != ST_SUCCESS) {
-              status = t.status;
+          if (eob) {
+            status = ST_SUCCESS;
+            state = final_block ? S_DONE : S_HEADER;
+          } else if (is_match) {
+            if (dist > ow.written()) {            // src/decompress.cpp:178-180
+              status = ST_INVALID_DISTANCE;
               state = S_DONE;
-            } else {
-              is_match = t.kind == 2;
-              eob = t.kind == 1;
-              value = static_cast<uint32_t>(t.value);
-              dist = static_cast<uint32_t>(t.dist);
-              br.seek_bit(t.next);
-            }
-          }
-          if (state == S_DECODE) {
-            if (eob) {
-              status = ST_SUCCESS;
-              state = final_block ? S_DONE : S_HEADER;
-            } else if (is_match) {
-              if (dist > ow.written()) {          // src/decompress.cpp:178-180
-                status = ST_INVALID_DISTANCE;
-                state = S_DONE;
-              } else if (ow.room() < value) {     // :181-183 (no partial copy)
-                status = ST_DST_TOO_SMALL;
-                state = S_DONE;
-              } else {
-                mlen = value;
-                mdist = dist;
-                state = S_MATCH;
-              }
-            } else if (ow.room() < 1) {           // decompress_literal, :150-152
+            } else if (ow.room() < value) {       // :181-183 (no partial copy)
               status = ST_DST_TOO_SMALL;
               state = S_DONE;
             } else {
-              chunk = value;
-              n = 1;
+              mlen = value;
+              mdist = dist;
+              state = S_MATCH;
             }
+          } else if (ow.room() < 1) {             // decompress_literal, :150-152
+            status = ST_DST_TOO_SMALL;
+            state = S_DONE;
+          } else {
+            pw0 = value;
+            pw1 = 0;
+            psh = 0;
+            pn = 1;
           }
         }
-        __syncwarp();
-        // ---- stage 2: up to 8 source bytes for lanes that are copying ------------------------
+        // ---- stage 4: fetch up to 8 source bytes for lanes that are copying ------------------
         if (state == S_MATCH) {
           // copy_from_before (src/decompress.cpp:388-398), <= 8 bytes per iteration
           const uint32_t vs = ow.vpos - mdist;
           const uint32_t wv = vs & ~7u;
           const uint32_t sh = 8 * (vs & 7u);
-          uint64_t s8;
           if (mdist >= 15) {
-            // both source words are already in memory (strictly below the open word)
-            const uint64_t w0 = *reinterpret_cast<const uint64_t*>(ow.al + wv);
-            const uint64_t w1 = *reinterpret_cast<const uint64_t*>(ow.al + wv + 8);
-            s8 = (w0 >> sh) | ((w1 << 1) << (63 - sh));
+            // both source words are already in memory (strictly below the open word);
+            // they are shifted together when the chunk is merged, one iteration from now
+            pw0 = *reinterpret_cast<const uint64_t*>(ow.al + wv);
+            pw1 = *reinterpret_cast<const uint64_t*>(ow.al + wv + 8);
+            psh = sh;
           } else {
-            s8 = ow.word_at(wv) >> sh;
+            uint64_t s8 = ow.word_at(wv) >> sh;
             if (sh) s8 |= ow.word_at(wv + 8) << (64 - sh);
             if (mdist < 8) {  // overlapping: replicate the mdist-byte period
               s8 &= low_bytes_mask(mdist);
@@ -984,30 +1032,31 @@ inflate_lanes_kernel(const BatchArgs a)
               s8 |= shl64(s8, 16 * mdist);
               s8 |= shl64(s8, 32 * mdist);
             }
+            pw0 = s8;
+            pw1 = 0;
+            psh = 0;
           }
-          n = mlen < 8 ? mlen : 8;
-          chunk = s8;
-          mlen -= n;
+          pn = mlen < 8 ? mlen : 8;
+          mlen -= pn;
           if (mlen == 0) state = S_DECODE;
         } else if (state == S_STORED) {
           // stored payload: up to 8 bytes from the input (src/decompress.cpp:434)
           const unsigned k = static_cast<unsigned>(reinterpret_cast<uintptr_t>(copy_src) & 7u);
           const uint8_t* wa = copy_src - k;
           uint64_t s8 = *reinterpret_cast<const uint64_t*>(wa) >> (8 * k);
-          n = copy_left < 8 ? copy_left : 8;
-          if (k && n > 8 - k) s8 |= *reinterpret_cast<const uint64_t*>(wa + 8) << (64 - 8 * k);
-          chunk = s8;
-          copy_src += n;
-          copy_left -= n;
+          pn = copy_left < 8 ? copy_left : 8;
+          if (k && pn > 8 - k) s8 |= *reinterpret_cast<const uint64_t*>(wa + 8) << (64 - 8 * k);
+          pw0 = s8;
+          pw1 = 0;
+          psh = 0;
+          copy_src += pn;
+          copy_left -= pn;
           if (copy_left == 0) {
             br.init_at(static_cast<uint32_t>(copy_src - br.base), 0);
             status = ST_SUCCESS;
             state = final_block ? S_DONE : S_HEADER;
           }
         }
-        __syncwarp();
-        // ---- stage 3: merge into the write-combining word ------------------------------------
-        if (n) ow.append(chunk, n);
       }
       if (state == S_DONE && live) {
         ow.flush_tail();
