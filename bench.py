@@ -332,10 +332,19 @@ def main():
                "d2h_bytes_per_step": int(w["total_out"] + 9 * n),
                "steps": e_steps, "timer": "host wall clock around sfb200_decompress_batch_host (pinned buffers)"}
 
+    # per-pass device time (CUDA events recorded inside the C-ABI call on its stream), taken
+    # on a few extra steps after the timed region so that the synchronising query stays out of it
+    pass_ms = []
+    for _ in range(3):
+        step()
+        pass_ms.append(ctx.last_pass_ms())
+    clear_ms, p1_ms, p2_ms = [float(x) for x in np.mean(np.array(pass_ms), axis=0)]
+
     peak, peak_src = measured_peak_gbs()
     k_ms = float(np.mean(kern_ms))
     algo_bytes = w["total_in"] + w["total_out"]
     achieved = algo_bytes / (k_ms * 1e-3) / 1e9
+    dominant = "huff_lanes_kernel (pass 1)" if p1_ms >= p2_ms else "lz_resolve_kernel (pass 2)"
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -353,8 +362,12 @@ def main():
                    "launch": ctx.launch_info()},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "inflate_lanes_kernel", "kernel_ms": k_ms,
+                     "kernel": dominant, "kernel_ms": k_ms,
                      "algorithmic_bytes": algo_bytes,
+                     "note": "achieved = (compressed read + decompressed written) / device time of the "
+                             "WHOLE step (scratch clear + pass 1 + pass 2), not of the dominant kernel alone",
+                     "passes_ms": {"clear": clear_ms, "huff_lanes_kernel": p1_ms,
+                                   "lz_resolve_kernel": p2_ms},
                      "frac_of_nominal_8TBs": achieved / 8000.0},
         "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
         "wall_s_timed_region": t_wall,

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SFB200_ABI_VERSION 1
+#define SFB200_ABI_VERSION 2
 
 /* starflate::DecompressStatus, numeric values preserved (src/decompress.hpp:13-23). */
 enum sfb200_status {
@@ -63,6 +63,8 @@ int sfb200_abi_version(void);
  *
  * Stream i reads  src_base[src_off[i] .. src_off[i]+src_len[i])  and writes
  *                 dst_base[dst_off[i] .. dst_off[i]+dst_cap[i]);
+ * `dst_bytes` is the size of the buffer at dst_base (every dst_off[i]+dst_cap[i] <= dst_bytes);
+ * it sizes the only scratch the decoder needs, one bit per dst byte (kept in the context).
  * status[i] receives the DecompressStatus, written[i] (may be NULL) the bytes produced.
  * All six arrays are DEVICE pointers; regions of different streams must not overlap.
  * Replaces one reference call per stream: decompress(src_i, dst_i) (src/decompress.cpp:402).
@@ -72,7 +74,7 @@ int sfb200_abi_version(void);
  * `cuda_stream` is a cudaStream_t (NULL = default stream); the call is asynchronous. */
 int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
                                    const uint64_t* src_off, const uint64_t* src_len,
-                                   uint8_t* dst_base, const uint64_t* dst_off,
+                                   uint8_t* dst_base, uint64_t dst_bytes, const uint64_t* dst_off,
                                    const uint64_t* dst_cap, uint8_t* status,
                                    uint64_t* written, uint64_t n, void* cuda_stream);
 
@@ -102,13 +104,24 @@ int sfb200_checksum_batch_device(sfb200_ctx* ctx, const uint8_t* base, const uin
 /* Tuning / introspection (bench harness only; not part of the reference surface). */
 typedef struct sfb200_launch_info {
   int sm_count;
+  /* pass 1, huff_lanes_kernel (one lane per stream) */
   int warps_per_cta;
   int ctas_per_sm;
   int smem_bytes_per_cta;
   int regs_per_thread;
+  /* pass 2, lz_resolve_kernel (one warp per stream) */
+  int lz_threads_per_cta;
+  int lz_ctas_per_sm;
+  int lz_regs_per_thread;
   uint64_t kernel_launches; /* kernels launched by this context so far */
 } sfb200_launch_info;
 int sfb200_get_launch_info(sfb200_ctx* ctx, sfb200_launch_info* out);
+
+/* Device time of the most recent sfb200_decompress_batch_device call on this context, from CUDA
+ * events recorded on its stream inside that call (waits for the call to finish):
+ *   out3[0] scratch clearing (memsets), out3[1] pass 1 (huff_lanes_kernel),
+ *   out3[2] pass 2 (lz_resolve_kernel), milliseconds. */
+int sfb200_last_pass_ms(sfb200_ctx* ctx, float* out3);
 
 #ifdef __cplusplus
 }

@@ -34,7 +34,8 @@ _u64p = C.POINTER(C.c_uint64)
 class _LaunchInfo(C.Structure):
     _fields_ = [("sm_count", C.c_int), ("warps_per_cta", C.c_int), ("ctas_per_sm", C.c_int),
                 ("smem_bytes_per_cta", C.c_int), ("regs_per_thread", C.c_int),
-                ("kernel_launches", C.c_uint64)]
+                ("lz_threads_per_cta", C.c_int), ("lz_ctas_per_sm", C.c_int),
+                ("lz_regs_per_thread", C.c_int), ("kernel_launches", C.c_uint64)]
 
 
 _lib = None
@@ -62,14 +63,15 @@ def load_library() -> C.CDLL:
     lib.sfb200_last_error.argtypes = [C.c_void_p]
     lib.sfb200_last_error.restype = C.c_char_p
     lib.sfb200_decompress_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                                   C.c_void_p, C.c_uint64, C.c_void_p]
+                                                   C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p,
+                                                   C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     lib.sfb200_decompress_batch_host.argtypes = [C.c_void_p, _u8p, C.c_uint64, _u64p, _u64p, _u8p,
                                                  C.c_uint64, _u64p, _u64p, _u8p, _u64p, C.c_uint64]
     lib.sfb200_decompress.argtypes = [C.c_void_p, _u8p, C.c_size_t, _u8p, C.c_size_t, _u8p, _u64p]
     lib.sfb200_checksum_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                  C.c_void_p, C.c_uint64, C.c_void_p]
     lib.sfb200_get_launch_info.argtypes = [C.c_void_p, C.POINTER(_LaunchInfo)]
+    lib.sfb200_last_pass_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     _lib = lib
     return lib
 
@@ -122,7 +124,7 @@ class Context:
             stream = torch.cuda.current_stream(src.device).cuda_stream
         rc = self.lib.sfb200_decompress_batch_device(
             self.h, src.data_ptr(), src_off.data_ptr(), src_len.data_ptr(), dst.data_ptr(),
-            dst_off.data_ptr(), dst_cap.data_ptr(), status.data_ptr(),
+            dst.numel(), dst_off.data_ptr(), dst_cap.data_ptr(), status.data_ptr(),
             written.data_ptr() if written is not None else None, n, stream)
         self._check(rc, "sfb200_decompress_batch_device")
 
@@ -162,6 +164,12 @@ class Context:
                                         C.byref(st), C.byref(wr))
         self._check(rc, "sfb200_decompress")
         return st.value, d[:dst_cap].tobytes(), wr.value
+
+    def last_pass_ms(self):
+        """(clear_ms, pass1_ms, pass2_ms) of the most recent device-batch call (CUDA events)."""
+        out = (C.c_float * 3)()
+        self._check(self.lib.sfb200_last_pass_ms(self.h, out), "sfb200_last_pass_ms")
+        return float(out[0]), float(out[1]), float(out[2])
 
     def launch_info(self) -> dict:
         li = _LaunchInfo()

@@ -1,0 +1,354 @@
+// Pass 1 of the batched raw-DEFLATE decoder for sm_100a: the Huffman layer, ONE LANE PER STREAM.
+//
+// Replaces the reference's symbol loop decompress_block_huffman (src/decompress.cpp:197-242)
+// together with read_header, the stored-block branch and the dynamic table decode (all via
+// deflate_lane.cuh) — everything of decompress() except the bytes a back-reference copies, which
+// pass 2 (lz_warp.cuh) fills in.  Per-stream status and `written` are final after this pass.
+//
+// Why a lane and not a warp per stream: Huffman decode of one stream is a serial dependency
+// chain (bit window -> LUT -> code length -> next window).  A warp per stream spends one issue
+// slot per instruction on ONE token; a lane per stream retires up to 32 tokens per issued
+// instruction.  Why the LZ77 copy is NOT done here: with 32 streams per warp and 8 warps per SM
+// there are ~38k streams in flight, whose 32 KiB windows (1.2 GB) cannot stay in the 126 MB L2;
+// the one-pass lane kernel of earlier revisions spent its time waiting on DRAM for match
+// sources (ncu: 6.4 of 11 stall cycles per issue on long scoreboard, 26 GB read for 0.75 GB of
+// input).  The Huffman layer never reads the output, so this pass has no such dependency.
+//
+// Output of this pass, written IN PLACE into each stream's dst region (no token buffer, so the
+// scratch memory is bounded by 1 bit per dst byte whatever the data):
+//   * literal bytes and stored-block payload at their final positions;
+//   * for a match (length L, distance D) that starts at output position p: a 3-byte descriptor
+//     at dst[p..p+3):  byte0 = L - 3, byte1..2 = (D - 1) little endian  (L >= 3, so it fits);
+//     dst[p+3..p+L) is left unspecified (pass 2 overwrites all of dst[p..p+L));
+//   * bit (dst_off + p) of the match-head bitmap is set for every such p.
+// The reference's output-side checks (distance > written -> InvalidDistance, room ->
+// DstTooSmall; src/decompress.cpp:150-152,178-183) only need the output POSITION, which this
+// pass tracks, so they are made here, in the reference's order.
+//
+// Each lane owns
+//   * a register bit window (five 32-bit words, funnel-shift peeks, branch-free slide) fed from
+//     a 64-byte ring in shared memory that cp.async fills 16 bytes at a time, several tokens
+//     ahead of the reader (deflate_lane.cuh: BitReader),
+//   * a two-level decode LUT in shared memory, interleaved so that element j of lane l sits at
+//     u16 index j*32+l (lane pairs share a bank: at most 2-way conflicts on random lookups),
+//   * an 8-byte write-combining register for its output window in HBM and a 32-bit
+//     accumulator for its current bitmap word.
+// The code lengths of the current block live in a per-lane slice of a global scratch buffer,
+// which keeps the shared-memory footprint at LUT + ring: 896 B per lane -> 8 warps per SM.
+// Scattered per-lane memory instructions are what bounds this pass (every lane touches its own
+// 128-byte line, ~2 L1 cycles each), so the loop issues as few of them as it can: one 16-byte
+// cp.async per ~9 tokens, one 8-byte store per ~1.5 tokens, one bitmap RED per 32 output bytes.
+#pragma once
+
+#include "deflate_lane.cuh"
+
+namespace sfb {
+
+// ---------------------------------------------------------------------------------------------
+// Per-lane output window of pass 1.
+// Invariant: bytes [vpos & ~7, vpos) of the output live in the low bytes of `obuf` (its
+// higher bytes are unspecified); every byte below vpos & ~7 that pass 2 will not overwrite is
+// in memory.
+struct TokWin {
+  uint8_t* al;      // 8-byte aligned address of virtual position 0
+  uint32_t lead;    // dst start within the first word (0..7): virtual position of byte 0
+  uint32_t vpos;    // virtual position of the next byte to produce
+  uint32_t vend;    // virtual position one past the capacity
+  uint64_t obuf;
+  uint32_t* bm;     // bitmap word that holds the bit of output byte 0
+  uint32_t qml;     // (bit of output byte 0 within *bm) - lead, mod 2^32
+  uint32_t mword;   // index, from bm, of the bitmap word `macc` belongs to
+  uint32_t macc;    // head bits not yet merged into the bitmap
+
+  __device__ __forceinline__ void open(uint8_t* dst_base, uint64_t off, uint32_t cap, uint32_t* bits)
+  {
+    uint8_t* d = dst_base + off;
+    lead = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(d) & 7u);
+    al = d - lead;
+    vpos = lead;
+    vend = lead + cap;
+    obuf = 0;
+    bm = bits + (off >> 5);
+    qml = static_cast<uint32_t>(off & 31u) - lead;
+    mword = 0;
+    macc = 0;
+  }
+  __device__ __forceinline__ void park()
+  {
+    al = nullptr;
+    lead = vpos = vend = 0;
+    obuf = 0;
+    bm = nullptr;
+    qml = mword = macc = 0;
+  }
+
+  __device__ __forceinline__ uint32_t written() const { return vpos - lead; }
+  __device__ __forceinline__ uint32_t room() const { return vend - vpos; }
+
+  // store the word at 8-aligned virtual position wv
+  __device__ __forceinline__ void store_word(uint32_t wv, uint64_t v)
+  {
+    if (wv >= lead) {
+      *reinterpret_cast<uint64_t*>(al + wv) = v;
+    } else {  // first word of an unaligned dst: bytes before `lead` are not ours
+      for (uint32_t b = lead; b < 8; ++b) al[b] = static_cast<uint8_t>(v >> (8 * b));
+    }
+  }
+
+  // The one output step of a token: append the n (0..3) low bytes of `chunk` at the cursor,
+  // then move the cursor `skipn` bytes further over bytes pass 2 will produce (the body of a
+  // match).  A word the cursor leaves is stored whole: its bytes past the appended ones all
+  // belong to the match body, so any value will do there.
+  __device__ __forceinline__ void emit(uint32_t chunk, uint32_t n, uint32_t skipn)
+  {
+    const uint32_t k = vpos & 7u;
+    const uint32_t sh = 8u * k;
+    const uint64_t merged = (obuf & ~(~0ull << sh)) | (static_cast<uint64_t>(chunk) << sh);
+    const uint32_t np = vpos + n + skipn;
+    const uint32_t wv = vpos & ~7u;
+    const bool leaves = (np & ~7u) != wv;
+    const bool spill = k + n > 8u;                         // the chunk reaches into the next word
+    const uint32_t carry = chunk >> ((64u - sh) & 31u);    // ... with these bytes (sh >= 48 then)
+    if (leaves) {
+      store_word(wv, merged);
+      if (spill && (np & ~7u) != wv + 8u) store_word(wv + 8u, carry);  // skipped past that word too
+    }
+    obuf = leaves ? (spill ? carry : 0u) : merged;
+    vpos = np;
+  }
+
+  __device__ __forceinline__ void flush_bits()
+  {
+    // (bitmap words at the edges of a dst region are shared with the neighbouring streams)
+    if (macc) atomicOr(bm + mword, macc);
+    macc = 0;
+  }
+  // a match starts at the cursor
+  __device__ __forceinline__ void mark_head()
+  {
+    const uint32_t bidx = vpos + qml;
+    const uint32_t w = bidx >> 5;
+    if (w != mword) {
+      flush_bits();
+      mword = w;
+    }
+    macc |= 1u << (bidx & 31u);
+  }
+
+  // pending bytes of the open word -> memory, bytewise (the window stays as it is)
+  __device__ __forceinline__ void spill_pending() const
+  {
+    const uint32_t wv = vpos & ~7u;
+    uint32_t b = wv < lead ? lead : wv;
+    for (; b < vpos; ++b) al[b] = static_cast<uint8_t>(obuf >> (8 * (b - wv)));
+  }
+  // the cursor was moved over bytes written straight to memory: re-read the open word
+  __device__ __forceinline__ void jump(uint32_t n)
+  {
+    vpos += n;
+    const uint32_t wv = vpos & ~7u;
+    obuf = 0;
+    for (uint32_t b = wv < lead ? lead : wv; b < vpos; ++b)
+      obuf |= static_cast<uint64_t>(al[b]) << (8 * (b - wv));
+  }
+  // called once, when the stream ends for any reason
+  __device__ __forceinline__ void flush_tail()
+  {
+    spill_pending();
+    flush_bits();
+  }
+};
+
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src)
+{
+  const uint32_t lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v), src);
+  const uint32_t hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), src);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+#ifdef SFB_CPU_EMU
+constexpr uint32_t LANES = 1;   // tests/cpu_emu runs one lane per "warp"
+#else
+constexpr uint32_t LANES = 32;
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// The pass-1 kernel.  One lane per stream, 32 streams per warp, warps pull groups of 32
+// consecutive streams from a global counter.
+//
+// Control structure (kept free of `break`s so that the warp reconverges after every stage):
+//   rounds:  lanes that need a block header parse it (lock-step when several do); stored
+//            blocks are then copied by the whole warp, one block at a time, coalesced; then
+//   tokens:  while any lane is inside a Huffman block, every iteration each such lane decodes
+//            exactly one token (literal | end of block | match) and emits it through the one
+//            emit() site; lanes waiting for the next header (or finished) idle until the
+//            round ends.
+template <class C>
+__global__ void __launch_bounds__(C::WARPS * 32)
+huff_lanes_kernel(const BatchArgs a)
+{
+#ifdef SFB_CPU_EMU
+  uint8_t* const smem = reinterpret_cast<uint8_t*>(SFB_EMU_SMEM);  // tests/cpu_emu: logic-only build
+#else
+  extern __shared__ __align__(16) uint8_t smem[];
+#endif
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = static_cast<int>(threadIdx.x & 31u);
+  const int warp = static_cast<int>(threadIdx.x >> 5);
+  uint32_t* const s_dist_info = reinterpret_cast<uint32_t*>(smem + C::WARPS * C::WARP_BYTES);
+  for (unsigned t = threadIdx.x; t < 32; t += blockDim.x) s_dist_info[t] = c_dist_info[t];
+  __syncthreads();
+
+  uint8_t* const warp_smem = smem + warp * C::WARP_BYTES;
+  LaneMem m;
+  m.lut = reinterpret_cast<uint16_t*>(warp_smem) + lane;
+  m.lens = a.lens_scratch +
+           (static_cast<size_t>(blockIdx.x) * C::WARPS + static_cast<size_t>(warp)) * (SCRATCH_WORDS * 32) +
+           lane;
+  const uint16_t* const lut = m.lut;
+  uint8_t* const ring = warp_smem + C::WARP_U16 * 2 + lane * 16;
+
+  const uint64_t n_groups = (a.n + 31) / 32;
+  for (;;) {
+    unsigned long long g = 0;
+    if (lane == 0) g = atomicAdd(a.group_counter, 1ull);
+    g = __shfl_sync(FULL, g, 0);
+    if (g >= n_groups) break;
+    const uint64_t idx = g * 32 + static_cast<uint64_t>(lane);
+
+    int state = S_DONE;
+    int status = ST_SUCCESS;
+    BitReader br;
+    TokWin ow;
+    // lanes without a stream still run the (predicated-off) decode stage
+    br.park(ring);
+    ow.park();
+    uint32_t final_block = 0;
+    int n_lit = 0, n_dist = 0;
+    const uint8_t* copy_src = nullptr;
+    uint32_t copy_left = 0;
+    bool live = idx < a.n;
+    if (live) {
+      const uint64_t slen = a.src_len[idx];
+      const uint64_t cap = a.dst_cap[idx];
+      if (slen >= 0xffffff00ull || cap >= 0xffffff00ull) {
+        a.status[idx] = ST_ERROR;  // outside the batch precondition
+        a.written[idx] = 0;
+        live = false;
+      } else {
+        br.open(a.src_base + a.src_off[idx], static_cast<uint32_t>(slen), ring);
+        ow.open(a.dst_base, a.dst_off[idx], static_cast<uint32_t>(cap), a.match_bits);
+        state = S_HEADER;
+      }
+    }
+
+    while (__any_sync(FULL, state != S_DONE)) {
+      if (state == S_HEADER) {
+        state = parse_block_header<C>(br, m, ow.room(), final_block, n_lit, n_dist, copy_src,
+                                      copy_left, &status);
+      }
+      // ---- stored blocks (src/decompress.cpp:434): the warp copies them, one at a time ------
+      for (unsigned sm = __ballot_sync(FULL, state == S_STORED); sm; sm &= sm - 1) {
+        const int owner = __ffs(static_cast<int>(sm)) - 1;
+        if (lane == owner) ow.spill_pending();
+        const uint8_t* s = reinterpret_cast<const uint8_t*>(
+            shfl_u64(reinterpret_cast<uint64_t>(copy_src), owner));
+        uint8_t* d = reinterpret_cast<uint8_t*>(
+            shfl_u64(reinterpret_cast<uint64_t>(ow.al + ow.vpos), owner));
+        const uint32_t len = __shfl_sync(FULL, copy_left, owner);
+        __syncwarp();
+        for (uint32_t i = static_cast<uint32_t>(lane); i < len; i += LANES) d[i] = s[i];
+        __syncwarp();
+        if (lane == owner) {
+          ow.jump(len);
+          br.init_at(static_cast<uint32_t>(copy_src + len - br.base), 0);
+          status = ST_SUCCESS;
+          state = final_block ? S_DONE : S_HEADER;
+        }
+      }
+      // ---- token iterations (all 32 lanes stay in this loop together) -----------------------
+      uint32_t it = 0;
+      while (__any_sync(FULL, state == S_DECODE)) {
+        // ---- decode one token (straight-line; results are only used by lanes in S_DECODE,
+        //      the others compute on stale data and discard) ----------------------------------
+        const bool dec = state == S_DECODE;
+        SFB_STAT(tokens);
+        const uint32_t rp0 = br.rp;   // token start (slow path only)
+        const uint32_t bo0 = br.bo;   // < 32
+        const uint32_t bits = br.peek();
+        const uint32_t bits_hi = funnel_r(br.w1, br.w2, bo0);
+        const uint32_t e = lut_lookup<C::ROOT_LIT, C::POOL_OFF, C::POOL>(lut, C::LIT_OFF, bits);
+        const uint32_t L = e & 15u;
+        const bool is_len = (e & 0x8000u) != 0;           // (pointers were resolved: L != 0 here)
+        const uint32_t xb = (e >> 12) & 7u;               // 0 for literals
+        uint32_t value = ((e >> 4) & 0xffu) + (is_len ? 3u + ((bits >> L) & ((1u << xb) - 1u)) : 0u);
+        const uint32_t used1 = L + xb;
+        const uint32_t dbits = br.peek_at(bo0 + used1);   // bo0 + used1 <= 31 + 20
+        const uint32_t de = lut_lookup<C::ROOT_DIST, C::POOL_OFF, C::POOL>(lut, C::DIST_OFF, dbits);
+        const uint32_t dL = de & 15u;
+        const uint32_t dinfo = s_dist_info[(de >> 4) & 31u];
+        const uint32_t dxb = dinfo >> 16;
+        uint32_t dist = (dinfo & 0xffffu) + ((dbits >> dL) & ((1u << dxb) - 1u));
+        // anything that is not a plain literal / length+distance is "slow"
+        bool slow = (L == 0) | (is_len & (dL == 0));
+        if (dec) br.skip(used1 + (is_len ? dL + dxb : 0u));
+        br.norm2();
+        if (br.tail()) slow |= br.real_left() < 0;
+        bool is_match = is_len;
+        bool eob = false;
+        if (dec & slow) {
+          // end of block, or anything the fast path cannot vouch for: redo this token exactly
+          SFB_STAT(slow_tokens);
+          const int64_t tok_pos = 32ll * (static_cast<int64_t>(rp0) - 5) -
+                                  8ll * static_cast<int64_t>(br.lead0) + static_cast<int64_t>(bo0);
+          const SlowToken t = slow_token(m.lens, (static_cast<uint64_t>(bits_hi) << 32) | bits,
+                                         static_cast<int64_t>(br.total_bits()) - tok_pos);
+          if (t.status != ST_SUCCESS) {
+            status = t.status;
+            state = S_DONE;
+          } else {
+            is_match = t.kind == 2;
+            eob = t.kind == 1;
+            value = static_cast<uint32_t>(t.value);
+            dist = static_cast<uint32_t>(t.dist);
+            br.seek_bit(static_cast<uint64_t>(tok_pos) + t.used);
+          }
+        }
+        if (it & 1u) br.stage_step();
+        ++it;
+        // ---- act on the token ----------------------------------------------------------------
+        uint32_t chunk = 0, n = 0, skipn = 0;
+        if (state == S_DECODE) {
+          if (eob) {
+            status = ST_SUCCESS;
+            state = final_block ? S_DONE : S_HEADER;
+          } else {
+            const bool bad_dist = is_match && dist > ow.written();   // src/decompress.cpp:178-180
+            const uint32_t need = is_match ? value : 1u;             // :181-183 / :150-152
+            if (bad_dist | (ow.room() < need)) {                     // (no partial copy)
+              status = bad_dist ? ST_INVALID_DISTANCE : ST_DST_TOO_SMALL;
+              state = S_DONE;
+            } else if (is_match) {
+              ow.mark_head();
+              chunk = (value - 3u) | ((dist - 1u) << 8);
+              n = 3;
+              skipn = value - 3u;
+            } else {
+              chunk = value;
+              n = 1;
+            }
+          }
+        }
+        ow.emit(chunk, n, skipn);
+      }
+      if (state == S_DONE && live) {
+        ow.flush_tail();
+        a.status[idx] = static_cast<uint8_t>(status);
+        a.written[idx] = ow.written();
+        live = false;
+      }
+    }
+  }
+}
+
+}  // namespace sfb

@@ -34,6 +34,8 @@ static inline unsigned __brev(unsigned v)
 template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
 template <class T> static inline T __shfl_down_sync(unsigned, T, int) { return T{}; }
 static inline int __any_sync(unsigned, int p) { return p != 0; }
+static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __all_sync(unsigned, int p) { return p != 0; }
 static inline void __syncthreads() {}
 static inline void __syncwarp() {}
@@ -41,5 +43,11 @@ static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long 
 {
   const unsigned long long old = *p;
   *p = old + v;
+  return old;
+}
+static inline unsigned atomicOr(unsigned* p, unsigned v)
+{
+  const unsigned old = *p;
+  *p = old | v;
   return old;
 }

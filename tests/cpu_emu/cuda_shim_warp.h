@@ -1,0 +1,68 @@
+// TEST INFRASTRUCTURE ONLY.
+// Lets g++ compile starflate_b200/csrc/lz_warp.cuh (a warp-cooperative kernel) for the host: the
+// 32 lanes of one warp run as 32 host threads and every warp primitive (__shfl_sync,
+// __any_sync, __all_sync, __syncwarp ...) is a rendezvous on a std::barrier, so the exchange
+// pattern, the divergence structure and the memory ordering the kernel relies on
+// (stores -> __syncwarp -> loads by other lanes) are exercised as written.  Never built into,
+// loaded by, or reachable from the product library — it is not a fallback.
+#pragma once
+#include <atomic>
+#include <barrier>
+#include <cstdint>
+#include <cstring>
+
+#define __device__
+#define __global__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
+#define __launch_bounds__(...)
+
+struct emu_dim3 { unsigned x = 0, y = 0, z = 0; };
+static thread_local emu_dim3 threadIdx, blockIdx;
+static thread_local emu_dim3 blockDim, gridDim;
+
+struct EmuWarp {
+  std::barrier<> bar{32};
+  uint64_t slot[32];
+};
+static EmuWarp* emu_warp = nullptr;
+
+template <class T> static inline T emu_exchange(T v, unsigned src)
+{
+  const unsigned lane = threadIdx.x & 31u;
+  uint64_t raw = 0;
+  std::memcpy(&raw, &v, sizeof(T));
+  emu_warp->slot[lane] = raw;
+  emu_warp->bar.arrive_and_wait();
+  raw = emu_warp->slot[src & 31u];
+  emu_warp->bar.arrive_and_wait();
+  T r;
+  std::memcpy(&r, &raw, sizeof(T));
+  return r;
+}
+template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return emu_exchange(v, static_cast<unsigned>(src)); }
+template <class T> static inline T __shfl_down_sync(unsigned, T v, int d)
+{
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned src = lane + static_cast<unsigned>(d);
+  return emu_exchange(v, src > 31u ? lane : src);
+}
+static inline unsigned __ballot_sync(unsigned, int p)
+{
+  const unsigned lane = threadIdx.x & 31u;
+  emu_warp->slot[lane] = p ? 1u : 0u;
+  emu_warp->bar.arrive_and_wait();
+  unsigned m = 0;
+  for (unsigned i = 0; i < 32; ++i) m |= static_cast<unsigned>(emu_warp->slot[i]) << i;
+  emu_warp->bar.arrive_and_wait();
+  return m;
+}
+static inline int __any_sync(unsigned mask, int p) { return __ballot_sync(mask, p) != 0; }
+static inline int __all_sync(unsigned mask, int p) { return __ballot_sync(mask, p) == 0xffffffffu; }
+static inline void __syncwarp() { emu_warp->bar.arrive_and_wait(); }
+static inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz(static_cast<unsigned>(v)); }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v)
+{
+  return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
+}

@@ -1,4 +1,7 @@
-// TEST INFRASTRUCTURE ONLY — CPU emulation of the CUDA kernel's lane logic (see cuda_shim.h).
+// TEST INFRASTRUCTURE ONLY — CPU emulation of the CUDA kernels' logic (see cuda_shim.h).
+// Pass 1 (huff_lanes.cuh) runs one emulated lane per stream; pass 2 is either the real kernel
+// on 32 host threads (emu_lz.cpp, mode 1) or a scalar restatement of the in-place token
+// format (mode 0, fast: it checks what pass 1 wrote, not how pass 2 is implemented).
 #define SFB_CPU_EMU 1
 #include "cuda_shim.h"
 
@@ -9,25 +12,47 @@ static thread_local uint16_t* emu_smem = nullptr;
 #define SFB_EMU_SMEM emu_smem
 static unsigned long long emu_stat_tokens = 0, emu_stat_slow_tokens = 0;
 #define SFB_STAT(name) (++emu_stat_##name)
-#include "../../starflate_b200/csrc/inflate_lanes.cuh"
+#include "../../starflate_b200/csrc/huff_lanes.cuh"
 
 using EmuCfg = sfb::Cfg<SFB_EMU_ROOT_LIT, SFB_EMU_ROOT_DIST, SFB_EMU_POOL, 1>;
 
+extern "C" void emu_lz_resolve(uint8_t* dst_base, const uint64_t* dst_off, const uint64_t* written,
+                               const uint32_t* match_bits, uint64_t n);
+
+// the in-place token format of huff_lanes.cuh, resolved byte by byte
+static void scalar_resolve(uint8_t* dst_base, uint64_t off, uint64_t written, const uint32_t* bits)
+{
+  uint8_t* d = dst_base + off;
+  uint64_t p = 0;
+  while (p < written) {
+    const uint64_t k = off + p;
+    if ((bits[k >> 5] >> (k & 31)) & 1u) {
+      const unsigned len = d[p] + 3u;
+      const unsigned dist = (d[p + 1] | (d[p + 2] << 8)) + 1u;
+      for (unsigned j = 0; j < len; ++j) d[p + j] = d[p + j - dist];
+      p += len;
+    } else {
+      ++p;
+    }
+  }
+}
+
 // Each stream is run in private, padded copies of its src/dst regions that keep the original
-// address alignment (mod 16).  The kernel's aligned word accesses may legitimately touch the
-// padding of src (reads) but must never modify anything outside [dst, dst+cap): the canaries
-// around dst are verified.  Returns 0, or 1000+i if stream i wrote out of bounds.
+// address alignment (mod 16) and the original dst offset modulo 32 (the bitmap phase).  The
+// kernels' aligned word accesses may legitimately touch the padding of src (reads) but must
+// never modify anything outside [dst, dst+cap): the canaries around dst are verified.
+// Returns 0, or 1000+i if stream i wrote out of bounds.
 extern "C" int emu_decompress_batch(const uint8_t* src, const uint64_t* src_off,
                                     const uint64_t* src_len, uint8_t* dst,
                                     const uint64_t* dst_off, const uint64_t* dst_cap,
-                                    uint8_t* status, uint64_t* written, uint64_t n)
+                                    uint8_t* status, uint64_t* written, uint64_t n, int warp_pass2)
 {
   std::vector<uint16_t> smem(EmuCfg::SMEM_BYTES / 2 + 64, 0xDEAD);
   std::vector<uint32_t> lens(sfb::SCRATCH_WORDS * 32, 0xDEADBEEFu);
   emu_smem = smem.data();
   blockDim.x = 1;  // one emulated lane
   gridDim.x = 1;
-  constexpr size_t PAD = 64;
+  constexpr size_t PAD = 96;
   for (uint64_t i = 0; i < n; ++i) {
     const uint8_t* s = src + src_off[i];
     uint8_t* d = dst + dst_off[i];
@@ -42,23 +67,32 @@ extern "C" int emu_decompress_batch(const uint8_t* src, const uint64_t* src_off,
     uint8_t* dp = place(dbuf, d);
     if (src_len[i]) std::memcpy(sp, s, src_len[i]);
     if (dst_cap[i]) std::memcpy(dp, d, dst_cap[i]);
+    const uint64_t doff = dst_off[i] & 31u;  // keep the bitmap phase of the real layout
+    uint8_t* dbase = dp - doff;
+    std::vector<uint32_t> bits((doff + dst_cap[i]) / 32 + 2, 0u);
     unsigned long long counter = 0;
     const uint64_t zero = 0;
+    uint64_t wr = 0;
     sfb::BatchArgs a;
     a.src_base = sp;
     a.src_off = &zero;
     a.src_len = &src_len[i];
-    a.dst_base = dp;
-    a.dst_off = &zero;
+    a.dst_base = dbase;
+    a.dst_off = &doff;
     a.dst_cap = &dst_cap[i];
     a.status = &status[i];
-    a.written = written ? &written[i] : nullptr;
+    a.written = &wr;
     a.n = 1;
     a.group_counter = &counter;
     a.lens_scratch = lens.data();
+    a.match_bits = bits.data();
     threadIdx.x = 0;
     blockIdx.x = 0;
-    sfb::inflate_lanes_kernel<EmuCfg>(a);
+    sfb::huff_lanes_kernel<EmuCfg>(a);
+    if (wr > dst_cap[i]) return 2000 + static_cast<int>(i);
+    if (warp_pass2) emu_lz_resolve(dbase, &doff, &wr, bits.data(), 1);
+    else scalar_resolve(dbase, doff, wr, bits.data());
+    if (written) written[i] = wr;
     for (uint8_t* q = dbuf.data(); q < dp; ++q)
       if (*q != 0xC3) return 1000 + static_cast<int>(i);
     for (uint8_t* q = dp + dst_cap[i]; q < dbuf.data() + dbuf.size(); ++q)

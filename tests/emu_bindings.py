@@ -15,14 +15,18 @@ _u8p = C.POINTER(C.c_uint8)
 _u64p = C.POINTER(C.c_uint64)
 
 
-def build(root_lit=8, root_dist=6, pool=128) -> str:
+def build(root_lit=8, root_dist=6, pool=96) -> str:
     out = os.path.join(HERE, "cpu_emu", f"libemu_{root_lit}_{root_dist}_{pool}.so")
-    srcs = [os.path.join(HERE, "cpu_emu", "emu.cpp"), os.path.join(HERE, "cpu_emu", "cuda_shim.h"),
-            os.path.join(ROOT, "starflate_b200", "csrc", "inflate_lanes.cuh")]
+    emu = os.path.join(HERE, "cpu_emu")
+    csrc = os.path.join(ROOT, "starflate_b200", "csrc")
+    srcs = [os.path.join(emu, "emu.cpp"), os.path.join(emu, "emu_lz.cpp"),
+            os.path.join(emu, "cuda_shim.h"), os.path.join(emu, "cuda_shim_warp.h"),
+            os.path.join(csrc, "deflate_lane.cuh"), os.path.join(csrc, "huff_lanes.cuh"),
+            os.path.join(csrc, "lz_warp.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
-        subprocess.check_call(["g++", "-std=c++20", "-O2", "-fPIC", "-shared",
+        subprocess.check_call(["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-pthread",
                                f"-DSFB_EMU_ROOT_LIT={root_lit}", f"-DSFB_EMU_ROOT_DIST={root_dist}",
-                               f"-DSFB_EMU_POOL={pool}", "-o", out, srcs[0]])
+                               f"-DSFB_EMU_POOL={pool}", "-o", out, srcs[0], srcs[1]])
     return out
 
 
@@ -30,15 +34,17 @@ class Emu:
     def __init__(self, **kw):
         self.lib = C.CDLL(build(**kw))
         self.lib.emu_decompress_batch.argtypes = [_u8p, _u64p, _u64p, _u8p, _u64p, _u64p, _u8p,
-                                                  _u64p, C.c_uint64]
+                                                  _u64p, C.c_uint64, C.c_int]
 
-    def decompress_batch(self, b, dst):
+    def decompress_batch(self, b, dst, warp_pass2=False):
+        """warp_pass2: run the real pass-2 kernel on 32 host threads (slow) instead of the
+        scalar restatement of the token format."""
         st = np.zeros(b.n, np.uint8)
         wr = np.zeros(b.n, np.uint64)
         p = lambda a, t: a.ctypes.data_as(t)
         rc = self.lib.emu_decompress_batch(p(b.src, _u8p), p(b.src_off, _u64p), p(b.src_len, _u64p),
                                            p(dst, _u8p), p(b.dst_off, _u64p), p(b.dst_cap, _u64p),
-                                           p(st, _u8p), p(wr, _u64p), b.n)
+                                           p(st, _u8p), p(wr, _u64p), b.n, int(warp_pass2))
         assert rc == 0, f"emulated kernel wrote outside a dst region (code {rc})"
         return st, wr
 
