@@ -95,6 +95,7 @@ struct Cfg {
 //                   reference rejects after decoding them), codes the pool had no room for,
 //                   and every slot of an over-subscribed code set.
 constexpr uint32_t E_SLOW = 0x0010u;
+constexpr int SUB_BITS_MAX = 5;
 constexpr uint32_t E_PTR = 0x8000u;
 
 // RFC 1951 §3.2.5 (reference: src/decompress.cpp:52-84).  info = base | extra << 16
@@ -134,18 +135,39 @@ __device__ __forceinline__ uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t 
 }
 
 // ---------------------------------------------------------------------------------------------
+// Shared-memory addresses of the input ring: 32-bit shared-window addresses on the device (so
+// that ring accesses are plain LDS / cp.async with no generic-address arithmetic), ordinary
+// pointers in the CPU build of tests/cpu_emu.
+#ifdef SFB_CPU_EMU
+using saddr_t = uint8_t*;
+__device__ __forceinline__ saddr_t to_saddr(void* p) { return static_cast<uint8_t*>(p); }
+__device__ __forceinline__ uint32_t lds32(saddr_t a) { return *reinterpret_cast<const uint32_t*>(a); }
+#else
+using saddr_t = uint32_t;
+__device__ __forceinline__ saddr_t to_saddr(void* p)
+{
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ uint32_t lds32(saddr_t a)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+#endif
+
 // cp.async staging (global -> shared, 16 bytes, L2 only).  `src_size` < 16 zero-fills the rest
 // of the block, which is exactly the "bits past the end read as zero" rule of the bit reader,
 // and means no byte past a stream's end is ever read.
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, uint32_t src_size)
+__device__ __forceinline__ void cp_async16(saddr_t smem_dst, const void* gsrc, uint32_t src_size)
 {
 #ifdef SFB_CPU_EMU
   uint8_t tmp[16] = {0};
   if (src_size) std::memcpy(tmp, gsrc, src_size);
   std::memcpy(smem_dst, tmp, 16);
 #else
-  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(src_size)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc),
+               "r"(src_size)
                : "memory");
 #endif
 }
@@ -166,12 +188,12 @@ __device__ __forceinline__ void cp_async_wait()
 // ---------------------------------------------------------------------------------------------
 // Bit reader (replaces huffman::bit_span, huffman/src/bit_span.hpp).  Bits are consumed LSB
 // first.  The compressed bytes are staged by cp.async into a per-lane ring of RING_BLOCKS
-// 16-byte blocks in shared memory; w0:w1:w2 is a 96-bit register window over the stream, w3
-// and w4 are the two following words (already taken from the ring), `bo` the offset of the
-// next unread bit inside the window.  With bo < 32 at the start of a token the window holds
-// >= 65 unread bits, more than the longest token (15 + 5 + 15 + 13 = 48), so a token is
-// decoded with two funnel-shift peeks and the window slides once per token (norm2(): by 0, 1
-// or 2 words, branch-free).
+// 16-byte blocks in shared memory; w0:w1:w2 is a 96-bit register window over the stream and
+// `bo` the offset of the next unread bit inside it.  With bo < 32 at the start of a token the
+// window holds >= 65 unread bits, more than the longest token (15 + 5 + 15 + 13 = 48), so a
+// token is decoded with two funnel-shift peeks and the window slides once per token, by 0, 1
+// or 2 words: the two candidate words are read from the ring at the START of the token
+// (next2(): their addresses do not depend on the token) and selected at its end (norm2()).
 //
 // Words are numbered from `base`, the stream start rounded down to 16 bytes; word x lives in
 // ring block (x >> 2) & 3.  Block b may be issued once block b-4 has been consumed, i.e. while
@@ -182,21 +204,28 @@ __device__ __forceinline__ void cp_async_wait()
 //     first read at least two such steps after it was issued, when its group has been waited
 //     for; typically it was issued ~25 tokens earlier and the wait is free.
 struct BitReader {
-  uint32_t w0, w1, w2, w3, w4;
+  uint32_t w0, w1, w2;
   uint32_t bo;
-  uint32_t rp;          // index of the next word to take from the ring (w4 is word rp-1)
+  uint32_t rp;          // index of the next word to take from the ring (w2 is word rp-1)
   uint32_t pfb;         // index of the next 16-byte block to stage
   uint32_t iend;        // byte offset (from base) one past the last stream byte
   uint32_t lead0;       // stream start - base (0..15)
   const uint8_t* base;  // stream start rounded down to 16 bytes
-  uint8_t* ring;        // this lane's block 0 in shared memory (block s at ring + s*512)
+  saddr_t ring;         // this lane's block 0 in shared memory (block s at ring + s*512)
 
   __device__ __forceinline__ const uint8_t* begin() const { return base + lead0; }
 
-  __device__ __forceinline__ uint32_t ring_word(uint32_t x) const
+  // ring offset of word x, and of the word after the one at offset o
+  static __device__ __forceinline__ uint32_t ring_off(uint32_t x)
   {
-    return *reinterpret_cast<const uint32_t*>(ring + ((x & 12u) << 7) + ((x & 3u) << 2));
+    return ((x & 12u) << 7) | ((x & 3u) << 2);
   }
+  static __device__ __forceinline__ uint32_t ring_next(uint32_t o)
+  {
+    return ((o | 0x1F0u) + 4u) & 0x60Cu;  // the carry out of bits 2-3 ripples into bits 9-10
+  }
+  __device__ __forceinline__ uint32_t ring_word(uint32_t x) const { return lds32(ring + ring_off(x)); }
+
   __device__ __forceinline__ void issue_block()
   {
     const uint32_t at = pfb << 4;
@@ -219,7 +248,7 @@ struct BitReader {
     cp_async_wait<2>();
   }
 
-  __device__ __forceinline__ void open(const uint8_t* begin_, uint32_t len, uint8_t* ring_)
+  __device__ __forceinline__ void open(const uint8_t* begin_, uint32_t len, saddr_t ring_)
   {
     ring = ring_;
     lead0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(begin_) & 15u);
@@ -228,12 +257,12 @@ struct BitReader {
     init_at(lead0, 0);
   }
   // a reader that owns no stream: never slides, never stages
-  __device__ __forceinline__ void park(uint8_t* ring_)
+  __device__ __forceinline__ void park(saddr_t ring_)
   {
     ring = ring_;
-    w0 = w1 = w2 = w3 = w4 = 0;
+    w0 = w1 = w2 = 0;
     bo = 0;
-    rp = 5;
+    rp = 3;
     pfb = 0xfffffff0u;
     iend = lead0 = 0;
     base = nullptr;
@@ -249,9 +278,7 @@ struct BitReader {
     w0 = ring_word(x0);
     w1 = ring_word(x0 + 1);
     w2 = ring_word(x0 + 2);
-    w3 = ring_word(x0 + 3);
-    w4 = ring_word(x0 + 4);
-    rp = x0 + 5;
+    rp = x0 + 3;
     fill_sync();
     bo = 8 * (at & 3u) + skip_bits;
     norm();
@@ -262,9 +289,7 @@ struct BitReader {
   {
     w0 = w1;
     w1 = w2;
-    w2 = w3;
-    w3 = w4;
-    w4 = ring_word(rp);
+    w2 = ring_word(rp);
     ++rp;
     bo -= 32;
     if ((rp & 3u) == 0) fill_sync();
@@ -274,19 +299,21 @@ struct BitReader {
   {
     while (bo >= 32) slide1();
   }
+  // the two words that may enter the window at the end of this token (token loop)
+  __device__ __forceinline__ void next2(uint32_t& n0, uint32_t& n1) const
+  {
+    const uint32_t o0 = ring_off(rp);
+    n0 = lds32(ring + o0);
+    n1 = lds32(ring + ring_next(o0));
+  }
   // make bo < 32 again for bo < 96, branch-free (token loop; staging is the caller's job)
-  __device__ __forceinline__ void norm2()
+  __device__ __forceinline__ void norm2(uint32_t n0, uint32_t n1)
   {
     const bool p1 = bo >= 32, p2 = bo >= 64;
-    uint32_t n0 = 0, n1 = 0;
-    if (p1) n0 = ring_word(rp);
-    if (p2) n1 = ring_word(rp + 1);
     w0 = p2 ? w2 : (p1 ? w1 : w0);
-    w1 = p2 ? w3 : (p1 ? w2 : w1);
-    w2 = p2 ? w4 : (p1 ? w3 : w2);
-    w3 = p2 ? n0 : (p1 ? w4 : w3);
-    w4 = p2 ? n1 : (p1 ? n0 : w4);
-    rp += p2 ? 2u : (p1 ? 1u : 0u);
+    w1 = p2 ? n0 : (p1 ? w2 : w1);
+    w2 = p2 ? n1 : (p1 ? n0 : w2);
+    rp += bo >> 5;
     bo &= 31u;
   }
   // 32 bits starting `off` bits into the window (off < 64)
@@ -300,10 +327,10 @@ struct BitReader {
   __device__ __forceinline__ void skip(uint32_t n) { bo += n; }
 
   // absolute bit position of the next unread bit, relative to the stream start
-  // (w0 is word rp-5; the window may start before the stream right after init_at)
+  // (w0 is word rp-3; the window may start before the stream right after init_at)
   __device__ __forceinline__ int64_t bitpos() const
   {
-    return 32ll * (static_cast<int64_t>(rp) - 5) - 8ll * static_cast<int64_t>(lead0) +
+    return 32ll * (static_cast<int64_t>(rp) - 3) - 8ll * static_cast<int64_t>(lead0) +
            static_cast<int64_t>(bo);
   }
   __device__ __forceinline__ uint64_t total_bits() const
@@ -317,10 +344,6 @@ struct BitReader {
   }
   // some word already in the window reaches past the end of the stream
   __device__ __forceinline__ bool tail() const { return 4u * rp > iend; }
-  __device__ __forceinline__ void seek_bit(uint64_t bit)
-  {
-    init_at(lead0 + static_cast<uint32_t>(bit >> 3), static_cast<unsigned>(bit & 7));
-  }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -576,16 +599,21 @@ __device__ __forceinline__ void build_lut(const LaneMem& m, int s0, int n, int r
       }
     }
   }
-  if (pmax < pmin) return;  // no long codes
-  // pass B: carve sub-tables out of the pool
+  // pass B: carve sub-tables out of the pool (none when there are no long codes: pmax < pmin).
+  // A sub-table indexes at most SUB_BITS_MAX bits — the deepest prefix of a text-like code
+  // would otherwise take 2^(15-ROOT) slots and starve the rest — and shrinks further to fit
+  // what is left of the pool; codes it is too short for keep "no code" slots and are decoded,
+  // exactly, by slow_token() (they are the rarest symbols of the block).
 #pragma unroll 1
   for (uint32_t pfx = pmin; pfx <= pmax; ++pfx) {
     uint16_t& slot = lut[(root_off + bitrev(pfx, ROOT)) * 32];
     const uint32_t e = slot;
     if ((e & 0xF000u) != 0xF000u) continue;
-    const int sb = static_cast<int>(e & 15u) - ROOT;
+    int sb = static_cast<int>(e & 15u) - ROOT;
+    if (sb > SUB_BITS_MAX) sb = SUB_BITS_MAX;
+    while (sb > 0 && pool_at + (1 << sb) > pool_end) --sb;
     const int size = 1 << sb;
-    if (sb <= 7 && pool_at + size <= pool_end) {
+    if (sb > 0) {
       slot = static_cast<uint16_t>(E_PTR | (static_cast<uint32_t>(sb) << 12) |
                                    (static_cast<uint32_t>(pool_at - POOL_OFF) << 4));
       for (int j = 0; j < size; ++j) lut[(pool_at + j) * 32] = 0;
@@ -595,15 +623,13 @@ __device__ __forceinline__ void build_lut(const LaneMem& m, int s0, int n, int r
     }
   }
   // pass C: fill sub-tables
-  {
+  if (pmax >= pmin) {
     uint32_t code = 0;
 #pragma unroll
     for (int L = 1; L < 16; ++L) {
       code = (code + count[L - 1]) << 1;
       next[L] = code;
     }
-  }
-  {
     LensReader r(m.lens, s0, n);
 #pragma unroll 1
     for (int s = 0; s < n; ++s) {
@@ -614,6 +640,7 @@ __device__ __forceinline__ void build_lut(const LaneMem& m, int s0, int n, int r
       const uint32_t e = lut[(root_off + bitrev(code >> rest, ROOT)) * 32];
       if (e == E_SLOW) continue;
       const uint32_t sb = (e >> 12) & 7u;
+      if (rest > sb) continue;  // longer than its (capped) sub-table reaches: slow_token()
       const uint32_t off = POOL_OFF + ((e >> 4) & 0xffu);
       const uint16_t v = make_entry<LITLEN>(static_cast<uint32_t>(s), L);
       for (uint32_t j = bitrev(code & ((1u << rest) - 1u), static_cast<int>(rest)); j < (1u << sb);
@@ -648,202 +675,200 @@ enum : int { S_DECODE = 0, S_STORED = 1, S_HEADER = 2, S_DONE = 3 };
 // reference would read past the input (assert-only pop_bits / pop_16) the documented choices
 // of this repository apply (SrcTooSmall; InvalidLitOrLen for malformed repeats).
 // Returns the next lane state; *status is set when the state is S_DONE.
+// Control flow: ONE exit and no jumps out of loops.  With early returns inside the loops the
+// only reconvergence point the compiler can use is the end of this (inlined) function, and the
+// lanes of a warp, which all parse their headers at the same time, would run the whole parse
+// and both table builds one lane after the other (ncu: 1.2 active threads per instruction).
 template <class C>
 __device__ __forceinline__ int parse_block_header(BitReader& br, const LaneMem& m, uint32_t room,
                                                   uint32_t& final_block, int& n_lit, int& n_dist,
                                                   const uint8_t*& copy_src, uint32_t& copy_left,
                                                   int* status)
 {
+  int err = -1;           // DecompressStatus once the stream is known to end here
+  int next = S_DECODE;
+  uint32_t type = 3;
   br.norm();
   if (br.real_left() < 3) {
-    *status = ST_INVALID_BLOCK_HEADER;
-    return S_DONE;
+    err = ST_INVALID_BLOCK_HEADER;
+  } else {
+    const uint32_t hdr = br.peek() & 7u;
+    type = hdr >> 1;
+    if (type == 3) {
+      err = ST_INVALID_BLOCK_HEADER;
+    } else {
+      final_block = hdr & 1u;
+      br.skip(3);
+    }
   }
-  const uint32_t hdr = br.peek() & 7u;
-  const uint32_t type = hdr >> 1;
-  if (type == 3) {
-    *status = ST_INVALID_BLOCK_HEADER;
-    return S_DONE;
-  }
-  final_block = hdr & 1u;
-  br.skip(3);
 
-  if (type == 0) {
+  if (err < 0 && type == 0) {
     // stored block: skip to the byte boundary (the window words are byte-aligned with the
     // stream, so the phase of `bo` is the phase of the stream)
     br.skip((8u - (br.bo & 7u)) & 7u);
     br.norm();
     if (br.real_left() < 32) {
-      *status = ST_SRC_TOO_SMALL;  // reference: pop_16 past the end (class U)
-      return S_DONE;
-    }
-    const uint32_t w = br.peek();
-    br.skip(32);
-    const uint32_t len = w & 0xffffu, nlen = w >> 16;
-    if (len != ((~nlen) & 0xffffu)) {
-      *status = ST_LEN_MISMATCH;
-      return S_DONE;
-    }
-    const uint64_t pos = br.bitpos();
-    if (br.total_bits() - pos < 8ull * len) {
-      *status = ST_SRC_TOO_SMALL;
-      return S_DONE;
-    }
-    if (room < len) {
-      *status = ST_DST_TOO_SMALL;
-      return S_DONE;
-    }
-    copy_src = br.begin() + (pos >> 3);
-    copy_left = len;
-    if (len == 0) {
-      br.norm();
-      if (final_block) {
-        *status = ST_SUCCESS;
-        return S_DONE;
-      }
-      return S_HEADER;
-    }
-    return S_STORED;
-  }
-
-  if (type == 1) {
-    // fixed codes: src/decompress.cpp:25-40
-    n_lit = 288;
-    n_dist = 32;
-#pragma unroll 1
-    for (int j = 0; j < LENS_WORDS; ++j) {
-      const int s = j * 8;
-      uint32_t v;
-      if (s < 144) v = 0x88888888u;
-      else if (s < 256) v = 0x99999999u;
-      else if (s < 280) v = 0x77777777u;
-      else if (s < 288) v = 0x88888888u;
-      else v = 0x55555555u;
-      m.lens[j * 32] = v;
-    }
-  } else {
-    // dynamic codes
-    br.norm();
-    if (br.real_left() < 14) {
-      *status = ST_SRC_TOO_SMALL;
-      return S_DONE;
-    }
-    uint32_t w = br.peek();
-    n_lit = 257 + static_cast<int>(w & 31u);
-    n_dist = 1 + static_cast<int>((w >> 5) & 31u);
-    const int n_cl = 4 + static_cast<int>((w >> 10) & 15u);
-    br.skip(14);
-    uint64_t cl_lens = 0;  // 19 x 3 bits, indexed by CL symbol
-#pragma unroll 1
-    for (int i = 0; i < n_cl; ++i) {
-      br.norm();
-      if (br.real_left() < 3) {
-        *status = ST_SRC_TOO_SMALL;
-        return S_DONE;
-      }
-      cl_lens |= static_cast<uint64_t>(br.peek() & 7u) << (3 * c_cl_order[i]);
-      br.skip(3);
-    }
-    // code-length code: 7-bit LUT of bytes (sym << 3 | len), overlaid on the pool region
-    // (two bytes per u16 slot: byte j of this lane lives in slot j >> 1).
-    // Filled from the longest length down so that, for over-subscribed sets, the shortest
-    // matching code wins exactly as the reference's bit-serial search does.
-    uint8_t* cl_lut = reinterpret_cast<uint8_t*>(m.lut + C::POOL_OFF * 32);
-    {
-      uint32_t cnt[8];
-#pragma unroll
-      for (int L = 0; L < 8; ++L) cnt[L] = 0;
-#pragma unroll 1
-      for (int s = 0; s < 19; ++s) cnt[(cl_lens >> (3 * s)) & 7u]++;
-      cnt[0] = 0;
-      uint32_t first[8];
-      first[0] = 0;
-      {
-        uint32_t code = 0;
-#pragma unroll
-        for (int L = 1; L < 8; ++L) {
-          code = (code + cnt[L - 1]) << 1;
-          first[L] = code;
+      err = ST_SRC_TOO_SMALL;  // reference: pop_16 past the end (class U)
+    } else {
+      const uint32_t w = br.peek();
+      br.skip(32);
+      const uint32_t len = w & 0xffffu, nlen = w >> 16;
+      const uint64_t pos = static_cast<uint64_t>(br.bitpos());
+      if (len != ((~nlen) & 0xffffu)) {
+        err = ST_LEN_MISMATCH;
+      } else if (br.total_bits() - pos < 8ull * len) {
+        err = ST_SRC_TOO_SMALL;
+      } else if (room < len) {
+        err = ST_DST_TOO_SMALL;
+      } else {
+        copy_src = br.begin() + (pos >> 3);
+        copy_left = len;
+        next = S_STORED;
+        if (len == 0) {
+          br.norm();
+          next = S_HEADER;
+          if (final_block) err = ST_SUCCESS;
         }
       }
+    }
+  } else if (err < 0) {
+    if (type == 1) {
+      // fixed codes: src/decompress.cpp:25-40
+      n_lit = 288;
+      n_dist = 32;
 #pragma unroll 1
-      for (int j = 0; j < 128; ++j) cl_lut[(j >> 1) * 64 + (j & 1)] = 0;
+      for (int j = 0; j < LENS_WORDS; ++j) {
+        const int s = j * 8;
+        uint32_t v;
+        if (s < 144) v = 0x88888888u;
+        else if (s < 256) v = 0x99999999u;
+        else if (s < 280) v = 0x77777777u;
+        else if (s < 288) v = 0x88888888u;
+        else v = 0x55555555u;
+        m.lens[j * 32] = v;
+      }
+    } else {
+      // dynamic codes
+      br.norm();
+      int n_cl = 0;
+      if (br.real_left() < 14) {
+        err = ST_SRC_TOO_SMALL;
+      } else {
+        const uint32_t w = br.peek();
+        n_lit = 257 + static_cast<int>(w & 31u);
+        n_dist = 1 + static_cast<int>((w >> 5) & 31u);
+        n_cl = 4 + static_cast<int>((w >> 10) & 15u);
+        br.skip(14);
+      }
+      uint64_t cl_lens = 0;  // 19 x 3 bits, indexed by CL symbol
 #pragma unroll 1
-      for (int L = 7; L >= 1; --L) {
-        uint32_t code = first[L];
+      for (int i = 0; i < n_cl && err < 0; ++i) {
+        br.norm();
+        if (br.real_left() < 3) {
+          err = ST_SRC_TOO_SMALL;
+        } else {
+          cl_lens |= static_cast<uint64_t>(br.peek() & 7u) << (3 * c_cl_order[i]);
+          br.skip(3);
+        }
+      }
+      if (err < 0) {
+        // code-length code: 7-bit LUT of bytes (sym << 3 | len), overlaid on the pool region
+        // (two bytes per u16 slot: byte j of this lane lives in slot j >> 1).
+        // Filled from the longest length down so that, for over-subscribed sets, the shortest
+        // matching code wins exactly as the reference's bit-serial search does.
+        uint8_t* cl_lut = reinterpret_cast<uint8_t*>(m.lut + C::POOL_OFF * 32);
+        {
+          uint32_t cnt[8];
+#pragma unroll
+          for (int L = 0; L < 8; ++L) cnt[L] = 0;
 #pragma unroll 1
-        for (int s = 0; s < 19; ++s) {
-          if (static_cast<int>((cl_lens >> (3 * s)) & 7u) != L) continue;
-          if (code < (1u << L)) {
-            for (uint32_t j = bitrev(code, L); j < 128u; j += 1u << L)
-              cl_lut[(j >> 1) * 64 + (j & 1)] = static_cast<uint8_t>((s << 3) | L);
+          for (int s = 0; s < 19; ++s) cnt[(cl_lens >> (3 * s)) & 7u]++;
+          cnt[0] = 0;
+          uint32_t first[8];
+          first[0] = 0;
+          {
+            uint32_t code = 0;
+#pragma unroll
+            for (int L = 1; L < 8; ++L) {
+              code = (code + cnt[L - 1]) << 1;
+              first[L] = code;
+            }
           }
-          ++code;
+#pragma unroll 1
+          for (int j = 0; j < 128; ++j) cl_lut[(j >> 1) * 64 + (j & 1)] = 0;
+#pragma unroll 1
+          for (int L = 7; L >= 1; --L) {
+            uint32_t code = first[L];
+#pragma unroll 1
+            for (int s = 0; s < 19; ++s) {
+              if (static_cast<int>((cl_lens >> (3 * s)) & 7u) == L) {
+                if (code < (1u << L)) {
+                  for (uint32_t j = bitrev(code, L); j < 128u; j += 1u << L)
+                    cl_lut[(j >> 1) * 64 + (j & 1)] = static_cast<uint8_t>((s << 3) | L);
+                }
+                ++code;
+              }
+            }
+          }
         }
+        // the two independent runs of code lengths (src/decompress.cpp:353-360)
+        const int total = n_lit + n_dist;
+        LensWriter lw(m.lens);
+        int run_begin = 0, run_end = n_lit;
+        uint32_t prev = 0;
+#pragma unroll 1
+        for (int i = 0; i < total && err < 0;) {
+          if (i == run_end) {
+            run_begin = n_lit;
+            run_end = total;
+          }
+          br.norm();
+          const uint32_t bits = br.peek();
+          const uint32_t j = bits & 127u;
+          const uint32_t e = cl_lut[(j >> 1) * 64 + (j & 1)];
+          const uint32_t L = e & 7u;
+          const int64_t left = br.real_left();
+          const uint32_t sym = e >> 3;
+          const uint32_t xbits = sym < 16 ? 0u : sym == 16 ? 2u : sym == 17 ? 3u : 7u;
+          // L + xbits <= 14 bits: still inside the peeked word
+          int repeat = 1;
+          uint32_t v = sym;
+          if (sym >= 16) {
+            repeat = static_cast<int>((bits >> L) & ((1u << xbits) - 1u)) + (sym == 18 ? 11 : 3);
+            v = sym == 16 ? prev : 0u;
+          }
+          if (L == 0 || static_cast<int64_t>(L) > left) {
+            err = ST_INVALID_LIT_OR_LEN;  // src/decompress.cpp:265-267
+          } else if (left - static_cast<int64_t>(L) < static_cast<int64_t>(xbits)) {
+            err = ST_SRC_TOO_SMALL;       // reference: unchecked pop_bits (class U)
+          } else if (sym == 16 && i == run_begin) {
+            err = ST_INVALID_LIT_OR_LEN;  // reference reads code_bitsizes[-1] (class U)
+          } else if (i + repeat > run_end) {
+            err = ST_INVALID_LIT_OR_LEN;  // reference writes past code_bitsizes (class U)
+          } else {
+            br.skip(L + xbits);
+#pragma unroll 1
+            for (int r = 0; r < repeat; ++r) lw.put(v);
+            prev = v;
+            i += repeat;
+          }
+        }
+        if (err < 0) lw.finish();
       }
     }
-    // the two independent runs of code lengths (src/decompress.cpp:353-360)
-    const int total = n_lit + n_dist;
-    LensWriter lw(m.lens);
-    int run_begin = 0, run_end = n_lit;
-    uint32_t prev = 0;
-#pragma unroll 1
-    for (int i = 0; i < total;) {
-      if (i == run_end) {
-        run_begin = n_lit;
-        run_end = total;
-      }
+    if (err < 0) {
+      int pool_at = C::POOL_OFF;
+      build_lut<C::ROOT_LIT, true, C::POOL_OFF>(m, 0, n_lit, C::LIT_OFF, C::POOL_OFF + C::POOL, pool_at);
+      build_lut<C::ROOT_DIST, false, C::POOL_OFF>(m, n_lit, n_dist, C::DIST_OFF, C::POOL_OFF + C::POOL,
+                                                  pool_at);
       br.norm();
-      const uint32_t bits = br.peek();
-      const uint32_t j = bits & 127u;
-      const uint32_t e = cl_lut[(j >> 1) * 64 + (j & 1)];
-      const uint32_t L = e & 7u;
-      const int64_t left = br.real_left();
-      if (L == 0 || static_cast<int64_t>(L) > left) {
-        *status = ST_INVALID_LIT_OR_LEN;  // src/decompress.cpp:265-267
-        return S_DONE;
-      }
-      br.skip(L);
-      const uint32_t sym = e >> 3;
-      if (sym < 16) {
-        lw.put(sym);
-        prev = sym;
-        ++i;
-        continue;
-      }
-      const uint32_t xbits = sym == 16 ? 2u : sym == 17 ? 3u : 7u;
-      if (left - static_cast<int64_t>(L) < static_cast<int64_t>(xbits)) {
-        *status = ST_SRC_TOO_SMALL;  // reference: unchecked pop_bits (class U)
-        return S_DONE;
-      }
-      // L + xbits <= 14 bits: still inside the peeked word
-      const int repeat = static_cast<int>((bits >> L) & ((1u << xbits) - 1u)) + (sym == 18 ? 11 : 3);
-      br.skip(xbits);
-      uint32_t v = 0;
-      if (sym == 16) {
-        if (i == run_begin) {
-          *status = ST_INVALID_LIT_OR_LEN;  // reference reads code_bitsizes[-1] (class U)
-          return S_DONE;
-        }
-        v = prev;
-      }
-      if (i + repeat > run_end) {
-        *status = ST_INVALID_LIT_OR_LEN;  // reference writes past code_bitsizes (class U)
-        return S_DONE;
-      }
-#pragma unroll 1
-      for (int r = 0; r < repeat; ++r) lw.put(v);
-      prev = v;
-      i += repeat;
     }
-    lw.finish();
   }
-  int pool_at = C::POOL_OFF;
-  build_lut<C::ROOT_LIT, true, C::POOL_OFF>(m, 0, n_lit, C::LIT_OFF, C::POOL_OFF + C::POOL, pool_at);
-  build_lut<C::ROOT_DIST, false, C::POOL_OFF>(m, n_lit, n_dist, C::DIST_OFF, C::POOL_OFF + C::POOL,
-                                              pool_at);
-  br.norm();
-  return S_DECODE;
+  if (err >= 0) {
+    *status = err;
+    next = S_DONE;
+  }
+  return next;
 }
 
 }  // namespace sfb

@@ -46,9 +46,8 @@ namespace sfb {
 
 // ---------------------------------------------------------------------------------------------
 // Per-lane output window of pass 1.
-// Invariant: bytes [vpos & ~7, vpos) of the output live in the low bytes of `obuf` (its
-// higher bytes are unspecified); every byte below vpos & ~7 that pass 2 will not overwrite is
-// in memory.
+// Invariant: bytes [vpos & ~7, vpos) of the output live in the low bytes of `obuf`, its higher
+// bytes are zero; every byte below vpos & ~7 that pass 2 will not overwrite is in memory.
 struct TokWin {
   uint8_t* al;      // 8-byte aligned address of virtual position 0
   uint32_t lead;    // dst start within the first word (0..7): virtual position of byte 0
@@ -101,19 +100,23 @@ struct TokWin {
   // belong to the match body, so any value will do there.
   __device__ __forceinline__ void emit(uint32_t chunk, uint32_t n, uint32_t skipn)
   {
+#ifdef SFB_TRACE_EMIT
+    SFB_TRACE_EMIT(vpos, chunk, n, skipn, obuf);
+#endif
     const uint32_t k = vpos & 7u;
     const uint32_t sh = 8u * k;
-    const uint64_t merged = (obuf & ~(~0ull << sh)) | (static_cast<uint64_t>(chunk) << sh);
+    const uint64_t merged = obuf | (static_cast<uint64_t>(chunk) << sh);  // chunk < 2^(8n)
     const uint32_t np = vpos + n + skipn;
     const uint32_t wv = vpos & ~7u;
     const bool leaves = (np & ~7u) != wv;
     const bool spill = k + n > 8u;                         // the chunk reaches into the next word
     const uint32_t carry = chunk >> ((64u - sh) & 31u);    // ... with these bytes (sh >= 48 then)
+    const bool stay = (np & ~7u) == wv + 8u;               // the cursor ends in the next word
     if (leaves) {
       store_word(wv, merged);
-      if (spill && (np & ~7u) != wv + 8u) store_word(wv + 8u, carry);  // skipped past that word too
+      if (spill && !stay) store_word(wv + 8u, carry);      // skipped past that word too
     }
-    obuf = leaves ? (spill ? carry : 0u) : merged;
+    obuf = leaves ? ((spill && stay) ? carry : 0u) : merged;
     vpos = np;
   }
 
@@ -206,7 +209,7 @@ huff_lanes_kernel(const BatchArgs a)
            (static_cast<size_t>(blockIdx.x) * C::WARPS + static_cast<size_t>(warp)) * (SCRATCH_WORDS * 32) +
            lane;
   const uint16_t* const lut = m.lut;
-  uint8_t* const ring = warp_smem + C::WARP_U16 * 2 + lane * 16;
+  const saddr_t ring = to_saddr(warp_smem + C::WARP_U16 * 2 + lane * 16);
 
   const uint64_t n_groups = (a.n + 31) / 32;
   for (;;) {
@@ -273,8 +276,9 @@ huff_lanes_kernel(const BatchArgs a)
         //      the others compute on stale data and discard) ----------------------------------
         const bool dec = state == S_DECODE;
         SFB_STAT(tokens);
-        const uint32_t rp0 = br.rp;   // token start (slow path only)
         const uint32_t bo0 = br.bo;   // < 32
+        uint32_t n0, n1;
+        br.next2(n0, n1);
         const uint32_t bits = br.peek();
         const uint32_t bits_hi = funnel_r(br.w1, br.w2, bo0);
         const uint32_t e = lut_lookup<C::ROOT_LIT, C::POOL_OFF, C::POOL>(lut, C::LIT_OFF, bits);
@@ -289,20 +293,16 @@ huff_lanes_kernel(const BatchArgs a)
         const uint32_t dinfo = s_dist_info[(de >> 4) & 31u];
         const uint32_t dxb = dinfo >> 16;
         uint32_t dist = (dinfo & 0xffffu) + ((dbits >> dL) & ((1u << dxb) - 1u));
-        // anything that is not a plain literal / length+distance is "slow"
-        bool slow = (L == 0) | (is_len & (dL == 0));
-        if (dec) br.skip(used1 + (is_len ? dL + dxb : 0u));
-        br.norm2();
-        if (br.tail()) slow |= br.real_left() < 0;
+        uint32_t used = used1 + (is_len ? dL + dxb : 0u);
         bool is_match = is_len;
         bool eob = false;
-        if (dec & slow) {
-          // end of block, or anything the fast path cannot vouch for: redo this token exactly
+        // anything that is not a plain literal / length+distance — end of block included — is
+        // redone exactly, from the same 64 window bits
+        const uint64_t snap = (static_cast<uint64_t>(bits_hi) << 32) | bits;
+        if (dec & ((L == 0) | (is_len & (dL == 0)))) {
           SFB_STAT(slow_tokens);
-          const int64_t tok_pos = 32ll * (static_cast<int64_t>(rp0) - 5) -
-                                  8ll * static_cast<int64_t>(br.lead0) + static_cast<int64_t>(bo0);
-          const SlowToken t = slow_token(m.lens, (static_cast<uint64_t>(bits_hi) << 32) | bits,
-                                         static_cast<int64_t>(br.total_bits()) - tok_pos);
+          const SlowToken t = slow_token(m.lens, snap, br.real_left());
+          used = t.used;
           if (t.status != ST_SUCCESS) {
             status = t.status;
             state = S_DONE;
@@ -311,8 +311,17 @@ huff_lanes_kernel(const BatchArgs a)
             eob = t.kind == 1;
             value = static_cast<uint32_t>(t.value);
             dist = static_cast<uint32_t>(t.dist);
-            br.seek_bit(static_cast<uint64_t>(tok_pos) + t.used);
           }
+        }
+        if (state == S_DECODE) br.skip(used);
+        br.norm2(n0, n1);
+        if (br.tail() && state == S_DECODE && br.real_left() < 0) {
+          // the token reaches past the end of the input: the same bits with the true count
+          // of real ones give the reference's status (never Success)
+          SFB_STAT(slow_tokens);
+          const SlowToken t = slow_token(m.lens, snap, br.real_left() + static_cast<int64_t>(used));
+          status = t.status != ST_SUCCESS ? t.status : ST_SRC_TOO_SMALL;
+          state = S_DONE;
         }
         if (it & 1u) br.stage_step();
         ++it;
