@@ -142,6 +142,7 @@ __device__ __forceinline__ uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t 
 using saddr_t = uint8_t*;
 __device__ __forceinline__ saddr_t to_saddr(void* p) { return static_cast<uint8_t*>(p); }
 __device__ __forceinline__ uint32_t lds32(saddr_t a) { return *reinterpret_cast<const uint32_t*>(a); }
+__device__ __forceinline__ uint32_t lds16(saddr_t a) { return *reinterpret_cast<const uint16_t*>(a); }
 #else
 using saddr_t = uint32_t;
 __device__ __forceinline__ saddr_t to_saddr(void* p)
@@ -152,6 +153,12 @@ __device__ __forceinline__ uint32_t lds32(saddr_t a)
 {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds16(saddr_t a)
+{
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
   return v;
 }
 #endif
@@ -661,6 +668,21 @@ __device__ __forceinline__ uint32_t lut_lookup(const uint16_t* lut, int root_off
     const uint32_t sb = (e >> 12) & 7u;
     const uint32_t idx = ((e >> 4) & 0xffu) + ((bits >> ROOT) & ((1u << sb) - 1u));
     e = lut[(POOL_OFF + (idx < POOL ? idx : POOL - 1u)) * 32];
+  }
+  return e;
+}
+
+// The same lookup for the token loop, on shared-window addresses: `lutb` is the address of this
+// lane's element 0, element j sits 64*j bytes further.
+template <int ROOT, int ROOT_OFF, int POOL_OFF, uint32_t POOL>
+__device__ __forceinline__ uint32_t lut_lookup_s(saddr_t lutb, uint32_t bits)
+{
+  uint32_t e = lds16(lutb + (ROOT_OFF * 64) + ((bits << 6) & (((1u << ROOT) - 1u) << 6)));
+  if ((e & (E_PTR | 15u)) == E_PTR) {  // sub-table pointer (codes longer than ROOT)
+    const uint32_t sb = (e >> 12) & 7u;
+    uint32_t idx = ((e >> 4) & 0xffu) + ((bits >> ROOT) & ~(0xffffffffu << sb));
+    idx = idx < POOL ? idx : POOL - 1u;  // (stale tables on idle lanes: stay inside the slice)
+    e = lds16(lutb + (POOL_OFF * 64) + (idx << 6));
   }
   return e;
 }

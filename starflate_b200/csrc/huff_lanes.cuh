@@ -208,7 +208,8 @@ huff_lanes_kernel(const BatchArgs a)
   m.lens = a.lens_scratch +
            (static_cast<size_t>(blockIdx.x) * C::WARPS + static_cast<size_t>(warp)) * (SCRATCH_WORDS * 32) +
            lane;
-  const uint16_t* const lut = m.lut;
+  const saddr_t lutb = to_saddr(m.lut);
+  const saddr_t sdi = to_saddr(s_dist_info);
   const saddr_t ring = to_saddr(warp_smem + C::WARP_U16 * 2 + lane * 16);
 
   const uint64_t n_groups = (a.n + 31) / 32;
@@ -274,81 +275,73 @@ huff_lanes_kernel(const BatchArgs a)
       while (__any_sync(FULL, state == S_DECODE)) {
         // ---- decode one token (straight-line; results are only used by lanes in S_DECODE,
         //      the others compute on stale data and discard) ----------------------------------
-        const bool dec = state == S_DECODE;
+        bool dec = state == S_DECODE;
         SFB_STAT(tokens);
         const uint32_t bo0 = br.bo;   // < 32
         uint32_t n0, n1;
         br.next2(n0, n1);
         const uint32_t bits = br.peek();
         const uint32_t bits_hi = funnel_r(br.w1, br.w2, bo0);
-        const uint32_t e = lut_lookup<C::ROOT_LIT, C::POOL_OFF, C::POOL>(lut, C::LIT_OFF, bits);
+        const uint32_t e = lut_lookup_s<C::ROOT_LIT, C::LIT_OFF, C::POOL_OFF, C::POOL>(lutb, bits);
         const uint32_t L = e & 15u;
-        const bool is_len = (e & 0x8000u) != 0;           // (pointers were resolved: L != 0 here)
         const uint32_t xb = (e >> 12) & 7u;               // 0 for literals
-        uint32_t value = ((e >> 4) & 0xffu) + (is_len ? 3u + ((bits >> L) & ((1u << xb) - 1u)) : 0u);
+        bool is_match = (e & 0x8000u) != 0;               // (pointers were resolved: L != 0 then)
+        uint32_t value = ((e >> 4) & 0xffu) + ((bits >> L) & ~(0xffffffffu << xb)) + (is_match ? 3u : 0u);
         const uint32_t used1 = L + xb;
         const uint32_t dbits = br.peek_at(bo0 + used1);   // bo0 + used1 <= 31 + 20
-        const uint32_t de = lut_lookup<C::ROOT_DIST, C::POOL_OFF, C::POOL>(lut, C::DIST_OFF, dbits);
+        const uint32_t de = lut_lookup_s<C::ROOT_DIST, C::DIST_OFF, C::POOL_OFF, C::POOL>(lutb, dbits);
         const uint32_t dL = de & 15u;
-        const uint32_t dinfo = s_dist_info[(de >> 4) & 31u];
+        const uint32_t dinfo = lds32(sdi + ((de >> 2) & 0x7cu));
         const uint32_t dxb = dinfo >> 16;
-        uint32_t dist = (dinfo & 0xffffu) + ((dbits >> dL) & ((1u << dxb) - 1u));
-        uint32_t used = used1 + (is_len ? dL + dxb : 0u);
-        bool is_match = is_len;
+        uint32_t dist = (dinfo & 0xffffu) + ((dbits >> dL) & ~(0xffffffffu << dxb));
+        uint32_t used = used1 + (is_match ? dL + dxb : 0u);
         bool eob = false;
         // anything that is not a plain literal / length+distance — end of block included — is
         // redone exactly, from the same 64 window bits
         const uint64_t snap = (static_cast<uint64_t>(bits_hi) << 32) | bits;
-        if (dec & ((L == 0) | (is_len & (dL == 0)))) {
+        if (dec & ((L == 0) | (is_match & (dL == 0)))) {
           SFB_STAT(slow_tokens);
           const SlowToken t = slow_token(m.lens, snap, br.real_left());
           used = t.used;
+          is_match = t.kind == 2;
+          eob = t.kind == 1;
+          value = static_cast<uint32_t>(t.value);
+          dist = static_cast<uint32_t>(t.dist);
           if (t.status != ST_SUCCESS) {
             status = t.status;
             state = S_DONE;
-          } else {
-            is_match = t.kind == 2;
-            eob = t.kind == 1;
-            value = static_cast<uint32_t>(t.value);
-            dist = static_cast<uint32_t>(t.dist);
+            dec = false;
           }
         }
-        if (state == S_DECODE) br.skip(used);
+        if (dec) br.skip(used);
         br.norm2(n0, n1);
-        if (br.tail() && state == S_DECODE && br.real_left() < 0) {
-          // the token reaches past the end of the input: the same bits with the true count
-          // of real ones give the reference's status (never Success)
-          SFB_STAT(slow_tokens);
-          const SlowToken t = slow_token(m.lens, snap, br.real_left() + static_cast<int64_t>(used));
-          status = t.status != ST_SUCCESS ? t.status : ST_SRC_TOO_SMALL;
-          state = S_DONE;
+        if (dec & br.tail()) {
+          if (br.real_left() < 0) {
+            // the token reaches past the end of the input: the same bits with the true count
+            // of real ones give the reference's status (never Success)
+            SFB_STAT(slow_tokens);
+            const SlowToken t = slow_token(m.lens, snap, br.real_left() + static_cast<int64_t>(used));
+            status = t.status != ST_SUCCESS ? t.status : ST_SRC_TOO_SMALL;
+            state = S_DONE;
+            dec = false;
+          }
         }
         if (it & 1u) br.stage_step();
         ++it;
         // ---- act on the token ----------------------------------------------------------------
-        uint32_t chunk = 0, n = 0, skipn = 0;
-        if (state == S_DECODE) {
-          if (eob) {
-            status = ST_SUCCESS;
-            state = final_block ? S_DONE : S_HEADER;
-          } else {
-            const bool bad_dist = is_match && dist > ow.written();   // src/decompress.cpp:178-180
-            const uint32_t need = is_match ? value : 1u;             // :181-183 / :150-152
-            if (bad_dist | (ow.room() < need)) {                     // (no partial copy)
-              status = bad_dist ? ST_INVALID_DISTANCE : ST_DST_TOO_SMALL;
-              state = S_DONE;
-            } else if (is_match) {
-              ow.mark_head();
-              chunk = (value - 3u) | ((dist - 1u) << 8);
-              n = 3;
-              skipn = value - 3u;
-            } else {
-              chunk = value;
-              n = 1;
-            }
-          }
+        // (src/decompress.cpp:178-183 distance then room for a match, :150-152 room for a
+        //  literal; nothing of a token that fails is written)
+        const bool bad_dist = is_match & (dist > ow.written());
+        const bool bad = bad_dist | (ow.room() < (is_match ? value : 1u));
+        if (dec & (eob | bad)) {
+          status = eob ? ST_SUCCESS : bad_dist ? ST_INVALID_DISTANCE : ST_DST_TOO_SMALL;
+          state = (eob && !final_block) ? S_HEADER : S_DONE;
+          dec = false;
         }
-        ow.emit(chunk, n, skipn);
+        const bool mt = dec & is_match;
+        if (mt) ow.mark_head();
+        const uint32_t desc = (value - 3u) | ((dist - 1u) << 8);
+        ow.emit(dec ? (mt ? desc : value) : 0u, dec ? (mt ? 3u : 1u) : 0u, mt ? value - 3u : 0u);
       }
       if (state == S_DONE && live) {
         ow.flush_tail();

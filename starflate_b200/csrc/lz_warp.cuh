@@ -44,12 +44,30 @@ struct ResolveArgs {
 
 constexpr int LZ_THREADS = 256;
 
-__device__ __forceinline__ uint32_t lz_lanes_below_or_at(uint32_t lane) { return 0xffffffffu >> (31u - lane); }
+// byte permute (PRMT): result byte i = byte sel.nibble[i] of the 8 bytes b:a
+__device__ __forceinline__ uint32_t lz_prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+#ifdef SFB_CPU_EMU
+  const uint64_t v = (static_cast<uint64_t>(b) << 32) | a;
+  uint32_t r = 0;
+  for (int i = 0; i < 4; ++i) r |= static_cast<uint32_t>((v >> (8 * ((sel >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+  return r;
+#else
+  return __byte_perm(a, b, sel);
+#endif
+}
 
 __global__ void __launch_bounds__(LZ_THREADS) lz_resolve_kernel(const ResolveArgs a)
 {
   constexpr unsigned FULL = 0xffffffffu;
   const uint32_t lane = threadIdx.x & 31u;
+  // loop invariants of the descriptor assembly: lane l takes bytes l+1 and l+2 of the chunk;
+  // for lanes 31 / 30,31 they are bytes 0 / 0,1 of the NEXT chunk, which travel in byte 1 of
+  // the shuffled value (v = cur | nxt << 8)
+  const int src1 = static_cast<int>((lane + 1u) & 31u), src2 = static_cast<int>((lane + 2u) & 31u);
+  const uint32_t sel1 = lane == 31u ? 0x7750u : 0x7740u;  // {cur.b0, t1.b0 | t1.b1, 0(b3 of cur: 0), ...}
+  const uint32_t sel2 = lane >= 30u ? 0x7510u : 0x7410u;  // {d.b0, d.b1, t2.b0 | t2.b1, 0}
+  const uint32_t le_mask = 0xffffffffu >> (31u - lane);   // lanes at or below this one
   for (;;) {
     unsigned long long si = 0;
     if (lane == 0) si = atomicAdd(a.stream_counter, 1ull);
@@ -60,44 +78,35 @@ __global__ void __launch_bounds__(LZ_THREADS) lz_resolve_kernel(const ResolveArg
     if (wr == 0) continue;
     // virtual positions: byte v of the view sits at base[v]; the stream occupies [q, end)
     uint8_t* const base = a.dst_base + (off & ~31ull);
-    const uint32_t* const bmw = a.match_bits + (off >> 5);
+    const uint32_t* bmw = a.match_bits + (off >> 5);
     const uint32_t q = static_cast<uint32_t>(off & 31u);
     const uint32_t end = q + static_cast<uint32_t>(wr);
     // the most recent match seen so far: [c_o, c_end) at distance c_d (none yet: empty range)
     uint32_t c_o = 0, c_end = 0, c_d = 1;
-    uint32_t cur = 0, M = 0;
-    {
-      const uint32_t p = lane;
-      if (p >= q && p < end) cur = base[p];
-      M = bmw[0];
-    }
-    for (uint32_t P = 0; P < end; P += 32) {
+    // two chunks of pass-1 bytes and bitmap words are kept in flight ahead of the one being
+    // resolved (nothing a chunk's resolution stores can change them: it only writes its own
+    // 32 bytes)
+    uint8_t* pb = base + lane;  // this lane's byte of the current chunk
+    uint32_t cur = 0, nxt = 0, M, nM = 0;
+    if (lane >= q && lane < end) cur = pb[0];
+    if (lane + 32u < end) nxt = pb[32];
+    M = bmw[0] & (0xffffffffu << q);
+    if (32u < end) nM = bmw[1];
+    for (uint32_t P = 0; P < end; P += 32, pb += 32, ++bmw) {
       const uint32_t p = P + lane;
-      const bool valid = p >= q && p < end;
-      // prefetch the following chunk (pass-1 bytes: nothing in this iteration modifies them)
-      const uint32_t np = p + 32;
-      uint32_t nxt = 0, nM = 0;
-      if (np >= q && np < end) nxt = base[np];
-      if (P + 32 < end) nM = bmw[(P >> 5) + 1];
-      // heads among the valid lanes of this chunk
-      const uint32_t lo = q > P ? q - P : 0u;
-      const uint32_t hi = end - P;  // >= 1
-      uint32_t Mv = M & (0xffffffffu << lo);
-      if (hi < 32) Mv &= (1u << hi) - 1u;
+      uint32_t nn = 0, nnM = 0;
+      if (p + 64u < end) nn = pb[64];
+      if (P + 64u < end) nnM = bmw[2];
+      const uint32_t hi = end - P;  // >= 1: valid lanes are those below hi (and, in chunk 0, from q)
+      const bool valid = lane < hi && p >= q;
+      const uint32_t Mv = hi < 32u ? M & ((1u << hi) - 1u) : M;
       // descriptor of a match that starts at this lane (only meaningful on head lanes)
-      uint32_t b1 = __shfl_down_sync(FULL, cur, 1);
-      uint32_t b2 = __shfl_down_sync(FULL, cur, 2);
-      const uint32_t n0 = __shfl_sync(FULL, nxt, 0);
-      const uint32_t n1 = __shfl_sync(FULL, nxt, 1);
-      if (lane == 31) {
-        b1 = n0;
-        b2 = n1;
-      } else if (lane == 30) {
-        b2 = n0;
-      }
-      const uint32_t desc = cur | (b1 << 8) | (b2 << 16);
+      const uint32_t v = cur | (nxt << 8);
+      const uint32_t t1 = __shfl_sync(FULL, v, src1);
+      const uint32_t t2 = __shfl_sync(FULL, v, src2);
+      const uint32_t desc = lz_prmt(lz_prmt(cur, t1, sel1), t2, sel2);
       // the match this lane may lie in: nearest head at or below the lane, else the carry
-      const uint32_t below = Mv & lz_lanes_below_or_at(lane);
+      const uint32_t below = Mv & le_mask;
       const uint32_t hb = 31u - static_cast<uint32_t>(__clz(static_cast<int>(below | 1u)));
       const uint32_t hdesc = __shfl_sync(FULL, desc, static_cast<int>(hb));
       uint32_t t_o = c_o, t_end = c_end, t_d = c_d;
@@ -132,10 +141,12 @@ __global__ void __launch_bounds__(LZ_THREADS) lz_resolve_kernel(const ResolveArg
         }
         val = __shfl_sync(FULL, val, static_cast<int>(ptr));
       }
-      if (valid) base[p] = static_cast<uint8_t>(val);
+      if (valid) pb[0] = static_cast<uint8_t>(val);
       __syncwarp();
       cur = nxt;
+      nxt = nn;
       M = nM;
+      nM = nnM;
     }
   }
 }
