@@ -8,8 +8,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <new>
 #include <string>
+#include <vector>
 
 namespace {
 
@@ -50,6 +52,9 @@ struct sfb200_ctx {
   uint64_t d_dst_cap = 0;
   uint64_t* d_meta = nullptr;  // src_off, src_len, dst_off, dst_cap, written : 5*n u64, then status n u8
   uint64_t d_meta_n = 0;
+  cudaStream_t hs[3] = {nullptr, nullptr, nullptr};  // H2D | kernels | D2H
+  uint64_t* h_meta = nullptr;  // pinned: written n u64, then status n u8 (so the D2H of the results never blocks the host)
+  uint64_t h_meta_n = 0;
 };
 
 namespace {
@@ -166,6 +171,9 @@ void sfb200_destroy(sfb200_ctx* ctx)
   cudaFree(ctx->d_meta);
   for (auto& e : ctx->ev)
     if (e) cudaEventDestroy(e);
+  for (auto& st : ctx->hs)
+    if (st) cudaStreamDestroy(st);
+  if (ctx->h_meta) cudaFreeHost(ctx->h_meta);
   delete ctx;
 }
 
@@ -295,6 +303,13 @@ int sfb200_checksum_batch_device(sfb200_ctx* ctx, const uint8_t* base, const uin
   return SFB200_RC_OK;
 }
 
+// Host buffers.  The batch is cut into sub-batches of about SFB200_HOST_CHUNK_MB of output
+// (default 1536) that flow through three CUDA streams — H2D of sub-batch k+1, the two kernels of
+// sub-batch k and D2H of sub-batch k-1 overlap — so the call is bounded by the slower PCIe
+// direction, not by the sum of the stages.  dst is NOT uploaded: only bytes the decoder produced
+// are copied back (whole runs of adjacent, completely filled regions in one copy; for a stream
+// that stopped early just its `written` prefix), so everything else in the caller's buffer
+// keeps its value, as the reference guarantees.
 int sfb200_decompress_batch_host(sfb200_ctx* ctx, const uint8_t* src, uint64_t src_bytes,
                                  const uint64_t* src_off, const uint64_t* src_len,
                                  uint8_t* dst, uint64_t dst_bytes, const uint64_t* dst_off,
@@ -312,7 +327,7 @@ int sfb200_decompress_batch_host(sfb200_ctx* ctx, const uint8_t* src, uint64_t s
   SFB_TRY(ctx, cudaSetDevice(ctx->device));
   int rc = grow(ctx, &ctx->d_src, &ctx->d_src_cap, src_bytes + 16);
   if (rc) return rc;
-  rc = grow(ctx, &ctx->d_dst, &ctx->d_dst_cap, dst_bytes + 16);
+  rc = grow(ctx, &ctx->d_dst, &ctx->d_dst_cap, dst_bytes + 64);
   if (rc) return rc;
   if (n > ctx->d_meta_n) {
     if (ctx->d_meta) SFB_TRY(ctx, cudaFree(ctx->d_meta));
@@ -322,6 +337,19 @@ int sfb200_decompress_batch_host(sfb200_ctx* ctx, const uint8_t* src, uint64_t s
     SFB_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_meta), want * (5 * 8 + 1)));
     ctx->d_meta_n = want;
   }
+  if (n > ctx->h_meta_n) {
+    if (ctx->h_meta) SFB_TRY(ctx, cudaFreeHost(ctx->h_meta));
+    ctx->h_meta = nullptr;
+    ctx->h_meta_n = 0;
+    const uint64_t want = n + n / 8 + 64;
+    SFB_TRY(ctx, cudaMallocHost(reinterpret_cast<void**>(&ctx->h_meta), want * 9));
+    ctx->h_meta_n = want;
+  }
+  uint64_t* const wr_host = ctx->h_meta;
+  uint8_t* const st_host = reinterpret_cast<uint8_t*>(ctx->h_meta + ctx->h_meta_n);
+  for (auto& st : ctx->hs)
+    if (!st) SFB_TRY(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  cudaStream_t s_in = ctx->hs[0], s_run = ctx->hs[1], s_out = ctx->hs[2];
   const uint64_t cap_n = ctx->d_meta_n;
   uint64_t* m_src_off = ctx->d_meta;
   uint64_t* m_src_len = m_src_off + cap_n;
@@ -329,22 +357,121 @@ int sfb200_decompress_batch_host(sfb200_ctx* ctx, const uint8_t* src, uint64_t s
   uint64_t* m_dst_cap = m_dst_off + cap_n;
   uint64_t* m_written = m_dst_cap + cap_n;
   uint8_t* m_status = reinterpret_cast<uint8_t*>(m_written + cap_n);
-  cudaStream_t st = nullptr;
-  if (src_bytes) SFB_TRY(ctx, cudaMemcpyAsync(ctx->d_src, src, src_bytes, cudaMemcpyHostToDevice, st));
-  // dst travels both ways so that bytes the decoder never touches keep the caller's values
-  if (dst_bytes) SFB_TRY(ctx, cudaMemcpyAsync(ctx->d_dst, dst, dst_bytes, cudaMemcpyHostToDevice, st));
-  SFB_TRY(ctx, cudaMemcpyAsync(m_src_off, src_off, n * 8, cudaMemcpyHostToDevice, st));
-  SFB_TRY(ctx, cudaMemcpyAsync(m_src_len, src_len, n * 8, cudaMemcpyHostToDevice, st));
-  SFB_TRY(ctx, cudaMemcpyAsync(m_dst_off, dst_off, n * 8, cudaMemcpyHostToDevice, st));
-  SFB_TRY(ctx, cudaMemcpyAsync(m_dst_cap, dst_cap, n * 8, cudaMemcpyHostToDevice, st));
-  rc = sfb200_decompress_batch_device(ctx, ctx->d_src, m_src_off, m_src_len, ctx->d_dst, dst_bytes,
-                                      m_dst_off, m_dst_cap, m_status, m_written, n, st);
+
+  // sub-batches of consecutive streams
+  uint64_t chunk_bytes = 1536ull << 20;
+  if (const char* e = std::getenv("SFB200_HOST_CHUNK_MB")) {
+    const long v = std::atol(e);
+    if (v > 0) chunk_bytes = static_cast<uint64_t>(v) << 20;
+  }
+  if (const char* e = std::getenv("SFB200_HOST_CHUNK_KB")) {  // (tests: force many sub-batches)
+    const long v = std::atol(e);
+    if (v > 0) chunk_bytes = static_cast<uint64_t>(v) << 10;
+  }
+  struct Sub {
+    uint64_t first, count, src_lo, src_hi, dst_lo, dst_hi;
+    cudaEvent_t in_done, run_done, meta_done;
+  };
+  std::vector<Sub> subs;
+  for (uint64_t i = 0; i < n;) {
+    Sub sb{i, 0, ~0ull, 0, ~0ull, 0, nullptr, nullptr, nullptr};
+    uint64_t acc = 0;
+    while (i < n && (sb.count == 0 || acc < chunk_bytes)) {
+      sb.src_lo = std::min(sb.src_lo, src_off[i]);
+      sb.src_hi = std::max(sb.src_hi, src_off[i] + src_len[i]);
+      sb.dst_lo = std::min(sb.dst_lo, dst_off[i]);
+      sb.dst_hi = std::max(sb.dst_hi, dst_off[i] + dst_cap[i]);
+      acc += dst_cap[i] + src_len[i];
+      ++sb.count;
+      ++i;
+    }
+    sb.dst_lo &= ~31ull;  // keep the bitmap phase of the caller's layout
+    subs.push_back(sb);
+  }
+  std::vector<uint64_t> rel_off(n);  // dst offsets relative to each sub-batch's window
+  for (const Sub& sb : subs)
+    for (uint64_t j = 0; j < sb.count; ++j) rel_off[sb.first + j] = dst_off[sb.first + j] - sb.dst_lo;
+  auto cleanup = [&](int code) {
+    for (auto& st : ctx->hs) cudaStreamSynchronize(st);
+    for (Sub& sb : subs)
+      for (cudaEvent_t ev : {sb.in_done, sb.run_done, sb.meta_done})
+        if (ev) cudaEventDestroy(ev);
+    return code;
+  };
+#define SFB_TRYC(call)                                        \
+  do {                                                        \
+    const cudaError_t e_ = (call);                            \
+    if (e_ != cudaSuccess) return cleanup(fail(ctx, e_, #call)); \
+  } while (0)
+  for (Sub& sb : subs) {
+    SFB_TRYC(cudaEventCreateWithFlags(&sb.in_done, cudaEventDisableTiming));
+    SFB_TRYC(cudaEventCreateWithFlags(&sb.run_done, cudaEventDisableTiming));
+    SFB_TRYC(cudaEventCreateWithFlags(&sb.meta_done, cudaEventDisableTiming));
+  }
+  auto enqueue = [&](Sub& sb) -> int {
+    const uint64_t f = sb.first, c = sb.count;
+    if (sb.src_hi > sb.src_lo)
+      SFB_TRYC(cudaMemcpyAsync(ctx->d_src + sb.src_lo, src + sb.src_lo, sb.src_hi - sb.src_lo,
+                               cudaMemcpyHostToDevice, s_in));
+    SFB_TRYC(cudaMemcpyAsync(m_src_off + f, src_off + f, c * 8, cudaMemcpyHostToDevice, s_in));
+    SFB_TRYC(cudaMemcpyAsync(m_src_len + f, src_len + f, c * 8, cudaMemcpyHostToDevice, s_in));
+    SFB_TRYC(cudaMemcpyAsync(m_dst_off + f, rel_off.data() + f, c * 8, cudaMemcpyHostToDevice, s_in));
+    SFB_TRYC(cudaMemcpyAsync(m_dst_cap + f, dst_cap + f, c * 8, cudaMemcpyHostToDevice, s_in));
+    SFB_TRYC(cudaEventRecord(sb.in_done, s_in));
+    SFB_TRYC(cudaStreamWaitEvent(s_run, sb.in_done, 0));
+    const int r = sfb200_decompress_batch_device(ctx, ctx->d_src, m_src_off + f, m_src_len + f,
+                                                 ctx->d_dst + sb.dst_lo, sb.dst_hi - sb.dst_lo,
+                                                 m_dst_off + f, m_dst_cap + f, m_status + f,
+                                                 m_written + f, c, s_run);
+    if (r) return cleanup(r);
+    SFB_TRYC(cudaEventRecord(sb.run_done, s_run));
+    SFB_TRYC(cudaStreamWaitEvent(s_out, sb.run_done, 0));
+    SFB_TRYC(cudaMemcpyAsync(st_host + f, m_status + f, c, cudaMemcpyDeviceToHost, s_out));
+    SFB_TRYC(cudaMemcpyAsync(wr_host + f, m_written + f, c * 8, cudaMemcpyDeviceToHost, s_out));
+    SFB_TRYC(cudaEventRecord(sb.meta_done, s_out));
+    return SFB200_RC_OK;
+  };
+  rc = enqueue(subs[0]);
   if (rc) return rc;
-  if (dst_bytes) SFB_TRY(ctx, cudaMemcpyAsync(dst, ctx->d_dst, dst_bytes, cudaMemcpyDeviceToHost, st));
-  SFB_TRY(ctx, cudaMemcpyAsync(status, m_status, n, cudaMemcpyDeviceToHost, st));
-  if (written) SFB_TRY(ctx, cudaMemcpyAsync(written, m_written, n * 8, cudaMemcpyDeviceToHost, st));
-  SFB_TRY(ctx, cudaStreamSynchronize(st));
-  return SFB200_RC_OK;
+  for (size_t k = 0; k < subs.size(); ++k) {
+    if (k + 1 < subs.size()) {
+      rc = enqueue(subs[k + 1]);
+      if (rc) return rc;
+    }
+    Sub& sb = subs[k];
+    SFB_TRYC(cudaEventSynchronize(sb.meta_done));
+    // bytes produced -> the caller's buffer, in as few copies as the layout allows
+    uint64_t run_lo = 0, run_hi = 0;  // pending run [run_lo, run_hi) of produced bytes
+    auto flush_run = [&]() -> int {
+      if (run_hi > run_lo)
+        SFB_TRYC(cudaMemcpyAsync(dst + run_lo, ctx->d_dst + run_lo, run_hi - run_lo,
+                                 cudaMemcpyDeviceToHost, s_out));
+      run_lo = run_hi = 0;
+      return SFB200_RC_OK;
+    };
+    for (uint64_t j = sb.first; j < sb.first + sb.count; ++j) {
+      const uint64_t w = wr_host[j];
+      status[j] = st_host[j];
+      if (written) written[j] = w;
+      if (w == 0) continue;
+      if (run_hi > run_lo && dst_off[j] == run_hi) {
+        run_hi += w;
+      } else {
+        rc = flush_run();
+        if (rc) return rc;
+        run_lo = dst_off[j];
+        run_hi = run_lo + w;
+      }
+      if (w != dst_cap[j]) {  // the rest of this region is not ours: the run ends here
+        rc = flush_run();
+        if (rc) return rc;
+      }
+    }
+    rc = flush_run();
+    if (rc) return rc;
+  }
+#undef SFB_TRYC
+  return cleanup(SFB200_RC_OK);
 }
 
 int sfb200_decompress(sfb200_ctx* ctx, const uint8_t* src, size_t src_len, uint8_t* dst,

@@ -108,6 +108,29 @@ def test_host_batch_api_matches_device_api(ctx, oracle):
     assert (st == ost).all() and (wr == owr).all() and (dst == dst_o).all()
 
 
+def test_host_batch_api_pipelined_sub_batches(ctx, oracle, monkeypatch):
+    """The host entry point cut into many sub-batches (H2D / kernels / D2H overlapped): ragged
+    regions, gaps, failures and short capacities must come back exactly as from one batch, and
+    every byte the decoder did not produce must keep the caller's value."""
+    monkeypatch.setenv("SFB200_HOST_CHUNK_KB", "48")
+    rng = np.random.default_rng(3)
+    streams, caps = [], []
+    for i in range(300):
+        kind = ["dynamic", "fixed", "stored", "multiblock", "repetitive"][i % 5]
+        plain, comp = T.make_stream(kind, int(rng.integers(1, 30000)), 9000 + i)
+        if i % 9 == 0:
+            comp = comp[: int(rng.integers(0, len(comp)))]
+        streams.append(comp)
+        caps.append(max(0, len(plain) + int(rng.integers(-40, 40)) if i % 4 == 0 else len(plain)))
+    for dst_align in (1, 64):
+        b = T.Batch(streams, caps, dst_align=dst_align)
+        dst = b.new_dst()
+        st, wr = ctx.decompress_batch_host(b.src, b.src_off, b.src_len, dst, b.dst_off, b.dst_cap)
+        dst_o = b.new_dst()
+        ost, owr, _ = oracle.decompress_batch(b.src, b.src_off, b.src_len, dst_o, b.dst_off, b.dst_cap)
+        assert (st == ost).all() and (wr == owr).all() and (dst == dst_o).all()
+
+
 def test_one_bad_stream_does_not_affect_neighbours(ctx, oracle):
     plain, comp = T.make_stream("dynamic", 30000, 1)
     streams = [comp, comp[:100], comp, b"\x07", comp]
