@@ -673,18 +673,17 @@ __device__ __forceinline__ uint32_t lut_lookup(const uint16_t* lut, int root_off
 }
 
 // The same lookup for the token loop, on shared-window addresses: `lutb` is the address of this
-// lane's element 0, element j sits 64*j bytes further.
+// lane's element 0, element j sits 64*j bytes further.  Branch-free: the second-level load is
+// always made (some lane of the warp needs it on practically every token anyway) and selected.
 template <int ROOT, int ROOT_OFF, int POOL_OFF, uint32_t POOL>
 __device__ __forceinline__ uint32_t lut_lookup_s(saddr_t lutb, uint32_t bits)
 {
-  uint32_t e = lds16(lutb + (ROOT_OFF * 64) + ((bits << 6) & (((1u << ROOT) - 1u) << 6)));
-  if ((e & (E_PTR | 15u)) == E_PTR) {  // sub-table pointer (codes longer than ROOT)
-    const uint32_t sb = (e >> 12) & 7u;
-    uint32_t idx = ((e >> 4) & 0xffu) + ((bits >> ROOT) & ~(0xffffffffu << sb));
-    idx = idx < POOL ? idx : POOL - 1u;  // (stale tables on idle lanes: stay inside the slice)
-    e = lds16(lutb + (POOL_OFF * 64) + (idx << 6));
-  }
-  return e;
+  const uint32_t e = lds16(lutb + (ROOT_OFF * 64) + ((bits << 6) & (((1u << ROOT) - 1u) << 6)));
+  const uint32_t sb = (e >> 12) & 7u;
+  uint32_t idx = ((e >> 4) & 0xffu) + ((bits >> ROOT) & ~(0xffffffffu << sb));
+  idx = idx < POOL ? idx : POOL - 1u;  // (a direct entry is not a pointer: stay inside the slice)
+  const uint32_t e2 = lds16(lutb + (POOL_OFF * 64) + (idx << 6));
+  return (e & (E_PTR | 15u)) == E_PTR ? e2 : e;
 }
 
 // lane states

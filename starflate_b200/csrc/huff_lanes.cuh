@@ -54,6 +54,8 @@ struct TokWin {
   uint32_t vpos;    // virtual position of the next byte to produce
   uint32_t vend;    // virtual position one past the capacity
   uint64_t obuf;
+  uint64_t first;   // word 0 of an unaligned dst once the cursor has left it: its bytes before
+                    // `lead` are not ours, so it is written bytewise at the end (flush_tail)
   uint32_t* bm;     // bitmap word that holds the bit of output byte 0
   uint32_t qml;     // (bit of output byte 0 within *bm) - lead, mod 2^32
   uint32_t mword;   // index, from bm, of the bitmap word `macc` belongs to
@@ -67,6 +69,7 @@ struct TokWin {
     vpos = lead;
     vend = lead + cap;
     obuf = 0;
+    first = 0;
     bm = bits + (off >> 5);
     qml = static_cast<uint32_t>(off & 31u) - lead;
     mword = 0;
@@ -76,7 +79,7 @@ struct TokWin {
   {
     al = nullptr;
     lead = vpos = vend = 0;
-    obuf = 0;
+    obuf = first = 0;
     bm = nullptr;
     qml = mword = macc = 0;
   }
@@ -84,20 +87,10 @@ struct TokWin {
   __device__ __forceinline__ uint32_t written() const { return vpos - lead; }
   __device__ __forceinline__ uint32_t room() const { return vend - vpos; }
 
-  // store the word at 8-aligned virtual position wv
-  __device__ __forceinline__ void store_word(uint32_t wv, uint64_t v)
-  {
-    if (wv >= lead) {
-      *reinterpret_cast<uint64_t*>(al + wv) = v;
-    } else {  // first word of an unaligned dst: bytes before `lead` are not ours
-      for (uint32_t b = lead; b < 8; ++b) al[b] = static_cast<uint8_t>(v >> (8 * b));
-    }
-  }
-
   // The one output step of a token: append the n (0..3) low bytes of `chunk` at the cursor,
   // then move the cursor `skipn` bytes further over bytes pass 2 will produce (the body of a
   // match).  A word the cursor leaves is stored whole: its bytes past the appended ones all
-  // belong to the match body, so any value will do there.
+  // belong to the match body, so any value will do there.  No branches: two predicated stores.
   __device__ __forceinline__ void emit(uint32_t chunk, uint32_t n, uint32_t skipn)
   {
 #ifdef SFB_TRACE_EMIT
@@ -108,34 +101,29 @@ struct TokWin {
     const uint64_t merged = obuf | (static_cast<uint64_t>(chunk) << sh);  // chunk < 2^(8n)
     const uint32_t np = vpos + n + skipn;
     const uint32_t wv = vpos & ~7u;
-    const bool leaves = (np & ~7u) != wv;
+    const uint32_t nw = np & ~7u;
+    const bool leaves = nw != wv;
     const bool spill = k + n > 8u;                         // the chunk reaches into the next word
     const uint32_t carry = chunk >> ((64u - sh) & 31u);    // ... with these bytes (sh >= 48 then)
-    const bool stay = (np & ~7u) == wv + 8u;               // the cursor ends in the next word
-    if (leaves) {
-      store_word(wv, merged);
-      if (spill && !stay) store_word(wv + 8u, carry);      // skipped past that word too
-    }
-    obuf = leaves ? ((spill && stay) ? carry : 0u) : merged;
+    const bool stay = nw == wv + 8u;                       // the cursor ends in the next word
+    const bool head = wv < lead;                           // word 0 of an unaligned dst
+    if (leaves & !head) *reinterpret_cast<uint64_t*>(al + wv) = merged;
+    if (leaves & head) first = merged;
+    if (leaves & spill & !stay) *reinterpret_cast<uint64_t*>(al + wv + 8u) = carry;  // skipped past it too
+    obuf = leaves ? ((spill & stay) ? carry : 0u) : merged;
     vpos = np;
   }
 
-  __device__ __forceinline__ void flush_bits()
-  {
-    // (bitmap words at the edges of a dst region are shared with the neighbouring streams)
-    if (macc) atomicOr(bm + mword, macc);
-    macc = 0;
-  }
-  // a match starts at the cursor
-  __device__ __forceinline__ void mark_head()
+  // a match starts at the cursor iff `is_head` (branch-free: one predicated RED)
+  __device__ __forceinline__ void mark_head(bool is_head)
   {
     const uint32_t bidx = vpos + qml;
     const uint32_t w = bidx >> 5;
-    if (w != mword) {
-      flush_bits();
-      mword = w;
-    }
-    macc |= 1u << (bidx & 31u);
+    const bool moved = is_head & (w != mword);
+    // (bitmap words at the edges of a dst region are shared with the neighbouring streams)
+    if (moved & (macc != 0)) atomicOr(bm + mword, macc);
+    macc = (moved ? 0u : macc) | (is_head ? 1u << (bidx & 31u) : 0u);
+    mword = is_head ? w : mword;
   }
 
   // pending bytes of the open word -> memory, bytewise (the window stays as it is)
@@ -148,7 +136,12 @@ struct TokWin {
   // the cursor was moved over bytes written straight to memory: re-read the open word
   __device__ __forceinline__ void jump(uint32_t n)
   {
+    const bool left0 = (vpos & ~7u) < lead && ((vpos + n) & ~7u) != 0;  // leaving word 0
     vpos += n;
+    if (left0) {  // all of its bytes from `lead` on are in memory now: keep `first` consistent
+      first = 0;
+      for (uint32_t b = lead; b < 8; ++b) first |= static_cast<uint64_t>(al[b]) << (8 * b);
+    }
     const uint32_t wv = vpos & ~7u;
     obuf = 0;
     for (uint32_t b = wv < lead ? lead : wv; b < vpos; ++b)
@@ -158,7 +151,10 @@ struct TokWin {
   __device__ __forceinline__ void flush_tail()
   {
     spill_pending();
-    flush_bits();
+    if (lead != 0 && vpos >= 8u)  // the cursor left word 0: its bytes from `lead` on are still pending
+      for (uint32_t b = lead; b < 8; ++b) al[b] = static_cast<uint8_t>(first >> (8 * b));
+    if (macc) atomicOr(bm + mword, macc);
+    macc = 0;
   }
 };
 
@@ -273,11 +269,15 @@ huff_lanes_kernel(const BatchArgs a)
       // ---- token iterations (all 32 lanes stay in this loop together) -----------------------
       uint32_t it = 0;
       while (__any_sync(FULL, state == S_DECODE)) {
-        // ---- decode one token (straight-line; results are only used by lanes in S_DECODE,
-        //      the others compute on stale data and discard) ----------------------------------
+        // ---- decode one token.  Straight-line and nearly branch-free (results are only used by
+        //      lanes in S_DECODE, the others compute on stale data and discard): the two rare
+        //      branches are the exact slow path and a token that does not fit the output. -----
         bool dec = state == S_DECODE;
         SFB_STAT(tokens);
         const uint32_t bo0 = br.bo;   // < 32
+        // while no window word reaches past the end of the stream every bit the token can see
+        // is real (a token is <= 48 of the >= 65 window bits); otherwise go the exact way
+        const bool tail = br.tail();
         uint32_t n0, n1;
         br.next2(n0, n1);
         const uint32_t bits = br.peek();
@@ -295,51 +295,39 @@ huff_lanes_kernel(const BatchArgs a)
         const uint32_t dxb = dinfo >> 16;
         uint32_t dist = (dinfo & 0xffffu) + ((dbits >> dL) & ~(0xffffffffu << dxb));
         uint32_t used = used1 + (is_match ? dL + dxb : 0u);
-        bool eob = false;
         // anything that is not a plain literal / length+distance — end of block included — is
         // redone exactly, from the same 64 window bits
-        const uint64_t snap = (static_cast<uint64_t>(bits_hi) << 32) | bits;
-        if (dec & ((L == 0) | (is_match & (dL == 0)))) {
+        if (dec & ((L == 0) | (is_match & (dL == 0)) | tail)) {
           SFB_STAT(slow_tokens);
-          const SlowToken t = slow_token(m.lens, snap, br.real_left());
+          const SlowToken t = slow_token(m.lens, (static_cast<uint64_t>(bits_hi) << 32) | bits,
+                                         br.real_left());
           used = t.used;
           is_match = t.kind == 2;
-          eob = t.kind == 1;
           value = static_cast<uint32_t>(t.value);
           dist = static_cast<uint32_t>(t.dist);
-          if (t.status != ST_SUCCESS) {
+          if (t.status != ST_SUCCESS || t.kind == 1) {  // failure, or end of block
             status = t.status;
-            state = S_DONE;
+            state = (t.status == ST_SUCCESS && !final_block) ? S_HEADER : S_DONE;
             dec = false;
+            // (the end-of-block code is consumed: the next header starts right behind it)
+            if (t.status == ST_SUCCESS) br.skip(used);
           }
         }
         if (dec) br.skip(used);
         br.norm2(n0, n1);
-        if (dec & br.tail()) {
-          if (br.real_left() < 0) {
-            // the token reaches past the end of the input: the same bits with the true count
-            // of real ones give the reference's status (never Success)
-            SFB_STAT(slow_tokens);
-            const SlowToken t = slow_token(m.lens, snap, br.real_left() + static_cast<int64_t>(used));
-            status = t.status != ST_SUCCESS ? t.status : ST_SRC_TOO_SMALL;
-            state = S_DONE;
-            dec = false;
-          }
-        }
         if (it & 1u) br.stage_step();
         ++it;
         // ---- act on the token ----------------------------------------------------------------
         // (src/decompress.cpp:178-183 distance then room for a match, :150-152 room for a
         //  literal; nothing of a token that fails is written)
         const bool bad_dist = is_match & (dist > ow.written());
-        const bool bad = bad_dist | (ow.room() < (is_match ? value : 1u));
-        if (dec & (eob | bad)) {
-          status = eob ? ST_SUCCESS : bad_dist ? ST_INVALID_DISTANCE : ST_DST_TOO_SMALL;
-          state = (eob && !final_block) ? S_HEADER : S_DONE;
+        if (dec & (bad_dist | (ow.room() < (is_match ? value : 1u)))) {
+          status = bad_dist ? ST_INVALID_DISTANCE : ST_DST_TOO_SMALL;
+          state = S_DONE;
           dec = false;
         }
         const bool mt = dec & is_match;
-        if (mt) ow.mark_head();
+        ow.mark_head(mt);
         const uint32_t desc = (value - 3u) | ((dist - 1u) << 8);
         ow.emit(dec ? (mt ? desc : value) : 0u, dec ? (mt ? 3u : 1u) : 0u, mt ? value - 3u : 0u);
       }
