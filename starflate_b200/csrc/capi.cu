@@ -205,8 +205,11 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
   if (!src_off || !src_len || !dst_off || !dst_cap || !status) return SFB200_RC_BAD_ARGUMENT;
   SFB_TRY(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-  // scratch: one bit per dst byte (+ a guard word), grown on demand and kept
-  const uint64_t bits_words = dst_bytes / 32 + 2;
+  // the kernels index dst (and the bitmap) from a 128-byte aligned base
+  const uint64_t delta = reinterpret_cast<uintptr_t>(dst_base) & 127u;
+  dst_base -= delta;
+  // scratch: one bit per dst byte (+ guard words), grown on demand and kept
+  const uint64_t bits_words = (dst_bytes + delta) / 32 + 8;
   if (bits_words > ctx->d_bits_words) {
     if (ctx->d_bits) SFB_TRY(ctx, cudaFree(ctx->d_bits));
     ctx->d_bits = nullptr;
@@ -237,6 +240,7 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
   a.src_off = src_off;
   a.src_len = src_len;
   a.dst_base = dst_base;
+  a.dst_delta = delta;
   a.dst_off = dst_off;
   a.dst_cap = dst_cap;
   a.status = status;
@@ -258,6 +262,7 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
   // pass 2: LZ77 back-references, one warp per stream
   sfb::ResolveArgs r;
   r.dst_base = dst_base;
+  r.dst_delta = delta;
   r.dst_off = dst_off;
   r.written = written;
   r.match_bits = ctx->d_bits;

@@ -49,7 +49,8 @@ struct BatchArgs {
   const uint8_t* src_base;
   const uint64_t* src_off;
   const uint64_t* src_len;
-  uint8_t* dst_base;
+  uint8_t* dst_base;       // 128-byte aligned
+  uint64_t dst_delta;      // added to every dst_off (the caller's dst_base - this dst_base)
   const uint64_t* dst_off;
   const uint64_t* dst_cap;
   uint8_t* status;

@@ -237,7 +237,7 @@ huff_lanes_kernel(const BatchArgs a)
         live = false;
       } else {
         br.open(a.src_base + a.src_off[idx], static_cast<uint32_t>(slen), ring);
-        ow.open(a.dst_base, a.dst_off[idx], static_cast<uint32_t>(cap), a.match_bits);
+        ow.open(a.dst_base, a.dst_off[idx] + a.dst_delta, static_cast<uint32_t>(cap), a.match_bits);
         state = S_HEADER;
       }
     }

@@ -1,5 +1,5 @@
 // Pass 2 of the batched raw-DEFLATE decoder for sm_100a: LZ77 back-references, ONE WARP PER
-// STREAM, one output byte per lane, 32-byte chunks aligned with the match-head bitmap.
+// STREAM, 128-byte chunks, one aligned 32-bit word (4 output bytes) per lane.
 //
 // Replaces the copy half of the reference's decompress_length_distance and copy_from_before
 // (src/decompress.cpp:157-187,388-398): pass 1 (huff_lanes.cuh) has already placed literals and
@@ -7,23 +7,23 @@
 // the match start plus a bit in the match-head bitmap; this pass turns each descriptor into the
 // bytes the reference would have copied.  All range/room checks were made in pass 1.
 //
-// Per 32-byte chunk [P, P+32) of a stream's output (P a multiple of 32 from dst_base):
-//   1. one bitmap word M says which lanes sit on a match head; those lanes assemble their
-//      descriptor from their own byte and the next two (the chunk after is prefetched, so a
-//      head in lanes 30/31 finds its bytes there);
-//   2. every lane finds the nearest head at or below it (clz on M below the lane), or falls
-//      back to the match carried in from earlier chunks, and so learns whether it lies inside
-//      a match and at which offset k;
-//   3. a covered lane's byte is the byte at  start - distance + (k mod distance)  — the
-//      forward-overlapping copy of copy_from_before() is periodic with period `distance`, so
-//      the source always lies BEFORE the match start.  Sources below P are final in memory
-//      (earlier chunks, ordered by __syncwarp) and are gathered; sources inside this chunk are
-//      lower lanes, resolved by pointer doubling with shuffles (chains only pass through
-//      different matches, so their depth is at most the number of matches in the chunk);
-//   4. the whole chunk is stored back (one 32-byte sector per warp store).
-// Streams are pulled from a global counter.  A stream's chunks are processed in order, so the
-// 32 KiB window a match may reach into was written by this same warp a few thousand
-// instructions earlier: with ~5k streams in flight the windows stay in the 126 MB L2.
+// Per 128-byte chunk [P, P+128) of a stream's output (128-byte aligned addresses):
+//   1. every lane loads its word and the 4 bitmap bits of its bytes; lanes with a match head
+//      assemble the descriptor from their word and the next lane's (lane 31: the next chunk's
+//      first word, which is prefetched) and publish their LAST head as one packed 30-bit value;
+//   2. the match a lane's first byte may lie in is the last head of the nearest lower lane that
+//      has one (ballot + FLO + one shuffle), else the match carried in from earlier chunks;
+//      the lane then walks its 4 bytes, switching to its own heads as it passes them;
+//   3. a covered byte's source is  start - distance + (k mod distance)  — the forward-
+//      overlapping copy of copy_from_before() is periodic with period `distance` — which always
+//      lies BEFORE the match start;
+//   4. resolution rounds: with F the first byte of the chunk that is still unresolved, every
+//      unresolved byte whose source lies below F is gathered from memory (below P: written by
+//      earlier chunks; in [P, F): literals of pass 1 or bytes stored by an earlier round, made
+//      visible by __syncwarp), the words are stored, F advances.  The first unresolved match
+//      always resolves completely (its sources precede its start), text-like data needs 2-3
+//      rounds per chunk, a chunk without near references one.
+// Streams are pulled from a global counter.
 #pragma once
 
 #include <cstdint>
@@ -34,7 +34,8 @@
 namespace sfb {
 
 struct ResolveArgs {
-  uint8_t* dst_base;
+  uint8_t* dst_base;           // 128-byte aligned
+  uint64_t dst_delta;          // added to every dst_off (the caller's dst_base - this dst_base)
   const uint64_t* dst_off;
   const uint64_t* written;
   const uint32_t* match_bits;  // bit k <-> dst_base[k]
@@ -56,97 +57,130 @@ __device__ __forceinline__ uint32_t lz_prmt(uint32_t a, uint32_t b, uint32_t sel
   return __byte_perm(a, b, sel);
 #endif
 }
+// bits [s, s+32) of hi:lo, 0 <= s < 32
+__device__ __forceinline__ uint32_t lz_funnel(uint32_t lo, uint32_t hi, uint32_t s)
+{
+#ifdef SFB_CPU_EMU
+  return static_cast<uint32_t>(((static_cast<uint64_t>(hi) << 32) | lo) >> (s & 31u));
+#else
+  return __funnelshift_r(lo, hi, s);
+#endif
+}
 
 __global__ void __launch_bounds__(LZ_THREADS) lz_resolve_kernel(const ResolveArgs a)
 {
   constexpr unsigned FULL = 0xffffffffu;
   const uint32_t lane = threadIdx.x & 31u;
-  // loop invariants of the descriptor assembly: lane l takes bytes l+1 and l+2 of the chunk;
-  // for lanes 31 / 30,31 they are bytes 0 / 0,1 of the NEXT chunk, which travel in byte 1 of
-  // the shuffled value (v = cur | nxt << 8)
-  const int src1 = static_cast<int>((lane + 1u) & 31u), src2 = static_cast<int>((lane + 2u) & 31u);
-  const uint32_t sel1 = lane == 31u ? 0x7750u : 0x7740u;  // {cur.b0, t1.b0 | t1.b1, 0(b3 of cur: 0), ...}
-  const uint32_t sel2 = lane >= 30u ? 0x7510u : 0x7410u;  // {d.b0, d.b1, t2.b0 | t2.b1, 0}
-  const uint32_t le_mask = 0xffffffffu >> (31u - lane);   // lanes at or below this one
+  const uint32_t lt_mask = (1u << lane) - 1u;             // lanes below this one
+  const int next_lane = static_cast<int>((lane + 1u) & 31u);
+  const uint32_t bit_sh = 4u * (lane & 7u);               // my 4 bits inside my bitmap word
   for (;;) {
     unsigned long long si = 0;
     if (lane == 0) si = atomicAdd(a.stream_counter, 1ull);
     si = __shfl_sync(FULL, si, 0);
     if (si >= a.n) break;
-    const uint64_t off = a.dst_off[si];
+    const uint64_t off = a.dst_off[si] + a.dst_delta;
     const uint64_t wr = a.written[si];
     if (wr == 0) continue;
     // virtual positions: byte v of the view sits at base[v]; the stream occupies [q, end)
-    uint8_t* const base = a.dst_base + (off & ~31ull);
-    const uint32_t* bmw = a.match_bits + (off >> 5);
-    const uint32_t q = static_cast<uint32_t>(off & 31u);
+    uint8_t* const base = a.dst_base + (off & ~127ull);
+    const uint32_t q = static_cast<uint32_t>(off & 127u);
     const uint32_t end = q + static_cast<uint32_t>(wr);
+    // this lane's word and bitmap word of the current chunk, and of the two after it
+    const uint32_t* pw = reinterpret_cast<const uint32_t*>(base) + lane;
+    const uint32_t* pm = a.match_bits + ((off & ~127ull) >> 5) + (lane >> 3);
+    // a word is read iff one of its bytes belongs to the stream (never a word wholly outside)
+    auto load_w = [&](uint32_t P) -> uint32_t {
+      const uint32_t wp = P + 4u * lane;
+      return (wp + 4u > q && wp < end) ? pw[P >> 2] : 0u;
+    };
+    auto load_m = [&](uint32_t P) -> uint32_t { return P < end ? pm[P >> 5] : 0u; };
+    uint32_t cw = load_w(0), ncw = load_w(128), mw = load_m(0), nmw = load_m(128);
     // the most recent match seen so far: [c_o, c_end) at distance c_d (none yet: empty range)
     uint32_t c_o = 0, c_end = 0, c_d = 1;
-    // two chunks of pass-1 bytes and bitmap words are kept in flight ahead of the one being
-    // resolved (nothing a chunk's resolution stores can change them: it only writes its own
-    // 32 bytes)
-    uint8_t* pb = base + lane;  // this lane's byte of the current chunk
-    uint32_t cur = 0, nxt = 0, M, nM = 0;
-    if (lane >= q && lane < end) cur = pb[0];
-    if (lane + 32u < end) nxt = pb[32];
-    M = bmw[0] & (0xffffffffu << q);
-    if (32u < end) nM = bmw[1];
-    for (uint32_t P = 0; P < end; P += 32, pb += 32, ++bmw) {
-      const uint32_t p = P + lane;
-      uint32_t nn = 0, nnM = 0;
-      if (p + 64u < end) nn = pb[64];
-      if (P + 64u < end) nnM = bmw[2];
-      const uint32_t hi = end - P;  // >= 1: valid lanes are those below hi (and, in chunk 0, from q)
-      const bool valid = lane < hi && p >= q;
-      const uint32_t Mv = hi < 32u ? M & ((1u << hi) - 1u) : M;
-      // descriptor of a match that starts at this lane (only meaningful on head lanes)
-      const uint32_t v = cur | (nxt << 8);
-      const uint32_t t1 = __shfl_sync(FULL, v, src1);
-      const uint32_t t2 = __shfl_sync(FULL, v, src2);
-      const uint32_t desc = lz_prmt(lz_prmt(cur, t1, sel1), t2, sel2);
-      // the match this lane may lie in: nearest head at or below the lane, else the carry
-      const uint32_t below = Mv & le_mask;
-      const uint32_t hb = 31u - static_cast<uint32_t>(__clz(static_cast<int>(below | 1u)));
-      const uint32_t hdesc = __shfl_sync(FULL, desc, static_cast<int>(hb));
+    for (uint32_t P = 0; P < end; P += 128) {
+      const uint32_t nncw = load_w(P + 256), nnmw = load_m(P + 256);
+      const uint32_t wp = P + 4u * lane;
+      // valid bytes of my word
+      uint32_t vm = 15u;
+      if (P < q || P + 128u > end) {  // (warp-uniform: first / last chunk of the stream)
+        const uint32_t lo = q > wp ? (q - wp < 4u ? q - wp : 4u) : 0u;
+        const uint32_t hi = end > wp ? (end - wp < 4u ? end - wp : 4u) : 0u;
+        vm = hi > lo ? ((1u << hi) - 1u) & ~((1u << lo) - 1u) : 0u;
+      }
+      const uint32_t hb4 = (mw >> bit_sh) & vm;  // match heads among my bytes
+      // the word after mine (lane 31: first word of the next chunk)
+      const uint32_t t = __shfl_sync(FULL, cw, next_lane);
+      const uint32_t u = __shfl_sync(FULL, ncw, 0);
+      const uint32_t nx = lane == 31u ? u : t;
+      // my last head, packed: position in chunk (7 bits) | descriptor (23 bits)
+      const uint32_t hl = 31u - static_cast<uint32_t>(__clz(static_cast<int>(hb4 | 1u)));
+      const uint32_t own_pack = (4u * lane + hl) | ((lz_funnel(cw, nx, 8u * hl) & 0xffffffu) << 7);
+      const uint32_t hm = __ballot_sync(FULL, hb4 != 0);
+      // the match my first byte may lie in
+      const uint32_t below = hm & lt_mask;
+      const uint32_t sl = 31u - static_cast<uint32_t>(__clz(static_cast<int>(below | 1u)));
+      const uint32_t in_pack = __shfl_sync(FULL, own_pack, static_cast<int>(sl));
       uint32_t t_o = c_o, t_end = c_end, t_d = c_d;
       if (below) {
-        t_o = P + hb;
-        t_end = t_o + (hdesc & 0xffu) + 3u;
-        t_d = (hdesc >> 8) + 1u;
+        t_o = P + (in_pack & 127u);
+        t_end = t_o + ((in_pack >> 7) & 255u) + 3u;
+        t_d = (in_pack >> 15) + 1u;
       }
-      if (Mv) {  // warp-uniform: the last head of this chunk is carried into the next ones
-        const uint32_t top = 31u - static_cast<uint32_t>(__clz(static_cast<int>(Mv)));
-        const uint32_t tdesc = __shfl_sync(FULL, desc, static_cast<int>(top));
-        c_o = P + top;
-        c_end = c_o + (tdesc & 0xffu) + 3u;
-        c_d = (tdesc >> 8) + 1u;
+      if (hm) {  // warp-uniform: the last head of this chunk is carried into the next ones
+        const uint32_t top = 31u - static_cast<uint32_t>(__clz(static_cast<int>(hm)));
+        const uint32_t pk = __shfl_sync(FULL, own_pack, static_cast<int>(top));
+        c_o = P + (pk & 127u);
+        c_end = c_o + ((pk >> 7) & 255u) + 3u;
+        c_d = (pk >> 15) + 1u;
       }
-      const bool covered = valid && p < t_end;
-      uint32_t val = cur;
-      uint32_t ptr = lane;
-      if (covered) {
+      // walk my 4 bytes
+      uint32_t src[4];
+      uint32_t pend = 0;
+#pragma unroll
+      for (uint32_t b = 0; b < 4; ++b) {
+        const uint32_t p = wp + b;
+        if ((hb4 >> b) & 1u) {
+          const uint32_t d = lz_funnel(cw, nx, 8u * b) & 0xffffffu;
+          t_o = p;
+          t_end = p + (d & 255u) + 3u;
+          t_d = (d >> 8) + 1u;
+        }
         uint32_t k = p - t_o;
         if (k >= t_d) k %= t_d;
-        const uint32_t src = t_o - t_d + k;  // >= q: pass 1 checked distance <= written
-        if (src >= P) ptr = src - P;         // a lower lane of this chunk
-        else val = base[src];                // final since an earlier chunk
+        src[b] = t_o - t_d + k;  // >= q: pass 1 checked distance <= written
+        if (((vm >> b) & 1u) && p < t_end) pend |= 1u << b;
       }
-      if (__any_sync(FULL, ptr != lane)) {
-        for (;;) {
-          const uint32_t pp = __shfl_sync(FULL, ptr, static_cast<int>(ptr));
-          const bool fix = pp == ptr;
-          ptr = pp;
-          if (__all_sync(FULL, fix)) break;
+      // resolution rounds
+      uint32_t res = cw;
+      for (;;) {
+        // F = first unresolved byte of the chunk (P + 128 if none)
+        const uint32_t pm_any = __ballot_sync(FULL, pend != 0);
+        if (pm_any == 0) break;
+        const int fl = __ffs(static_cast<int>(pm_any)) - 1;
+        const uint32_t fp = __shfl_sync(FULL, pend, fl);
+        const uint32_t F = P + 4u * static_cast<uint32_t>(fl) + static_cast<uint32_t>(__ffs(static_cast<int>(fp)) - 1);
+#pragma unroll
+        for (uint32_t b = 0; b < 4; ++b) {
+          if (((pend >> b) & 1u) && src[b] < F) {
+            const uint32_t byte = base[src[b]];
+            res = lz_prmt(res, byte, 0x3210u ^ ((0x4u ^ b) << (4u * b)));  // byte b <- `byte`
+            pend &= ~(1u << b);
+          }
         }
-        val = __shfl_sync(FULL, val, static_cast<int>(ptr));
+        if (vm == 15u) {
+          *reinterpret_cast<uint32_t*>(base + wp) = res;
+        } else {  // first / last word of the stream: only our bytes
+#pragma unroll
+          for (uint32_t b = 0; b < 4; ++b)
+            if ((vm >> b) & 1u) base[wp + b] = static_cast<uint8_t>(res >> (8u * b));
+        }
+        __syncwarp();
       }
-      if (valid) pb[0] = static_cast<uint8_t>(val);
-      __syncwarp();
-      cur = nxt;
-      nxt = nn;
-      M = nM;
-      nM = nnM;
+      cw = ncw;
+      ncw = nncw;
+      mw = nmw;
+      nmw = nnmw;
     }
   }
 }

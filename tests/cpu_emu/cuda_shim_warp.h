@@ -61,6 +61,7 @@ static inline unsigned __ballot_sync(unsigned, int p)
 static inline int __any_sync(unsigned mask, int p) { return __ballot_sync(mask, p) != 0; }
 static inline int __all_sync(unsigned mask, int p) { return __ballot_sync(mask, p) == 0xffffffffu; }
 static inline void __syncwarp() { emu_warp->bar.arrive_and_wait(); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz(static_cast<unsigned>(v)); }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v)
 {

@@ -17,7 +17,7 @@ static unsigned long long emu_stat_tokens = 0, emu_stat_slow_tokens = 0;
 using EmuCfg = sfb::Cfg<SFB_EMU_ROOT_LIT, SFB_EMU_ROOT_DIST, SFB_EMU_POOL, 1>;
 
 extern "C" void emu_lz_resolve(uint8_t* dst_base, const uint64_t* dst_off, const uint64_t* written,
-                               const uint32_t* match_bits, uint64_t n);
+                               const uint32_t* match_bits, uint64_t n);  // dst_base 128-byte aligned
 
 // the in-place token format of huff_lanes.cuh, resolved byte by byte
 static void scalar_resolve(uint8_t* dst_base, uint64_t off, uint64_t written, const uint32_t* bits)
@@ -52,7 +52,7 @@ extern "C" int emu_decompress_batch(const uint8_t* src, const uint64_t* src_off,
   emu_smem = smem.data();
   blockDim.x = 1;  // one emulated lane
   gridDim.x = 1;
-  constexpr size_t PAD = 96;
+  constexpr size_t PAD = 320;
   for (uint64_t i = 0; i < n; ++i) {
     const uint8_t* s = src + src_off[i];
     uint8_t* d = dst + dst_off[i];
@@ -67,9 +67,11 @@ extern "C" int emu_decompress_batch(const uint8_t* src, const uint64_t* src_off,
     uint8_t* dp = place(dbuf, d);
     if (src_len[i]) std::memcpy(sp, s, src_len[i]);
     if (dst_cap[i]) std::memcpy(dp, d, dst_cap[i]);
-    const uint64_t doff = dst_off[i] & 31u;  // keep the bitmap phase of the real layout
-    uint8_t* dbase = dp - doff;
-    std::vector<uint32_t> bits((doff + dst_cap[i]) / 32 + 2, 0u);
+    // the kernels want a 128-byte aligned dst base: the aligned address below dp, with the
+    // stream at the offset that falls out (its low bits follow the caller's layout mod 16)
+    uint8_t* dbase = reinterpret_cast<uint8_t*>(reinterpret_cast<uintptr_t>(dp) & ~uintptr_t{127});
+    const uint64_t doff = static_cast<uint64_t>(dp - dbase);
+    std::vector<uint32_t> bits((doff + dst_cap[i]) / 32 + 8, 0u);
     unsigned long long counter = 0;
     const uint64_t zero = 0;
     uint64_t wr = 0;
@@ -78,6 +80,7 @@ extern "C" int emu_decompress_batch(const uint8_t* src, const uint64_t* src_off,
     a.src_off = &zero;
     a.src_len = &src_len[i];
     a.dst_base = dbase;
+    a.dst_delta = 0;
     a.dst_off = &doff;
     a.dst_cap = &dst_cap[i];
     a.status = &status[i];

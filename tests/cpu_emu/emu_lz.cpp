@@ -16,6 +16,7 @@ extern "C" void emu_lz_resolve(uint8_t* dst_base, const uint64_t* dst_off, const
   unsigned long long counter = 0;
   sfb::ResolveArgs a;
   a.dst_base = dst_base;
+  a.dst_delta = 0;
   a.dst_off = dst_off;
   a.written = written;
   a.match_bits = match_bits;

@@ -81,3 +81,16 @@ def test_warp_pass2_emulation_vs_oracle(emu, oracle, golden):
     assert (st == ost).all() and (wr == owr).all()
     assert (dst_e == dst_o).all()
     _check_family(emu, oracle, golden, "known_answers", 1, warp_pass2=True)
+    # longer streams: windows that wrap many chunks, distance-1 runs, far and near references
+    streams, caps = [], []
+    for i, (kind, size) in enumerate([("dynamic", 70000), ("repetitive", 90000), ("multiblock", 40000),
+                                      ("fixed", 30000), ("repetitive", 5000), ("dynamic", 12345)]):
+        plain, comp = T.make_stream(kind, size, 4100 + i)
+        streams.append(comp)
+        caps.append(len(plain) - (7 if i == 2 else 0))
+    b = T.Batch(streams, caps, dst_align=1)
+    dst_e, dst_o = b.new_dst(), b.new_dst()
+    st, wr = emu.decompress_batch(b, dst_e, warp_pass2=True)
+    ost, owr, _ = oracle.decompress_batch(b.src, b.src_off, b.src_len, dst_o, b.dst_off, b.dst_cap)
+    assert (st == ost).all() and (wr == owr).all()
+    assert (dst_e == dst_o).all()
