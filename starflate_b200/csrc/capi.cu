@@ -25,6 +25,7 @@ namespace {
 #define SFB_LZ_CTAS_PER_SM 0  /* 0 = as many as fit */
 #endif
 using LaneCfg = sfb::Cfg<SFB_ROOT_LIT, SFB_ROOT_DIST, SFB_POOL, SFB_WARPS>;
+constexpr uint64_t kMaxWaves = 256;  // work counters per call: [2k] pass 1, [2k+1] pass 2 of wave k
 
 }  // namespace
 
@@ -35,7 +36,7 @@ struct sfb200_ctx {
   int regs_per_thread = 0;
   int lz_ctas_per_sm = 0;
   int lz_regs_per_thread = 0;
-  unsigned long long* d_counter = nullptr;  // [0] pass-1 group counter, [1] pass-2 stream counter
+  unsigned long long* d_counter = nullptr;  // 2 * kMaxWaves work counters
   uint32_t* d_lens = nullptr;  // per-resident-lane code-length scratch
   uint32_t* d_bits = nullptr;  // match-head bitmap: 1 bit per dst byte (grown on demand)
   uint64_t d_bits_words = 0;
@@ -53,6 +54,8 @@ struct sfb200_ctx {
   uint64_t* d_meta = nullptr;  // src_off, src_len, dst_off, dst_cap, written : 5*n u64, then status n u8
   uint64_t d_meta_n = 0;
   cudaStream_t hs[3] = {nullptr, nullptr, nullptr};  // H2D | kernels | D2H
+  cudaStream_t ps[2] = {nullptr, nullptr};           // pass-1 chain | pass-2 chain (wave overlap)
+  std::vector<cudaEvent_t> wave_ev;
   uint64_t* h_meta = nullptr;  // pinned: written n u64, then status n u8 (so the D2H of the results never blocks the host)
   uint64_t h_meta_n = 0;
 };
@@ -140,7 +143,7 @@ int sfb200_create(int device, sfb200_ctx** out)
     if (cudaFuncGetAttributes(&lfa, sfb::lz_resolve_kernel) == cudaSuccess)
       ctx->lz_regs_per_thread = lfa.numRegs;
   }
-  if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_counter), 2 * sizeof(unsigned long long)) !=
+  if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_counter), 2 * kMaxWaves * sizeof(unsigned long long)) !=
       cudaSuccess)
     return bail(SFB200_RC_OUT_OF_MEMORY);
   const size_t lens_bytes = static_cast<size_t>(ctx->sm_count) * static_cast<size_t>(per_sm) *
@@ -173,6 +176,9 @@ void sfb200_destroy(sfb200_ctx* ctx)
     if (e) cudaEventDestroy(e);
   for (auto& st : ctx->hs)
     if (st) cudaStreamDestroy(st);
+  for (auto& st : ctx->ps)
+    if (st) cudaStreamDestroy(st);
+  for (auto& e : ctx->wave_ev) cudaEventDestroy(e);
   if (ctx->h_meta) cudaFreeHost(ctx->h_meta);
   delete ctx;
 }
@@ -229,57 +235,100 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
     }
     written = ctx->d_written;
   }
+  // Waves.  Pass 1 runs one wave of streams (as many as there are resident lanes) at a time
+  // and is latency-bound (about half of the issue slots stay idle); pass 2 needs no shared
+  // memory and few registers.  With more than one wave, pass 1 of wave k+1 and pass 2 of wave
+  // k are put on two internal streams so that they share the SMs; a single wave runs on the
+  // caller's stream directly.
+  const uint64_t wave = static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->ctas_per_sm) *
+                        LaneCfg::WARPS * 32;
+  uint64_t n_waves = (n + wave - 1) / wave;
+  if (const char* e = std::getenv("SFB200_NO_OVERLAP"))
+    if (e[0] == '1') n_waves = 1;
+  if (n_waves > kMaxWaves) n_waves = 1;  // (counters are a fixed array: enormous batches run unsplit)
+  const uint64_t per_wave = n_waves == 1 ? n : wave;
+  const bool overlap = n_waves > 1;
+  if (overlap) {
+    for (auto& ps : ctx->ps)
+      if (!ps) SFB_TRY(ctx, cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
+    for (uint64_t k = ctx->wave_ev.size(); k < n_waves + 3; ++k) {
+      cudaEvent_t e = nullptr;
+      SFB_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ctx->wave_ev.push_back(e);
+    }
+  }
+  cudaStream_t s1 = overlap ? ctx->ps[0] : st;  // pass-1 chain
+  cudaStream_t s2 = overlap ? ctx->ps[1] : st;  // pass-2 chain
   ctx->ev_valid = false;
   SFB_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
-  SFB_TRY(ctx, cudaMemsetAsync(ctx->d_counter, 0, 2 * sizeof(unsigned long long), st));
+  SFB_TRY(ctx, cudaMemsetAsync(ctx->d_counter, 0, 2 * kMaxWaves * sizeof(unsigned long long), st));
   SFB_TRY(ctx, cudaMemsetAsync(ctx->d_bits, 0, bits_words * sizeof(uint32_t), st));
   SFB_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
-  // pass 1: Huffman layer, one lane per stream
-  sfb::BatchArgs a;
-  a.src_base = src_base;
-  a.src_off = src_off;
-  a.src_len = src_len;
-  a.dst_base = dst_base;
-  a.dst_delta = delta;
-  a.dst_off = dst_off;
-  a.dst_cap = dst_cap;
-  a.status = status;
-  a.written = written;
-  a.n = n;
-  a.group_counter = ctx->d_counter;
-  a.lens_scratch = ctx->d_lens;
-  a.match_bits = ctx->d_bits;
-  {
-    const uint64_t groups = (n + 31) / 32;
-    const uint64_t want = (groups + LaneCfg::WARPS - 1) / LaneCfg::WARPS;
-    const uint64_t resident =
-        static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->ctas_per_sm);
-    const unsigned grid = static_cast<unsigned>(want < resident ? want : resident);
-    sfb::huff_lanes_kernel<LaneCfg><<<grid, LaneCfg::WARPS * 32, LaneCfg::SMEM_BYTES, st>>>(a);
-    SFB_TRY(ctx, cudaGetLastError());
+  if (overlap) {
+    SFB_TRY(ctx, cudaEventRecord(ctx->wave_ev[n_waves], st));
+    SFB_TRY(ctx, cudaStreamWaitEvent(s1, ctx->wave_ev[n_waves], 0));
+    SFB_TRY(ctx, cudaStreamWaitEvent(s2, ctx->wave_ev[n_waves], 0));
   }
-  SFB_TRY(ctx, cudaEventRecord(ctx->ev[2], st));
-  // pass 2: LZ77 back-references, one warp per stream
-  sfb::ResolveArgs r;
-  r.dst_base = dst_base;
-  r.dst_delta = delta;
-  r.dst_off = dst_off;
-  r.written = written;
-  r.match_bits = ctx->d_bits;
-  r.n = n;
-  r.stream_counter = ctx->d_counter + 1;
-  {
-    constexpr uint64_t wpc = sfb::LZ_THREADS / 32;
-    const uint64_t want = (n + wpc - 1) / wpc;
-    const uint64_t resident =
-        static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->lz_ctas_per_sm);
-    const unsigned grid = static_cast<unsigned>(want < resident ? want : resident);
-    sfb::lz_resolve_kernel<<<grid, sfb::LZ_THREADS, 0, st>>>(r);
-    SFB_TRY(ctx, cudaGetLastError());
+  for (uint64_t k = 0; k < n_waves; ++k) {
+    const uint64_t first = k * per_wave;
+    const uint64_t cnt = std::min(per_wave, n - first);
+    // pass 1: Huffman layer, one lane per stream
+    sfb::BatchArgs a;
+    a.src_base = src_base;
+    a.src_off = src_off + first;
+    a.src_len = src_len + first;
+    a.dst_base = dst_base;
+    a.dst_delta = delta;
+    a.dst_off = dst_off + first;
+    a.dst_cap = dst_cap + first;
+    a.status = status + first;
+    a.written = written + first;
+    a.n = cnt;
+    a.group_counter = ctx->d_counter + 2 * k;
+    a.lens_scratch = ctx->d_lens;
+    a.match_bits = ctx->d_bits;
+    {
+      const uint64_t groups = (cnt + 31) / 32;
+      const uint64_t want = (groups + LaneCfg::WARPS - 1) / LaneCfg::WARPS;
+      const uint64_t resident =
+          static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->ctas_per_sm);
+      const unsigned grid = static_cast<unsigned>(want < resident ? want : resident);
+      sfb::huff_lanes_kernel<LaneCfg><<<grid, LaneCfg::WARPS * 32, LaneCfg::SMEM_BYTES, s1>>>(a);
+      SFB_TRY(ctx, cudaGetLastError());
+    }
+    if (overlap) {
+      SFB_TRY(ctx, cudaEventRecord(ctx->wave_ev[k], s1));
+      SFB_TRY(ctx, cudaStreamWaitEvent(s2, ctx->wave_ev[k], 0));
+    }
+    if (k + 1 == n_waves) SFB_TRY(ctx, cudaEventRecord(ctx->ev[2], s1));  // end of all of pass 1
+    // pass 2: LZ77 back-references, one warp per stream
+    sfb::ResolveArgs r;
+    r.dst_base = dst_base;
+    r.dst_delta = delta;
+    r.dst_off = dst_off + first;
+    r.written = written + first;
+    r.match_bits = ctx->d_bits;
+    r.n = cnt;
+    r.stream_counter = ctx->d_counter + 2 * k + 1;
+    {
+      constexpr uint64_t wpc = sfb::LZ_THREADS / 32;
+      const uint64_t want = (cnt + wpc - 1) / wpc;
+      const uint64_t resident =
+          static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->lz_ctas_per_sm);
+      const unsigned grid = static_cast<unsigned>(want < resident ? want : resident);
+      sfb::lz_resolve_kernel<<<grid, sfb::LZ_THREADS, 0, s2>>>(r);
+      SFB_TRY(ctx, cudaGetLastError());
+    }
+    ctx->launches += 2;
+  }
+  if (overlap) {
+    SFB_TRY(ctx, cudaEventRecord(ctx->wave_ev[n_waves + 1], s1));
+    SFB_TRY(ctx, cudaEventRecord(ctx->wave_ev[n_waves + 2], s2));
+    SFB_TRY(ctx, cudaStreamWaitEvent(st, ctx->wave_ev[n_waves + 1], 0));
+    SFB_TRY(ctx, cudaStreamWaitEvent(st, ctx->wave_ev[n_waves + 2], 0));
   }
   SFB_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
   ctx->ev_valid = true;
-  ctx->launches += 2;
   return SFB200_RC_OK;
 }
 
