@@ -67,6 +67,20 @@ __device__ __forceinline__ uint32_t lz_funnel(uint32_t lo, uint32_t hi, uint32_t
 #endif
 }
 
+// k mod d for d <= k < 4096 (only overlapping matches get here, so d <= 257): multiply by a
+// 20-bit reciprocal.  inv = trunc(2^20 / d) + 2 with the quotient from a fast float division
+// (absolute error < 1) lies in (2^20/d, 2^20/d + 3), which makes floor(k * inv / 2^20) exact
+// for k < 2^20 / (3 d)  (checked exhaustively for d < 300, k < 700 in the design notes).
+__device__ __forceinline__ uint32_t lz_mod_small(uint32_t k, uint32_t d)
+{
+#ifdef SFB_CPU_EMU
+  const uint32_t inv = static_cast<uint32_t>(1048576.0f / static_cast<float>(d)) + 2u;
+#else
+  const uint32_t inv = static_cast<uint32_t>(__fdividef(1048576.0f, static_cast<float>(d))) + 2u;
+#endif
+  return k - ((k * inv) >> 20) * d;
+}
+
 __global__ void __launch_bounds__(LZ_THREADS) lz_resolve_kernel(const ResolveArgs a)
 {
   constexpr unsigned FULL = 0xffffffffu;
@@ -103,7 +117,8 @@ __global__ void __launch_bounds__(LZ_THREADS) lz_resolve_kernel(const ResolveArg
       const uint32_t wp = P + 4u * lane;
       // valid bytes of my word
       uint32_t vm = 15u;
-      if (P < q || P + 128u > end) {  // (warp-uniform: first / last chunk of the stream)
+      const bool interior = P >= q && P + 128u <= end;  // (warp-uniform)
+      if (!interior) {  // first / last chunk of the stream
         const uint32_t lo = q > wp ? (q - wp < 4u ? q - wp : 4u) : 0u;
         const uint32_t hi = end > wp ? (end - wp < 4u ? end - wp : 4u) : 0u;
         vm = hi > lo ? ((1u << hi) - 1u) & ~((1u << lo) - 1u) : 0u;
@@ -134,7 +149,28 @@ __global__ void __launch_bounds__(LZ_THREADS) lz_resolve_kernel(const ResolveArg
         c_end = c_o + ((pk >> 7) & 255u) + 3u;
         c_d = (pk >> 15) + 1u;
       }
-      // walk my 4 bytes
+      // ---- chunks that lie wholly inside one long match (no head, interior of the stream):
+      //      every source is below P, no per-byte bookkeeping is needed -----------------------
+      if (interior && hm == 0 && c_end >= P + 128u && c_o < P) {  // (warp-uniform)
+        if (c_d == 1u) {  // a run: all bytes equal the one before the match
+          const uint32_t v = base[c_o - 1u];
+          *reinterpret_cast<uint32_t*>(base + wp) = v * 0x01010101u;
+          __syncwarp();
+          cw = ncw; ncw = nncw; mw = nmw; nmw = nnmw;
+          continue;
+        }
+        if (c_d >= 128u && c_end - c_o <= c_d) {  // a far, non-overlapping copy: unaligned word gather
+          const uint32_t s0 = wp - c_d;
+          const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(base + (s0 & ~3u));
+          const uint32_t lo = wsrc[0];
+          const uint32_t hi = (s0 & 3u) ? wsrc[1] : 0u;
+          *reinterpret_cast<uint32_t*>(base + wp) = lz_funnel(lo, hi, 8u * (s0 & 3u));
+          __syncwarp();
+          cw = ncw; ncw = nncw; mw = nmw; nmw = nnmw;
+          continue;
+        }
+      }
+      // ---- walk my 4 bytes, switching to my own heads as I pass them -------------------------
       uint32_t src[4];
       uint32_t pend = 0;
 #pragma unroll
@@ -146,10 +182,11 @@ __global__ void __launch_bounds__(LZ_THREADS) lz_resolve_kernel(const ResolveArg
           t_end = p + (d & 255u) + 3u;
           t_d = (d >> 8) + 1u;
         }
+        const bool cov = ((vm >> b) & 1u) && p < t_end;
         uint32_t k = p - t_o;
-        if (k >= t_d) k %= t_d;
-        src[b] = t_o - t_d + k;  // >= q: pass 1 checked distance <= written
-        if (((vm >> b) & 1u) && p < t_end) pend |= 1u << b;
+        if (cov && k >= t_d) k = lz_mod_small(k, t_d);  // overlapping copy: period t_d
+        src[b] = t_o - t_d + k;  // = start - distance + (k mod distance) >= q (pass 1 checked)
+        if (cov) pend |= 1u << b;
       }
       // resolution rounds
       uint32_t res = cw;
