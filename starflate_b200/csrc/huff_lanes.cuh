@@ -257,7 +257,25 @@ huff_lanes_kernel(const BatchArgs a)
             shfl_u64(reinterpret_cast<uint64_t>(ow.al + ow.vpos), owner));
         const uint32_t len = __shfl_sync(FULL, copy_left, owner);
         __syncwarp();
-        for (uint32_t i = static_cast<uint32_t>(lane); i < len; i += LANES) d[i] = s[i];
+        {
+          // dst-aligned 32-bit words, each funnelled from the two aligned src words it spans
+          // (src words are only read where they hold at least one payload byte)
+          const uint32_t head = min(len, static_cast<uint32_t>(-reinterpret_cast<intptr_t>(d)) & 3u);
+          const uint32_t nwords = (len - head) >> 2;
+          const uint32_t tail0 = head + 4u * nwords;
+          for (uint32_t i = static_cast<uint32_t>(lane); i < head; i += LANES) d[i] = s[i];
+          const uint8_t* sb = s + head;
+          const uint32_t sh = 8u * (static_cast<uint32_t>(reinterpret_cast<uintptr_t>(sb)) & 3u);
+          const uint32_t* sw = reinterpret_cast<const uint32_t*>(sb - (sh >> 3));
+          uint32_t* dw = reinterpret_cast<uint32_t*>(d + head);
+#pragma unroll 4
+          for (uint32_t i = static_cast<uint32_t>(lane); i < nwords; i += LANES) {
+            const uint32_t lo = sw[i];
+            const uint32_t hi = sh ? sw[i + 1] : 0u;
+            dw[i] = funnel_r(lo, hi, sh);
+          }
+          for (uint32_t i = tail0 + static_cast<uint32_t>(lane); i < len; i += LANES) d[i] = s[i];
+        }
         __syncwarp();
         if (lane == owner) {
           ow.jump(len);
@@ -297,7 +315,10 @@ huff_lanes_kernel(const BatchArgs a)
         uint32_t used = used1 + (is_match ? dL + dxb : 0u);
         // anything that is not a plain literal / length+distance — end of block included — is
         // redone exactly, from the same 64 window bits
-        if (dec & ((L == 0) | (is_match & (dL == 0)) | tail)) {
+        // (near the end of the input the token must also fit into the real bits that are left)
+        const int32_t left32 = 8 * (static_cast<int32_t>(br.iend) - 4 * static_cast<int32_t>(br.rp - 3u)) -
+                               static_cast<int32_t>(bo0);
+        if (dec & ((L == 0) | (is_match & (dL == 0)) | (tail & (static_cast<int32_t>(used) > left32)))) {
           SFB_STAT(slow_tokens);
           const SlowToken t = slow_token(m.lens, (static_cast<uint64_t>(bits_hi) << 32) | bits,
                                          br.real_left());

@@ -33,6 +33,7 @@ static inline unsigned __brev(unsigned v)
 }
 template <class T> static inline T __shfl_sync(unsigned, T v, int) { return v; }
 template <class T> static inline T __shfl_down_sync(unsigned, T, int) { return T{}; }
+static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
 static inline int __any_sync(unsigned, int p) { return p != 0; }
 static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
