@@ -109,6 +109,10 @@ typedef struct sfb200_launch_info {
   int ctas_per_sm;
   int smem_bytes_per_cta;
   int regs_per_thread;
+  /* pass 1 with the small table geometry (tried first; 0 CTAs per SM = unavailable) */
+  int small_warps_per_cta;
+  int small_ctas_per_sm;
+  int small_regs_per_thread;
   /* pass 2, lz_resolve_kernel (one warp per stream) */
   int lz_threads_per_cta;
   int lz_ctas_per_sm;

@@ -34,6 +34,8 @@ _u64p = C.POINTER(C.c_uint64)
 class _LaunchInfo(C.Structure):
     _fields_ = [("sm_count", C.c_int), ("warps_per_cta", C.c_int), ("ctas_per_sm", C.c_int),
                 ("smem_bytes_per_cta", C.c_int), ("regs_per_thread", C.c_int),
+                ("small_warps_per_cta", C.c_int), ("small_ctas_per_sm", C.c_int),
+                ("small_regs_per_thread", C.c_int),
                 ("lz_threads_per_cta", C.c_int), ("lz_ctas_per_sm", C.c_int),
                 ("lz_regs_per_thread", C.c_int), ("kernel_launches", C.c_uint64)]
 

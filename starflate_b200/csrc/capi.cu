@@ -24,8 +24,17 @@ namespace {
 #ifndef SFB_LZ_CTAS_PER_SM
 #define SFB_LZ_CTAS_PER_SM 0  /* 0 = as many as fit */
 #endif
+// Two LUT geometries for pass 1.  LaneCfg holds any block's codes (8/6-bit roots,
+// 896 B of shared memory per lane, 8 warps per SM).  SmallCfg (6/5-bit roots, 448 B per lane,
+// 16 warps per SM) is tried first: low-entropy alphabets — short codes — fit it, and twice the
+// lanes in flight is twice the throughput of this latency-bound pass; a stream whose first
+// block does not fit is handed to a LaneCfg launch.
 using LaneCfg = sfb::Cfg<SFB_ROOT_LIT, SFB_ROOT_DIST, SFB_POOL, SFB_WARPS>;
-constexpr uint64_t kMaxWaves = 256;  // work counters per call: [2k] pass 1, [2k+1] pass 2 of wave k
+using SmallCfg = sfb::Cfg<6, 5, 96, 8, 2>;
+// work counters per call, four per wave k: [4k] small pass 1, [4k+1] large pass 1, [4k+2] pass 2,
+// [4k+3] number of streams handed from the small to the large geometry
+constexpr uint64_t kMaxWaves = 256;
+constexpr uint64_t kCountersPerWave = 4;
 
 }  // namespace
 
@@ -36,6 +45,10 @@ struct sfb200_ctx {
   int regs_per_thread = 0;
   int lz_ctas_per_sm = 0;
   int lz_regs_per_thread = 0;
+  int small_ctas_per_sm = 0;   // SmallCfg pass 1 (0: not usable)
+  int small_regs_per_thread = 0;
+  uint32_t* d_defer = nullptr;  // streams handed from the small to the large geometry
+  uint64_t d_defer_n = 0;
   unsigned long long* d_counter = nullptr;  // 2 * kMaxWaves work counters
   uint32_t* d_lens = nullptr;  // per-resident-lane code-length scratch
   uint32_t* d_bits = nullptr;  // match-head bitmap: 1 bit per dst byte (grown on demand)
@@ -143,11 +156,27 @@ int sfb200_create(int device, sfb200_ctx** out)
     if (cudaFuncGetAttributes(&lfa, sfb::lz_resolve_kernel) == cudaSuccess)
       ctx->lz_regs_per_thread = lfa.numRegs;
   }
-  if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_counter), 2 * kMaxWaves * sizeof(unsigned long long)) !=
+  if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_counter), kCountersPerWave * kMaxWaves * sizeof(unsigned long long)) !=
       cudaSuccess)
     return bail(SFB200_RC_OUT_OF_MEMORY);
-  const size_t lens_bytes = static_cast<size_t>(ctx->sm_count) * static_cast<size_t>(per_sm) *
-                            LaneCfg::WARPS * sfb::SCRATCH_WORDS * 32 * sizeof(uint32_t);
+  {
+    auto sk = sfb::huff_lanes_kernel<SmallCfg>;
+    int sp = 0;
+    if (cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, SmallCfg::SMEM_BYTES) ==
+            cudaSuccess &&
+        cudaFuncSetAttribute(sk, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sp, sk, SmallCfg::WARPS * 32,
+                                                      SmallCfg::SMEM_BYTES) == cudaSuccess)
+      ctx->small_ctas_per_sm = sp;
+    cudaFuncAttributes sfa;
+    if (cudaFuncGetAttributes(&sfa, sk) == cudaSuccess) ctx->small_regs_per_thread = sfa.numRegs;
+    cudaGetLastError();
+  }
+  const size_t big_warps = static_cast<size_t>(per_sm) * LaneCfg::WARPS;
+  const size_t small_warps = static_cast<size_t>(ctx->small_ctas_per_sm) * SmallCfg::WARPS;
+  const size_t lens_bytes = static_cast<size_t>(ctx->sm_count) * std::max(big_warps, small_warps) *
+                            sfb::SCRATCH_WORDS * 32 * sizeof(uint32_t);
   if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_lens), lens_bytes) != cudaSuccess) {
     cudaFree(ctx->d_counter);
     return bail(SFB200_RC_OUT_OF_MEMORY);
@@ -169,6 +198,7 @@ void sfb200_destroy(sfb200_ctx* ctx)
   cudaFree(ctx->d_lens);
   cudaFree(ctx->d_bits);
   cudaFree(ctx->d_written);
+  cudaFree(ctx->d_defer);
   cudaFree(ctx->d_src);
   cudaFree(ctx->d_dst);
   cudaFree(ctx->d_meta);
@@ -196,6 +226,9 @@ int sfb200_get_launch_info(sfb200_ctx* ctx, sfb200_launch_info* out)
   out->lz_threads_per_cta = sfb::LZ_THREADS;
   out->lz_ctas_per_sm = ctx->lz_ctas_per_sm;
   out->lz_regs_per_thread = ctx->lz_regs_per_thread;
+  out->small_warps_per_cta = SmallCfg::WARPS;
+  out->small_ctas_per_sm = ctx->small_ctas_per_sm;
+  out->small_regs_per_thread = ctx->small_regs_per_thread;
   out->kernel_launches = ctx->launches;
   return SFB200_RC_OK;
 }
@@ -235,13 +268,31 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
     }
     written = ctx->d_written;
   }
+  // Geometry.  Measured on C2 (profiles/r01_small_geometry_c2.md): with 16 warps per SM the small
+  // geometry makes pass 1 issue-bound (63 % of issue slots, 11.1 ms against 12.1 ms for the
+  // large one), and the few percent of streams it hands on cost a whole extra stream latency
+  // (4.5 ms) — so the large geometry is the default and the small one is opt-in
+  // (SFB200_GEOMETRY=small) until the hand-over can overlap.
+  bool use_small = false;
+  if (const char* e = std::getenv("SFB200_GEOMETRY")) use_small = e[0] == 's' && ctx->small_ctas_per_sm > 0;
+  if (use_small && n > ctx->d_defer_n) {
+    if (ctx->d_defer) SFB_TRY(ctx, cudaFree(ctx->d_defer));
+    ctx->d_defer = nullptr;
+    ctx->d_defer_n = 0;
+    const uint64_t want = n + n / 8 + 64;
+    SFB_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_defer), want * sizeof(uint32_t)));
+    ctx->d_defer_n = want;
+  }
   // Waves.  Pass 1 runs one wave of streams (as many as there are resident lanes) at a time
   // and is latency-bound (about half of the issue slots stay idle); pass 2 needs no shared
   // memory and few registers.  With more than one wave, pass 1 of wave k+1 and pass 2 of wave
   // k are put on two internal streams so that they share the SMs; a single wave runs on the
   // caller's stream directly.
-  const uint64_t wave = static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->ctas_per_sm) *
-                        LaneCfg::WARPS * 32;
+  const uint64_t big_lanes = static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->ctas_per_sm) *
+                             LaneCfg::WARPS * 32;
+  const uint64_t small_lanes = static_cast<uint64_t>(ctx->sm_count) *
+                               static_cast<uint64_t>(ctx->small_ctas_per_sm) * SmallCfg::WARPS * 32;
+  const uint64_t wave = use_small ? small_lanes : big_lanes;
   uint64_t n_waves = (n + wave - 1) / wave;
   if (const char* e = std::getenv("SFB200_NO_OVERLAP"))
     if (e[0] == '1') n_waves = 1;
@@ -261,7 +312,8 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
   cudaStream_t s2 = overlap ? ctx->ps[1] : st;  // pass-2 chain
   ctx->ev_valid = false;
   SFB_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
-  SFB_TRY(ctx, cudaMemsetAsync(ctx->d_counter, 0, 2 * kMaxWaves * sizeof(unsigned long long), st));
+  SFB_TRY(ctx, cudaMemsetAsync(ctx->d_counter, 0,
+                               kCountersPerWave * std::max<uint64_t>(n_waves, 1) * sizeof(unsigned long long), st));
   SFB_TRY(ctx, cudaMemsetAsync(ctx->d_bits, 0, bits_words * sizeof(uint32_t), st));
   SFB_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
   if (overlap) {
@@ -272,6 +324,7 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
   for (uint64_t k = 0; k < n_waves; ++k) {
     const uint64_t first = k * per_wave;
     const uint64_t cnt = std::min(per_wave, n - first);
+    unsigned long long* const ctr = ctx->d_counter + kCountersPerWave * k;
     // pass 1: Huffman layer, one lane per stream
     sfb::BatchArgs a;
     a.src_base = src_base;
@@ -284,17 +337,39 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
     a.status = status + first;
     a.written = written + first;
     a.n = cnt;
-    a.group_counter = ctx->d_counter + 2 * k;
     a.lens_scratch = ctx->d_lens;
     a.match_bits = ctx->d_bits;
+    a.defer_list = nullptr;
+    a.defer_count = nullptr;
+    a.todo_list = nullptr;
+    a.todo_count = nullptr;
+    const uint64_t groups = (cnt + 31) / 32;
+    if (use_small) {
+      a.group_counter = ctr + 0;
+      a.defer_list = ctx->d_defer + first;
+      a.defer_count = ctr + 3;
+      const uint64_t want = (groups + SmallCfg::WARPS - 1) / SmallCfg::WARPS;
+      const uint64_t resident =
+          static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->small_ctas_per_sm);
+      const unsigned grid = static_cast<unsigned>(want < resident ? want : resident);
+      sfb::huff_lanes_kernel<SmallCfg><<<grid, SmallCfg::WARPS * 32, SmallCfg::SMEM_BYTES, s1>>>(a);
+      SFB_TRY(ctx, cudaGetLastError());
+      ctx->launches += 1;
+      // the streams it handed on (none for low-entropy data: this launch then ends at once)
+      a.defer_list = nullptr;
+      a.defer_count = nullptr;
+      a.todo_list = ctx->d_defer + first;
+      a.todo_count = ctr + 3;
+    }
     {
-      const uint64_t groups = (cnt + 31) / 32;
+      a.group_counter = ctr + 1;
       const uint64_t want = (groups + LaneCfg::WARPS - 1) / LaneCfg::WARPS;
       const uint64_t resident =
           static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->ctas_per_sm);
       const unsigned grid = static_cast<unsigned>(want < resident ? want : resident);
       sfb::huff_lanes_kernel<LaneCfg><<<grid, LaneCfg::WARPS * 32, LaneCfg::SMEM_BYTES, s1>>>(a);
       SFB_TRY(ctx, cudaGetLastError());
+      ctx->launches += 1;
     }
     if (overlap) {
       SFB_TRY(ctx, cudaEventRecord(ctx->wave_ev[k], s1));
@@ -309,7 +384,7 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
     r.written = written + first;
     r.match_bits = ctx->d_bits;
     r.n = cnt;
-    r.stream_counter = ctx->d_counter + 2 * k + 1;
+    r.stream_counter = ctr + 2;
     {
       constexpr uint64_t wpc = sfb::LZ_THREADS / 32;
       const uint64_t want = (cnt + wpc - 1) / wpc;
@@ -319,7 +394,7 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
       sfb::lz_resolve_kernel<<<grid, sfb::LZ_THREADS, 0, s2>>>(r);
       SFB_TRY(ctx, cudaGetLastError());
     }
-    ctx->launches += 2;
+    ctx->launches += 1;
   }
   if (overlap) {
     SFB_TRY(ctx, cudaEventRecord(ctx->wave_ev[n_waves + 1], s1));

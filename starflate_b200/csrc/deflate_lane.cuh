@@ -59,6 +59,12 @@ struct BatchArgs {
   unsigned long long* group_counter;  // dynamic work distribution (zeroed before launch)
   uint32_t* lens_scratch;             // gridDim.x * WARPS * SCRATCH_WORDS * 32 words
   uint32_t* match_bits;               // match-head bitmap, bit k <-> dst_base[k] (zeroed before launch)
+  // Two LUT geometries: the launch with the small one hands streams whose first
+  // block's codes do not fit its tables to a launch with the large one.
+  uint32_t* defer_list;                     // out (small geometry): indices of the streams handed on; else null
+  unsigned long long* defer_count;          // out: how many
+  const uint32_t* todo_list;                // in (large geometry): the streams to do (null: all n)
+  const unsigned long long* todo_count;     // in: how many
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -67,8 +73,9 @@ struct BatchArgs {
 // 16-byte blocks per lane, block s of lane l at byte (s*32+l)*16 of the ring region).
 constexpr int RING_BLOCKS = 4;
 constexpr int RING_WARP_BYTES = RING_BLOCKS * 32 * 16;
-template <int ROOT_LIT_, int ROOT_DIST_, int POOL_, int WARPS_>
+template <int ROOT_LIT_, int ROOT_DIST_, int POOL_, int WARPS_, int CTAS_ = 2>
 struct Cfg {
+  static constexpr int CTAS = CTAS_;                // resident CTAs per SM the kernel is built for
   static constexpr int ROOT_LIT = ROOT_LIT_;
   static constexpr int ROOT_DIST = ROOT_DIST_;
   static constexpr int POOL = POOL_;
@@ -81,6 +88,7 @@ struct Cfg {
   static constexpr int WARP_BYTES = WARP_U16 * 2 + RING_WARP_BYTES;
   static constexpr int INFO_WORDS = 32;             // shared distance info table
   static constexpr int SMEM_BYTES = WARPS * WARP_BYTES + INFO_WORDS * 4;
+  static constexpr uint32_t DEFER_LOST = 64;        // 2^-9 of the code space, in units of 2^-15
   static_assert(POOL <= 256, "sub-table offsets are 8 bits");
   static_assert(POOL >= 64, "the 128-entry CL LUT (one byte each) is overlaid on the pool");
 };
@@ -541,7 +549,7 @@ __device__ __forceinline__ uint16_t make_entry(uint32_t s, uint32_t L)
 
 template <int ROOT, bool LITLEN, int POOL_OFF>
 __device__ __forceinline__ void build_lut(const LaneMem& m, int s0, int n, int root_off, int pool_end,
-                          int& pool_at)
+                          int& pool_at, uint32_t& lost)
 {
   uint16_t* const lut = m.lut;
   uint32_t* const g_first = m.lens + (SCR_FIRST + (LITLEN ? 0 : 16)) * 32;
@@ -646,9 +654,18 @@ __device__ __forceinline__ void build_lut(const LaneMem& m, int s0, int n, int r
       const uint32_t code = next[L]++;
       const uint32_t rest = L - ROOT;
       const uint32_t e = lut[(root_off + bitrev(code >> rest, ROOT)) * 32];
-      if (e == E_SLOW) continue;
+      // codes the tables cannot hold go through slow_token(); `lost` adds up their share of
+      // the code space (2^-L in units of 2^-15) as an estimate of how often that will happen
+      const bool is_eob = LITLEN && s == 256;  // (the end-of-block symbol takes the slow path anyway)
+      if (e == E_SLOW) {
+        if (!is_eob) lost += 1u << (15u - L);
+        continue;
+      }
       const uint32_t sb = (e >> 12) & 7u;
-      if (rest > sb) continue;  // longer than its (capped) sub-table reaches: slow_token()
+      if (rest > sb) {  // longer than its (capped) sub-table reaches
+        if (!is_eob) lost += 1u << (15u - L);
+        continue;
+      }
       const uint32_t off = POOL_OFF + ((e >> 4) & 0xffu);
       const uint16_t v = make_entry<LITLEN>(static_cast<uint32_t>(s), L);
       for (uint32_t j = bitrev(code & ((1u << rest) - 1u), static_cast<int>(rest)); j < (1u << sb);
@@ -705,8 +722,9 @@ template <class C>
 __device__ __forceinline__ int parse_block_header(BitReader& br, const LaneMem& m, uint32_t room,
                                                   uint32_t& final_block, int& n_lit, int& n_dist,
                                                   const uint8_t*& copy_src, uint32_t& copy_left,
-                                                  int* status)
+                                                  int* status, uint32_t* lost_out)
 {
+  *lost_out = 0;
   int err = -1;           // DecompressStatus once the stream is known to end here
   int next = S_DECODE;
   uint32_t type = 3;
@@ -880,9 +898,12 @@ __device__ __forceinline__ int parse_block_header(BitReader& br, const LaneMem& 
     }
     if (err < 0) {
       int pool_at = C::POOL_OFF;
-      build_lut<C::ROOT_LIT, true, C::POOL_OFF>(m, 0, n_lit, C::LIT_OFF, C::POOL_OFF + C::POOL, pool_at);
+      uint32_t lost = 0;
+      build_lut<C::ROOT_LIT, true, C::POOL_OFF>(m, 0, n_lit, C::LIT_OFF, C::POOL_OFF + C::POOL, pool_at,
+                                                lost);
       build_lut<C::ROOT_DIST, false, C::POOL_OFF>(m, n_lit, n_dist, C::DIST_OFF, C::POOL_OFF + C::POOL,
-                                                  pool_at);
+                                                  pool_at, lost);
+      *lost_out = lost;
       br.norm();
     }
   }

@@ -183,7 +183,7 @@ constexpr uint32_t LANES = 32;
 //            emit() site; lanes waiting for the next header (or finished) idle until the
 //            round ends.
 template <class C>
-__global__ void __launch_bounds__(C::WARPS * 32)
+__global__ void __launch_bounds__(C::WARPS * 32, C::CTAS)
 huff_lanes_kernel(const BatchArgs a)
 {
 #ifdef SFB_CPU_EMU
@@ -208,13 +208,16 @@ huff_lanes_kernel(const BatchArgs a)
   const saddr_t sdi = to_saddr(s_dist_info);
   const saddr_t ring = to_saddr(warp_smem + C::WARP_U16 * 2 + lane * 16);
 
-  const uint64_t n_groups = (a.n + 31) / 32;
+  // the streams of this launch: all n, or the ones an earlier launch handed on
+  const uint64_t n_todo = a.todo_list ? static_cast<uint64_t>(*a.todo_count) : a.n;
+  const uint64_t n_groups = (n_todo + 31) / 32;
   for (;;) {
     unsigned long long g = 0;
     if (lane == 0) g = atomicAdd(a.group_counter, 1ull);
     g = __shfl_sync(FULL, g, 0);
     if (g >= n_groups) break;
-    const uint64_t idx = g * 32 + static_cast<uint64_t>(lane);
+    const uint64_t slot = g * 32 + static_cast<uint64_t>(lane);
+    const uint64_t idx = (a.todo_list && slot < n_todo) ? a.todo_list[slot] : slot;
 
     int state = S_DONE;
     int status = ST_SUCCESS;
@@ -227,7 +230,8 @@ huff_lanes_kernel(const BatchArgs a)
     int n_lit = 0, n_dist = 0;
     const uint8_t* copy_src = nullptr;
     uint32_t copy_left = 0;
-    bool live = idx < a.n;
+    bool live = slot < n_todo;
+    bool first_header = true;  // nothing of this stream has been decided yet
     if (live) {
       const uint64_t slen = a.src_len[idx];
       const uint64_t cap = a.dst_cap[idx];
@@ -244,8 +248,18 @@ huff_lanes_kernel(const BatchArgs a)
 
     while (__any_sync(FULL, state != S_DONE)) {
       if (state == S_HEADER) {
+        uint32_t lost = 0;
         state = parse_block_header<C>(br, m, ow.room(), final_block, n_lit, n_dist, copy_src,
-                                      copy_left, &status);
+                                      copy_left, &status, &lost);
+        // A small-geometry launch hands the stream on when the codes of its FIRST block do not
+        // fit the tables well (more than ~2^-9 of the code space would take the exact slow
+        // path): nothing has been written for it yet.  Later blocks just live with it.
+        if (a.defer_list != nullptr && first_header && state == S_DECODE && lost > C::DEFER_LOST) {
+          a.defer_list[atomicAdd(a.defer_count, 1ull)] = static_cast<uint32_t>(idx);
+          state = S_DONE;
+          live = false;
+        }
+        first_header = false;
       }
       // ---- stored blocks (src/decompress.cpp:434): the warp copies them, one at a time ------
       for (unsigned sm = __ballot_sync(FULL, state == S_STORED); sm; sm &= sm - 1) {
@@ -286,6 +300,11 @@ huff_lanes_kernel(const BatchArgs a)
       }
       // ---- token iterations (all 32 lanes stay in this loop together) -----------------------
       uint32_t it = 0;
+      // software pipeline: the output step of a token is deferred to the start of the next
+      // iteration, where it is independent of everything around it and fills the latency of
+      // the decode chain (window -> LUT -> length -> window)
+      uint32_t p_chunk = 0, p_n = 0, p_skip = 0;
+      bool p_mt = false;
       while (__any_sync(FULL, state == S_DECODE)) {
         // ---- decode one token.  Straight-line and nearly branch-free (results are only used by
         //      lanes in S_DECODE, the others compute on stale data and discard): the two rare
@@ -301,6 +320,8 @@ huff_lanes_kernel(const BatchArgs a)
         const uint32_t bits = br.peek();
         const uint32_t bits_hi = funnel_r(br.w1, br.w2, bo0);
         const uint32_t e = lut_lookup_s<C::ROOT_LIT, C::LIT_OFF, C::POOL_OFF, C::POOL>(lutb, bits);
+        ow.mark_head(p_mt);                  // (the previous token's output step)
+        ow.emit(p_chunk, p_n, p_skip);
         const uint32_t L = e & 15u;
         const uint32_t xb = (e >> 12) & 7u;               // 0 for literals
         bool is_match = (e & 0x8000u) != 0;               // (pointers were resolved: L != 0 then)
@@ -348,10 +369,14 @@ huff_lanes_kernel(const BatchArgs a)
           dec = false;
         }
         const bool mt = dec & is_match;
-        ow.mark_head(mt);
         const uint32_t desc = (value - 3u) | ((dist - 1u) << 8);
-        ow.emit(dec ? (mt ? desc : value) : 0u, dec ? (mt ? 3u : 1u) : 0u, mt ? value - 3u : 0u);
+        p_mt = mt;
+        p_chunk = dec ? (mt ? desc : value) : 0u;
+        p_n = dec ? (mt ? 3u : 1u) : 0u;
+        p_skip = mt ? value - 3u : 0u;
       }
+      ow.mark_head(p_mt);  // drain the pipeline
+      ow.emit(p_chunk, p_n, p_skip);
       if (state == S_DONE && live) {
         ow.flush_tail();
         a.status[idx] = static_cast<uint8_t>(status);

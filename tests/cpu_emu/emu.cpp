@@ -15,6 +15,8 @@ static unsigned long long emu_stat_tokens = 0, emu_stat_slow_tokens = 0;
 #include "../../starflate_b200/csrc/huff_lanes.cuh"
 
 using EmuCfg = sfb::Cfg<SFB_EMU_ROOT_LIT, SFB_EMU_ROOT_DIST, SFB_EMU_POOL, 1>;
+using EmuSmall = sfb::Cfg<6, 5, 96, 1>;  // the product's small geometry (capi.cu: SmallCfg)
+static unsigned long long emu_stat_deferred = 0;
 
 extern "C" void emu_lz_resolve(uint8_t* dst_base, const uint64_t* dst_off, const uint64_t* written,
                                const uint32_t* match_bits, uint64_t n);  // dst_base 128-byte aligned
@@ -45,9 +47,10 @@ static void scalar_resolve(uint8_t* dst_base, uint64_t off, uint64_t written, co
 extern "C" int emu_decompress_batch(const uint8_t* src, const uint64_t* src_off,
                                     const uint64_t* src_len, uint8_t* dst,
                                     const uint64_t* dst_off, const uint64_t* dst_cap,
-                                    uint8_t* status, uint64_t* written, uint64_t n, int warp_pass2)
+                                    uint8_t* status, uint64_t* written, uint64_t n, int warp_pass2,
+                                    int small_first)
 {
-  std::vector<uint16_t> smem(EmuCfg::SMEM_BYTES / 2 + 64, 0xDEAD);
+  std::vector<uint16_t> smem((EmuCfg::SMEM_BYTES > EmuSmall::SMEM_BYTES ? EmuCfg::SMEM_BYTES : EmuSmall::SMEM_BYTES) / 2 + 64, 0xDEAD);
   std::vector<uint32_t> lens(sfb::SCRATCH_WORDS * 32, 0xDEADBEEFu);
   emu_smem = smem.data();
   blockDim.x = 1;  // one emulated lane
@@ -89,9 +92,28 @@ extern "C" int emu_decompress_batch(const uint8_t* src, const uint64_t* src_off,
     a.group_counter = &counter;
     a.lens_scratch = lens.data();
     a.match_bits = bits.data();
+    a.defer_list = nullptr;
+    a.defer_count = nullptr;
+    a.todo_list = nullptr;
+    a.todo_count = nullptr;
     threadIdx.x = 0;
     blockIdx.x = 0;
-    sfb::huff_lanes_kernel<EmuCfg>(a);
+    uint32_t handed[1] = {0xffffffffu};
+    unsigned long long n_handed = 0;
+    bool run_large = true;
+    if (small_first) {  // as capi.cu does: small geometry first, the large one for what it hands on
+      a.defer_list = handed;
+      a.defer_count = &n_handed;
+      sfb::huff_lanes_kernel<EmuSmall>(a);
+      run_large = n_handed != 0;
+      emu_stat_deferred += n_handed;
+      a.defer_list = nullptr;
+      a.defer_count = nullptr;
+      a.todo_list = handed;
+      a.todo_count = &n_handed;
+      counter = 0;
+    }
+    if (run_large) sfb::huff_lanes_kernel<EmuCfg>(a);
     if (wr > dst_cap[i]) return 2000 + static_cast<int>(i);
     if (warp_pass2) emu_lz_resolve(dbase, &doff, &wr, bits.data(), 1);
     else scalar_resolve(dbase, doff, wr, bits.data());
@@ -109,4 +131,5 @@ extern "C" void emu_stats(unsigned long long* out)
 {
   out[0] = emu_stat_tokens;
   out[1] = emu_stat_slow_tokens;
+  out[2] = emu_stat_deferred;
 }

@@ -34,9 +34,9 @@ class Emu:
     def __init__(self, **kw):
         self.lib = C.CDLL(build(**kw))
         self.lib.emu_decompress_batch.argtypes = [_u8p, _u64p, _u64p, _u8p, _u64p, _u64p, _u8p,
-                                                  _u64p, C.c_uint64, C.c_int]
+                                                  _u64p, C.c_uint64, C.c_int, C.c_int]
 
-    def decompress_batch(self, b, dst, warp_pass2=False):
+    def decompress_batch(self, b, dst, warp_pass2=False, small_first=False):
         """warp_pass2: run the real pass-2 kernel on 32 host threads (slow) instead of the
         scalar restatement of the token format."""
         st = np.zeros(b.n, np.uint8)
@@ -44,11 +44,12 @@ class Emu:
         p = lambda a, t: a.ctypes.data_as(t)
         rc = self.lib.emu_decompress_batch(p(b.src, _u8p), p(b.src_off, _u64p), p(b.src_len, _u64p),
                                            p(dst, _u8p), p(b.dst_off, _u64p), p(b.dst_cap, _u64p),
-                                           p(st, _u8p), p(wr, _u64p), b.n, int(warp_pass2))
+                                           p(st, _u8p), p(wr, _u64p), b.n, int(warp_pass2),
+                                           int(small_first))
         assert rc == 0, f"emulated kernel wrote outside a dst region (code {rc})"
         return st, wr
 
     def stats(self):
-        out = (C.c_ulonglong * 2)()
+        out = (C.c_ulonglong * 3)()
         self.lib.emu_stats(out)
-        return {"tokens": out[0], "slow_tokens": out[1]}
+        return {"tokens": out[0], "slow_tokens": out[1], "deferred": out[2]}

@@ -131,6 +131,20 @@ def test_host_batch_api_pipelined_sub_batches(ctx, oracle, monkeypatch):
         assert (st == ost).all() and (wr == owr).all() and (dst == dst_o).all()
 
 
+def test_small_table_geometry_with_hand_over(oracle, golden, monkeypatch):
+    """SFB200_GEOMETRY=small: pass 1 tries 6/5-bit-root tables (16 warps per SM) and hands the
+    streams whose first block does not fit them (real HTML) to the large geometry."""
+    import starflate_b200 as S
+    monkeypatch.setenv("SFB200_GEOMETRY", "small")
+    c = S.Context(0)
+    try:
+        for name in ("known_answers", "cut7_starfleet_dynamic", "cut1_multiblock_12000", "cap_dynamic_4096",
+                     "crafted_dynamic_headers", "flip_repetitive_70000", "cap_stored_4096"):
+            _check_family(c, oracle, golden, name)
+    finally:
+        c.close()
+
+
 def test_one_bad_stream_does_not_affect_neighbours(ctx, oracle):
     plain, comp = T.make_stream("dynamic", 30000, 1)
     streams = [comp, comp[:100], comp, b"\x07", comp]

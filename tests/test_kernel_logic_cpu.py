@@ -15,11 +15,11 @@ def emu():
     return emu_bindings.Emu()
 
 
-def _check_family(emu, oracle, golden, name, stride, warp_pass2=False):
+def _check_family(emu, oracle, golden, name, stride, warp_pass2=False, small_first=False):
     cases = golden.cases(name, stride)
     b = T.Batch([c[1] for c in cases], [c[2] for c in cases])   # packed, arbitrary alignments
     dst = b.new_dst()
-    st, wr = emu.decompress_batch(b, dst, warp_pass2)
+    st, wr = emu.decompress_batch(b, dst, warp_pass2, small_first)
     for k, (i, src, cap) in enumerate(cases):
         want_st, want_wr, want_hash, cls = golden.expected(name, i)
         assert (int(st[k]), int(wr[k])) == (want_st, want_wr), (name, i, cls)
@@ -94,3 +94,23 @@ def test_warp_pass2_emulation_vs_oracle(emu, oracle, golden):
     ost, owr, _ = oracle.decompress_batch(b.src, b.src_off, b.src_len, dst_o, b.dst_off, b.dst_cap)
     assert (st == ost).all() and (wr == owr).all()
     assert (dst_e == dst_o).all()
+
+
+def test_small_geometry_first_with_hand_over(emu, oracle, golden):
+    """The product's order of play: the 6/5-bit-root tables first, and the large tables for the
+    streams whose first block does not fit them (real HTML does not, the synthetic text does)."""
+    s0 = emu.stats()
+    for name in ("known_answers", "crafted_dynamic_headers", "cut7_starfleet_dynamic", "cut1_multiblock_12000",
+                 "flip_dynamic_4096", "cap_repetitive_70000", "cap_stored_4096", "cut1_fixed_4096"):
+        if name in golden.families:
+            _check_family(emu, oracle, golden, name, 7, small_first=True)
+    s1 = emu.stats()
+    assert s1["deferred"] > s0["deferred"]                       # starfleet's codes do not fit
+    plain, comp = T.make_stream("dynamic", 65536, 4242)
+    b = T.Batch([comp], [len(plain)])
+    dst = b.new_dst()
+    st, wr = emu.decompress_batch(b, dst, small_first=True)
+    s2 = emu.stats()
+    assert st[0] == 0 and dst.tobytes()[: len(plain)] == plain
+    assert s2["deferred"] == s1["deferred"]                      # the C2 text does fit ...
+    assert (s2["slow_tokens"] - s1["slow_tokens"]) * 200 < (s2["tokens"] - s1["tokens"])  # ... well
