@@ -365,7 +365,10 @@ def main():
                      "kernel": dominant, "kernel_ms": k_ms,
                      "algorithmic_bytes": algo_bytes,
                      "note": "achieved = (compressed read + decompressed written) / device time of the "
-                             "WHOLE step (scratch clear + pass 1 + pass 2), not of the dominant kernel alone",
+                             "WHOLE step (scratch clear + pass 1 + pass 2), not of the dominant kernel alone; "
+                             "with more than one wave of streams the passes overlap on two internal streams: "
+                             "passes_ms then gives clear | start of pass 1 .. end of its last wave | the part "
+                             "of pass 2 that runs after that",
                      "passes_ms": {"clear": clear_ms, "huff_lanes_kernel": p1_ms,
                                    "lz_resolve_kernel": p2_ms},
                      "frac_of_nominal_8TBs": achieved / 8000.0},
