@@ -35,8 +35,28 @@ METRIC = "decompressed GB/s (device-timed) batched dynamic-Huffman"
 UNIT = "GB/s"
 
 
+_HTML = None
+
+
+def _html_plain(size: int, seed: int) -> bytes:
+    """A `size`-byte window of real HTML: the reference's own test page (decoded from the committed
+    fixture tests/golden/bases/starfleet_dynamic.deflate), read cyclically from a seeded offset."""
+    global _HTML
+    if _HTML is None:
+        with open(os.path.join(ROOT, "tests", "golden", "bases", "starfleet_dynamic.deflate"), "rb") as f:
+            _HTML = zlib.decompress(f.read(), -15)
+    off = (seed * 7919) % len(_HTML)
+    rep = (_HTML[off:] + _HTML * (size // len(_HTML) + 2))[:size]
+    return rep
+
+
 def _gen_one(args):
     kind, size, seed = args
+    if kind == "html":
+        plain = _html_plain(size, seed)
+        co = zlib.compressobj(6, zlib.DEFLATED, -15, 8, zlib.Z_DEFAULT_STRATEGY)
+        comp = co.compress(plain) + co.flush()
+        return comp, zlib.crc32(plain), len(plain)
     plain, comp = T.make_stream(kind, size, seed)
     assert T.first_block_type(comp) == {"dynamic": 2, "fixed": 1, "stored": 0}.get(kind, 2) or kind in ("repetitive", "multiblock")
     return comp, zlib.crc32(plain), len(plain)
@@ -50,6 +70,8 @@ def make_workload(name: str, n_streams: int, unique: int, rank: int):
         kind, size = "mixed", 4096
     elif name == "c4":
         kind, size = "repetitive", 1 << 20
+    elif name == "html":   # not a BASELINE config: real-HTML statistics (rich alphabet), 64 KiB streams
+        kind, size = "html", 65536
     else:
         raise ValueError(name)
     unique = min(unique, n_streams)
@@ -189,7 +211,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "html"])
     ap.add_argument("--streams", type=int, default=0, help="streams per GPU (0 = the config's size)")
     ap.add_argument("--unique", type=int, default=0, help="distinct seeds (0 = all streams distinct)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -200,7 +222,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    default_n = {"c2": 65536, "c3": 1048576, "c4": 16384}[args.workload]
+    default_n = {"c2": 65536, "c3": 1048576, "c4": 16384, "html": 65536}[args.workload]
     n_streams = args.streams or default_n
     unique = args.unique or n_streams
     if args.workload == "c3" and not args.unique:
@@ -219,7 +241,8 @@ def main():
         v = float(np.mean(vals)) if vals else cb["value"]
         cb["value"] = v
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+                "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": (w["total_out"] / (v * 1e9) * 1e3) if v else None, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": {"workload": w["desc"], "note": "reference CPU decompress(), bounded sample per step"},
                 "cpu_baseline": cb,
@@ -238,7 +261,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     import starflate_b200 as S
-    from starflate_b200 import build
+    from starflate_b200 import build, sharding
     if rank == 0:
         build.build_all()
     if world > 1:
@@ -301,10 +324,7 @@ def main():
     kern_ms = [a.elapsed_time(b) for a, b in evs]
     launches = ctx.launch_info()["kernel_launches"] - launches0
     clocks = sampler.stop()
-    if world > 1:
-        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+    total_ms = sharding.max_over_ranks(total_ms, dev)  # a sharded job is as slow as its slowest rank
     ms_per_step = total_ms / args.steps
     value = world * w["total_out"] / (ms_per_step * 1e-3) / 1e9
 
@@ -323,10 +343,7 @@ def main():
         barrier()
         dt = (time.perf_counter() - t0) / e_steps
         assert not st.any()
-        if world > 1:
-            t = torch.tensor([dt], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = sharding.max_over_ranks(dt, dev)
         e2e = {"value": world * w["total_out"] / dt / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(w["total_in"] + 32 * n),
                "d2h_bytes_per_step": int(w["total_out"] + 9 * n),
