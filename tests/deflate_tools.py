@@ -344,3 +344,46 @@ def fnv1a64(data: bytes) -> int:
     for b in data:
         h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
     return h
+
+
+# --------------------------------------------------------------------------- crafted LZ77 shapes
+def crafted_lz_streams():
+    """Fixed-Huffman streams that walk the LZ77 resolve pass through its special cases at every
+    phase of its 128-byte chunks: distance-1 runs, short periods, far non-overlapping copies,
+    maximum-length matches back to back, matches that straddle chunk and word boundaries,
+    matches whose source lies in the same chunk.  -> list of (name, compressed bytes, plain length)."""
+    out = []
+    rng = np.random.default_rng(99)
+    for lead in (0, 1, 2, 3, 5, 31, 61, 126, 127, 128, 129, 200, 257):
+        for dist, reps in ((1, 5), (2, 3), (3, 3), (7, 3), (127, 2), (128, 3), (129, 3), (200, 3), (258, 2), (1000, 2)):
+            w = BitWriter()
+            blk = fixed_block(w, True)
+            n = max(lead, dist)
+            for b in rng.integers(32, 127, n):
+                blk.literal(int(b))
+            total = n
+            for r in range(reps):
+                ln = 258 if r % 2 == 0 else int(rng.integers(3, 258))
+                blk.match(ln, dist)
+                total += ln
+                blk.literal(int(rng.integers(32, 127)))
+                total += 1
+            blk.eob()
+            out.append((f"lead{lead}_d{dist}", w.tobytes(), total))
+    # dense short matches: every 3-5 bytes a match, near and far sources mixed
+    w = BitWriter()
+    blk = fixed_block(w, True)
+    for b in rng.integers(32, 127, 300):
+        blk.literal(int(b))
+    total = 300
+    for i in range(400):
+        d = int(rng.choice([1, 2, 3, 4, 5, 8, 16, 33, 64, 100, 127, 128, 129, 250, 299]))
+        ln = int(rng.choice([3, 3, 4, 5, 6, 9, 17, 40]))
+        blk.match(ln, min(d, total))
+        total += ln
+        if i % 3 == 0:
+            blk.literal(int(rng.integers(32, 127)))
+            total += 1
+    blk.eob()
+    out.append(("dense_short", w.tobytes(), total))
+    return out

@@ -145,6 +145,35 @@ def test_small_table_geometry_with_hand_over(oracle, golden, monkeypatch):
         c.close()
 
 
+def test_crafted_lz_shapes_and_unaligned_dst_base(ctx, oracle):
+    """Runs, short periods, far copies and dense short matches at every chunk phase
+    (tests.deflate_tools.crafted_lz_streams), packed back to back, through a dst pointer that is
+    NOT 128-byte aligned (the C ABI re-bases it), incl. many 1-3 byte streams sharing bitmap words."""
+    cases = T.crafted_lz_streams()
+    streams = [c[1] for c in cases] + [bytes.fromhex("730400")] * 40 + [bytes.fromhex("731c0500")] * 3
+    caps = [c[2] for c in cases] + [1] * 20 + [3] * 20 + [259, 258, 300]
+    for dst_align in (1, 7):
+        b = T.Batch(streams, caps, dst_align=dst_align)
+        dst_o = b.new_dst()
+        ost, owr, _ = oracle.decompress_batch(b.src, b.src_off, b.src_len, dst_o, b.dst_off, b.dst_cap)
+        assert (ost[: len(cases)] == 0).all()
+        dev = torch.device("cuda", ctx.device)
+        for shift in (0, 13, 77):
+            big = torch.full((b.dst_total + 256,), 0xA5, dtype=torch.uint8, device=dev)
+            dst = big[shift: shift + b.dst_total]           # data_ptr() is base + shift
+            t = lambda a: torch.from_numpy(a.view(np.int64)).to(dev)
+            status = torch.full((b.n,), 0xEE, dtype=torch.uint8, device=dev)
+            written = torch.full((b.n,), -1, dtype=torch.int64, device=dev)
+            ctx.decompress_batch_device(torch.from_numpy(b.src).to(dev), t(b.src_off), t(b.src_len), dst,
+                                        t(b.dst_off), t(b.dst_cap), status, written)
+            torch.cuda.synchronize(dev)
+            assert (status.cpu().numpy() == ost).all()
+            assert (written.cpu().numpy().view(np.uint64) == owr).all()
+            got = big.cpu().numpy()
+            assert (got[shift: shift + b.dst_total] == dst_o).all()
+            assert (got[:shift] == 0xA5).all() and (got[shift + b.dst_total:] == 0xA5).all()
+
+
 def test_one_bad_stream_does_not_affect_neighbours(ctx, oracle):
     plain, comp = T.make_stream("dynamic", 30000, 1)
     streams = [comp, comp[:100], comp, b"\x07", comp]

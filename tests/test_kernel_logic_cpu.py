@@ -114,3 +114,15 @@ def test_small_geometry_first_with_hand_over(emu, oracle, golden):
     assert st[0] == 0 and dst.tobytes()[: len(plain)] == plain
     assert s2["deferred"] == s1["deferred"]                      # the C2 text does fit ...
     assert (s2["slow_tokens"] - s1["slow_tokens"]) * 200 < (s2["tokens"] - s1["tokens"])  # ... well
+
+
+def test_crafted_lz_shapes_on_warp_emulation(emu, oracle):
+    """tests.deflate_tools.crafted_lz_streams through the real pass-2 kernel on 32 host threads."""
+    cases = T.crafted_lz_streams()
+    b = T.Batch([c[1] for c in cases], [c[2] for c in cases], dst_align=1)
+    dst_e, dst_o = b.new_dst(), b.new_dst()
+    st, wr = emu.decompress_batch(b, dst_e, warp_pass2=True)
+    ost, owr, _ = oracle.decompress_batch(b.src, b.src_off, b.src_len, dst_o, b.dst_off, b.dst_cap)
+    assert (ost == 0).all() and (owr == b.dst_cap).all()
+    assert (st == ost).all() and (wr == owr).all()
+    assert (dst_e == dst_o).all()
