@@ -297,6 +297,11 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
   if (const char* e = std::getenv("SFB200_NO_OVERLAP"))
     if (e[0] == '1') n_waves = 1;
   if (n_waves > kMaxWaves) n_waves = 1;  // (counters are a fixed array: enormous batches run unsplit)
+  // With two waves the overlapped part (pass 1 of the second, pass 2 of the first) wants ~95 % of
+  // the issue slots and pass 1, which is latency-bound, slows down by more than pass 2 gains
+  // (C2: 21.8 ms overlapped, 20.2 ms back to back); from three waves on it pays (131 072 streams:
+  // 218 against 200 GB/s).
+  if (n_waves == 2) n_waves = 1;
   const uint64_t per_wave = n_waves == 1 ? n : wave;
   const bool overlap = n_waves > 1;
   if (overlap) {
@@ -505,7 +510,10 @@ int sfb200_decompress_batch_host(sfb200_ctx* ctx, const uint8_t* src, uint64_t s
   for (uint64_t i = 0; i < n;) {
     Sub sb{i, 0, ~0ull, 0, ~0ull, 0, nullptr, nullptr, nullptr};
     uint64_t acc = 0;
-    while (i < n && (sb.count == 0 || acc < chunk_bytes)) {
+    // (the first sub-batch is a quarter of the others so that the D2H direction, which bounds
+    //  the call, starts early)
+    const uint64_t target = subs.empty() ? chunk_bytes / 4 : chunk_bytes;
+    while (i < n && (sb.count == 0 || acc < target)) {
       sb.src_lo = std::min(sb.src_lo, src_off[i]);
       sb.src_hi = std::max(sb.src_hi, src_off[i] + src_len[i]);
       sb.dst_lo = std::min(sb.dst_lo, dst_off[i]);

@@ -56,42 +56,49 @@ struct TokWin {
   uint64_t obuf;
   uint64_t first;   // word 0 of an unaligned dst once the cursor has left it: its bytes before
                     // `lead` are not ours, so it is written bytewise at the end (flush_tail)
-  uint32_t* bm;     // bitmap word that holds the bit of output byte 0
-  uint32_t qml;     // (bit of output byte 0 within *bm) - lead, mod 2^32
-  uint32_t mword;   // index, from bm, of the bitmap word `macc` belongs to
-  uint32_t macc;    // head bits not yet merged into the bitmap
+  uint8_t* fbase;   // match-head bitmap, byte granular: the bits of word wv live in fbase[wv >> 3]
+                    // (dst_base is 128-byte aligned, so address words and bitmap bytes line up)
+  uint32_t fb;      // head bits of the open word
 
   __device__ __forceinline__ void open(uint8_t* dst_base, uint64_t off, uint32_t cap, uint32_t* bits)
   {
     uint8_t* d = dst_base + off;
-    lead = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(d) & 7u);
+    lead = static_cast<uint32_t>(off & 7u);
     al = d - lead;
     vpos = lead;
     vend = lead + cap;
     obuf = 0;
     first = 0;
-    bm = bits + (off >> 5);
-    qml = static_cast<uint32_t>(off & 31u) - lead;
-    mword = 0;
-    macc = 0;
+    fbase = reinterpret_cast<uint8_t*>(bits) + ((off - lead) >> 3);
+    fb = 0;
   }
   __device__ __forceinline__ void park()
   {
     al = nullptr;
     lead = vpos = vend = 0;
     obuf = first = 0;
-    bm = nullptr;
-    qml = mword = macc = 0;
+    fbase = nullptr;
+    fb = 0;
   }
 
   __device__ __forceinline__ uint32_t written() const { return vpos - lead; }
   __device__ __forceinline__ uint32_t room() const { return vend - vpos; }
 
-  // The one output step of a token: append the n (0..3) low bytes of `chunk` at the cursor,
-  // then move the cursor `skipn` bytes further over bytes pass 2 will produce (the body of a
-  // match).  A word the cursor leaves is stored whole: its bytes past the appended ones all
-  // belong to the match body, so any value will do there.  No branches: two predicated stores.
-  __device__ __forceinline__ void emit(uint32_t chunk, uint32_t n, uint32_t skipn)
+  // merge the head bits of word wv into the bitmap with an atomic (words at the edges of a dst
+  // region share their bitmap byte with the neighbouring stream)
+  __device__ __forceinline__ void or_bits(uint32_t wv, uint32_t bits8) const
+  {
+    uint8_t* p = fbase + (wv >> 3);
+    const uint32_t sh = 8u * (static_cast<uint32_t>(reinterpret_cast<uintptr_t>(p)) & 3u);
+    atomicOr(reinterpret_cast<uint32_t*>(p - (sh >> 3)), bits8 << sh);
+  }
+
+  // The one output step of a token: append the n (0..3) low bytes of `chunk` at the cursor —
+  // the descriptor of a match iff `is_head` — then move the cursor `skipn` bytes further over
+  // bytes pass 2 will produce (the body of a match).  A word the cursor leaves is stored whole:
+  // its bytes past the appended ones all belong to the match body, so any value will do there;
+  // its head bits go to the bitmap byte of that word.  No branches: predicated stores.
+  __device__ __forceinline__ void emit(uint32_t chunk, uint32_t n, uint32_t skipn, bool is_head)
   {
 #ifdef SFB_TRACE_EMIT
     SFB_TRACE_EMIT(vpos, chunk, n, skipn, obuf);
@@ -99,6 +106,7 @@ struct TokWin {
     const uint32_t k = vpos & 7u;
     const uint32_t sh = 8u * k;
     const uint64_t merged = obuf | (static_cast<uint64_t>(chunk) << sh);  // chunk < 2^(8n)
+    const uint32_t hb = fb | (is_head ? 1u << k : 0u);
     const uint32_t np = vpos + n + skipn;
     const uint32_t wv = vpos & ~7u;
     const uint32_t nw = np & ~7u;
@@ -107,23 +115,15 @@ struct TokWin {
     const uint32_t carry = chunk >> ((64u - sh) & 31u);    // ... with these bytes (sh >= 48 then)
     const bool stay = nw == wv + 8u;                       // the cursor ends in the next word
     const bool head = wv < lead;                           // word 0 of an unaligned dst
+    const bool edge = head | (wv + 8u > vend);             // a word this region does not own alone
     if (leaves & !head) *reinterpret_cast<uint64_t*>(al + wv) = merged;
     if (leaves & head) first = merged;
     if (leaves & spill & !stay) *reinterpret_cast<uint64_t*>(al + wv + 8u) = carry;  // skipped past it too
+    if (leaves & (hb != 0) & !edge) fbase[wv >> 3] = static_cast<uint8_t>(hb);
+    if (leaves & (hb != 0) & edge) or_bits(wv, hb);
+    fb = leaves ? 0u : hb;
     obuf = leaves ? ((spill & stay) ? carry : 0u) : merged;
     vpos = np;
-  }
-
-  // a match starts at the cursor iff `is_head` (branch-free: one predicated RED)
-  __device__ __forceinline__ void mark_head(bool is_head)
-  {
-    const uint32_t bidx = vpos + qml;
-    const uint32_t w = bidx >> 5;
-    const bool moved = is_head & (w != mword);
-    // (bitmap words at the edges of a dst region are shared with the neighbouring streams)
-    if (moved & (macc != 0)) atomicOr(bm + mword, macc);
-    macc = (moved ? 0u : macc) | (is_head ? 1u << (bidx & 31u) : 0u);
-    mword = is_head ? w : mword;
   }
 
   // pending bytes of the open word -> memory, bytewise (the window stays as it is)
@@ -136,13 +136,18 @@ struct TokWin {
   // the cursor was moved over bytes written straight to memory: re-read the open word
   __device__ __forceinline__ void jump(uint32_t n)
   {
-    const bool left0 = (vpos & ~7u) < lead && ((vpos + n) & ~7u) != 0;  // leaving word 0
+    const uint32_t w0 = vpos & ~7u;
+    const bool left0 = w0 < lead && ((vpos + n) & ~7u) != 0;  // leaving word 0
     vpos += n;
+    const uint32_t wv = vpos & ~7u;
+    if (wv != w0 && fb != 0) {  // head bits of the word left behind
+      or_bits(w0, fb);
+      fb = 0;
+    }
     if (left0) {  // all of its bytes from `lead` on are in memory now: keep `first` consistent
       first = 0;
       for (uint32_t b = lead; b < 8; ++b) first |= static_cast<uint64_t>(al[b]) << (8 * b);
     }
-    const uint32_t wv = vpos & ~7u;
     obuf = 0;
     for (uint32_t b = wv < lead ? lead : wv; b < vpos; ++b)
       obuf |= static_cast<uint64_t>(al[b]) << (8 * (b - wv));
@@ -153,8 +158,8 @@ struct TokWin {
     spill_pending();
     if (lead != 0 && vpos >= 8u)  // the cursor left word 0: its bytes from `lead` on are still pending
       for (uint32_t b = lead; b < 8; ++b) al[b] = static_cast<uint8_t>(first >> (8 * b));
-    if (macc) atomicOr(bm + mword, macc);
-    macc = 0;
+    if (fb) or_bits(vpos & ~7u, fb);
+    fb = 0;
   }
 };
 
@@ -320,8 +325,7 @@ huff_lanes_kernel(const BatchArgs a)
         const uint32_t bits = br.peek();
         const uint32_t bits_hi = funnel_r(br.w1, br.w2, bo0);
         const uint32_t e = lut_lookup_s<C::ROOT_LIT, C::LIT_OFF, C::POOL_OFF, C::POOL>(lutb, bits);
-        ow.mark_head(p_mt);                  // (the previous token's output step)
-        ow.emit(p_chunk, p_n, p_skip);
+        ow.emit(p_chunk, p_n, p_skip, p_mt);   // (the previous token's output step)
         const uint32_t L = e & 15u;
         const uint32_t xb = (e >> 12) & 7u;               // 0 for literals
         bool is_match = (e & 0x8000u) != 0;               // (pointers were resolved: L != 0 then)
@@ -375,8 +379,7 @@ huff_lanes_kernel(const BatchArgs a)
         p_n = dec ? (mt ? 3u : 1u) : 0u;
         p_skip = mt ? value - 3u : 0u;
       }
-      ow.mark_head(p_mt);  // drain the pipeline
-      ow.emit(p_chunk, p_n, p_skip);
+      ow.emit(p_chunk, p_n, p_skip, p_mt);  // drain the pipeline
       if (state == S_DONE && live) {
         ow.flush_tail();
         a.status[idx] = static_cast<uint8_t>(status);
