@@ -225,6 +225,8 @@ struct BitReader {
   uint32_t rp;          // index of the next word to take from the ring (w2 is word rp-1)
   uint32_t pfb;         // index of the next 16-byte block to stage
   uint32_t iend;        // byte offset (from base) one past the last stream byte
+  uint32_t ebits;       // 8 * iend + 96 (mod 2^32): real bits left at a token start are
+                        // ebits - 32 * rp - bo whenever the window touches the end of the stream
   uint32_t lead0;       // stream start - base (0..15)
   const uint8_t* base;  // stream start rounded down to 16 bytes
   saddr_t ring;         // this lane's block 0 in shared memory (block s at ring + s*512)
@@ -270,6 +272,7 @@ struct BitReader {
     lead0 = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(begin_) & 15u);
     base = begin_ - lead0;
     iend = lead0 + len;
+    ebits = 8u * iend + 96u;
     init_at(lead0, 0);
   }
   // a reader that owns no stream: never slides, never stages
@@ -281,6 +284,7 @@ struct BitReader {
     rp = 3;
     pfb = 0xfffffff0u;
     iend = lead0 = 0;
+    ebits = 96u;
     base = nullptr;
   }
 

@@ -341,8 +341,7 @@ huff_lanes_kernel(const BatchArgs a)
         // anything that is not a plain literal / length+distance — end of block included — is
         // redone exactly, from the same 64 window bits
         // (near the end of the input the token must also fit into the real bits that are left)
-        const int32_t left32 = 8 * (static_cast<int32_t>(br.iend) - 4 * static_cast<int32_t>(br.rp - 3u)) -
-                               static_cast<int32_t>(bo0);
+        const int32_t left32 = static_cast<int32_t>(br.ebits - 32u * br.rp - bo0);  // (meaningful when `tail`)
         if (dec & ((L == 0) | (is_match & (dL == 0)) | (tail & (static_cast<int32_t>(used) > left32)))) {
           SFB_STAT(slow_tokens);
           const SlowToken t = slow_token(m.lens, (static_cast<uint64_t>(bits_hi) << 32) | bits,
