@@ -541,6 +541,40 @@ __device__ __noinline__ SlowToken slow_token(const uint32_t* lens, uint64_t snap
 // accepts but a prefix LUT cannot represent exactly (over-subscribed: some code value reaches
 // 2^len, "shortest code wins") get E_SLOW in every root slot.
 // LITLEN selects the entry payload (see the entry format above).
+// ---------------------------------------------------------------------------------------------
+// Codes longer than the LUT root that found no slot in the sub-table pool (alphabets with more
+// symbols than the tables have entries: real HTML has 240) are still decoded in registers: per
+// length, first code and count — the canonical form — kept by the lane, one compare per length,
+// and the symbol fetched from the sorted list in the lane's scratch.  Only valid for code sets
+// that are not over-subscribed (prefix-free), where "no code of <= ROOT bits matches" follows
+// from the root slot being a pointer / pool marker; anything it does not find goes to slow_token().
+template <int ROOT>
+struct LongTab {
+  uint32_t fc[15 - ROOT];  // lengths ROOT+1 .. 15: first code | count << 16
+  uint32_t off0;           // symbols with shorter codes (rank of the first one of length ROOT+1)
+  bool usable;             // false for over-subscribed sets
+};
+
+// -> code length (0: none) and rank of the symbol in canonical order
+template <int ROOT>
+__device__ __forceinline__ uint32_t long_decode(const LongTab<ROOT>& t, uint32_t bits, uint32_t& rank)
+{
+  const uint32_t rev = __brev(bits);  // codes are packed MSB first
+  uint32_t found = 0, off = t.off0;
+#pragma unroll
+  for (int i = 0; i < 15 - ROOT; ++i) {
+    const uint32_t L = ROOT + 1 + i;
+    const uint32_t k = (rev >> (32u - L)) - (t.fc[i] & 0xffffu);
+    const uint32_t cnt = t.fc[i] >> 16;
+    if (found == 0 && k < cnt) {
+      found = L;
+      rank = off + k;
+    }
+    off += cnt;
+  }
+  return found;
+}
+
 template <bool LITLEN>
 __device__ __forceinline__ uint16_t make_entry(uint32_t s, uint32_t L)
 {
@@ -553,7 +587,7 @@ __device__ __forceinline__ uint16_t make_entry(uint32_t s, uint32_t L)
 
 template <int ROOT, bool LITLEN, int POOL_OFF>
 __device__ __forceinline__ void build_lut(const LaneMem& m, int s0, int n, int root_off, int pool_end,
-                          int& pool_at, uint32_t& lost)
+                          int& pool_at, uint32_t& lost, LongTab<ROOT>& lt)
 {
   uint16_t* const lut = m.lut;
   uint32_t* const g_first = m.lens + (SCR_FIRST + (LITLEN ? 0 : 16)) * 32;
@@ -583,8 +617,11 @@ __device__ __forceinline__ void build_lut(const LaneMem& m, int s0, int n, int r
       off += count[L];
       if (count[L]) maxlen = L;
       if (code + count[L] > (1u << L)) over = true;
+      if (L > ROOT) lt.fc[L - ROOT - 1] = (code & 0xffffu) | (static_cast<uint32_t>(count[L]) << 16);
+      if (L == ROOT + 1) lt.off0 = offset[L];
     }
     g_first[0] = maxlen;
+    lt.usable = !over;
   }
 #pragma unroll 1
   for (int j = 0; j < (1 << ROOT); ++j)
@@ -726,7 +763,9 @@ template <class C>
 __device__ __forceinline__ int parse_block_header(BitReader& br, const LaneMem& m, uint32_t room,
                                                   uint32_t& final_block, int& n_lit, int& n_dist,
                                                   const uint8_t*& copy_src, uint32_t& copy_left,
-                                                  int* status, uint32_t* lost_out)
+                                                  int* status, uint32_t* lost_out,
+                                                  LongTab<C::ROOT_LIT>& lt_lit,
+                                                  LongTab<C::ROOT_DIST>& lt_dist)
 {
   *lost_out = 0;
   int err = -1;           // DecompressStatus once the stream is known to end here
@@ -904,9 +943,9 @@ __device__ __forceinline__ int parse_block_header(BitReader& br, const LaneMem& 
       int pool_at = C::POOL_OFF;
       uint32_t lost = 0;
       build_lut<C::ROOT_LIT, true, C::POOL_OFF>(m, 0, n_lit, C::LIT_OFF, C::POOL_OFF + C::POOL, pool_at,
-                                                lost);
+                                                lost, lt_lit);
       build_lut<C::ROOT_DIST, false, C::POOL_OFF>(m, n_lit, n_dist, C::DIST_OFF, C::POOL_OFF + C::POOL,
-                                                  pool_at, lost);
+                                                  pool_at, lost, lt_dist);
       *lost_out = lost;
       br.norm();
     }

@@ -233,6 +233,14 @@ huff_lanes_kernel(const BatchArgs a)
     ow.park();
     uint32_t final_block = 0;
     int n_lit = 0, n_dist = 0;
+    LongTab<C::ROOT_LIT> lt_lit;     // canonical first/count of the codes longer than the LUT roots
+    LongTab<C::ROOT_DIST> lt_dist;
+    lt_lit.usable = lt_dist.usable = false;
+#pragma unroll
+    for (int i = 0; i < 15 - C::ROOT_LIT; ++i) lt_lit.fc[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 15 - C::ROOT_DIST; ++i) lt_dist.fc[i] = 0;
+    lt_lit.off0 = lt_dist.off0 = 0;
     const uint8_t* copy_src = nullptr;
     uint32_t copy_left = 0;
     bool live = slot < n_todo;
@@ -255,7 +263,7 @@ huff_lanes_kernel(const BatchArgs a)
       if (state == S_HEADER) {
         uint32_t lost = 0;
         state = parse_block_header<C>(br, m, ow.room(), final_block, n_lit, n_dist, copy_src,
-                                      copy_left, &status, &lost);
+                                      copy_left, &status, &lost, lt_lit, lt_dist);
         // A small-geometry launch hands the stream on when the codes of its FIRST block do not
         // fit the tables well (more than ~2^-9 of the code space would take the exact slow
         // path): nothing has been written for it yet.  Later blocks just live with it.
@@ -343,19 +351,75 @@ huff_lanes_kernel(const BatchArgs a)
         // (near the end of the input the token must also fit into the real bits that are left)
         const int32_t left32 = static_cast<int32_t>(br.ebits - 32u * br.rp - bo0);  // (meaningful when `tail`)
         if (dec & ((L == 0) | (is_match & (dL == 0)) | (tail & (static_cast<int32_t>(used) > left32)))) {
-          SFB_STAT(slow_tokens);
-          const SlowToken t = slow_token(m.lens, (static_cast<uint64_t>(bits_hi) << 32) | bits,
-                                         br.real_left());
-          used = t.used;
-          is_match = t.kind == 2;
-          value = static_cast<uint32_t>(t.value);
-          dist = static_cast<uint32_t>(t.dist);
-          if (t.status != ST_SUCCESS || t.kind == 1) {  // failure, or end of block
-            status = t.status;
-            state = (t.status == ST_SUCCESS && !final_block) ? S_HEADER : S_DONE;
-            dec = false;
-            // (the end-of-block code is consumed: the next header starts right behind it)
-            if (t.status == ST_SUCCESS) br.skip(used);
+          // (a) a valid code longer than the tables hold: canonical decode in registers
+          bool done = false;
+          if (lt_lit.usable & lt_dist.usable) {
+            const uint16_t* sorted = reinterpret_cast<const uint16_t*>(m.lens + SCR_SORTED * 32);
+            bool ok = true, mt2 = is_match;
+            uint32_t u1 = used1, val2 = value;
+            if (L == 0) {
+              uint32_t rank = 0;
+              const uint32_t Lm = long_decode<C::ROOT_LIT>(lt_lit, bits, rank);
+              const uint32_t sym = Lm ? sorted[(rank >> 1) * 64 + (rank & 1u)] : 999u;
+              if (sym < 256u) {
+                val2 = sym;
+                mt2 = false;
+                u1 = Lm;
+              } else if (sym >= 257u && sym <= 285u) {
+                const uint32_t info = c_len_info[sym - 257u];
+                const uint32_t x = info >> 16;
+                val2 = (info & 0xffffu) + ((bits >> Lm) & ~(0xffffffffu << x));
+                mt2 = true;
+                u1 = Lm + x;
+              } else {
+                ok = false;  // end of block, 286/287, or no code at all: the exact path decides
+              }
+            }
+            uint32_t u2 = u1, dist2 = dist;
+            if (ok & mt2) {
+              const uint32_t db2 = br.peek_at(bo0 + u1);  // u1 <= 20
+              const uint32_t de2 = lut_lookup_s<C::ROOT_DIST, C::DIST_OFF, C::POOL_OFF, C::POOL>(lutb, db2);
+              uint32_t dl2 = de2 & 15u, dsym = (de2 >> 4) & 31u;
+              if (dl2 == 0) {
+                uint32_t rank = 0;
+                dl2 = long_decode<C::ROOT_DIST>(lt_dist, db2, rank);
+                const uint32_t r2 = 288u + rank;
+                dsym = dl2 ? sorted[(r2 >> 1) * 64 + (r2 & 1u)] : 99u;
+              }
+              if (dl2 != 0 && dsym < 30u) {
+                const uint32_t di = c_dist_info[dsym];
+                const uint32_t x = di >> 16;
+                dist2 = (di & 0xffffu) + ((db2 >> dl2) & ~(0xffffffffu << x));
+                u2 = u1 + dl2 + x;
+              } else {
+                ok = false;
+              }
+            }
+            if (ok && (!tail || static_cast<int32_t>(u2) <= left32)) {
+              SFB_STAT(long_tokens);
+              done = true;
+              used = u2;
+              is_match = mt2;
+              value = val2;
+              dist = dist2;
+            }
+          }
+          // (b) everything else — end of block included — is redone exactly, bit by bit
+          if (!done) {
+            SFB_STAT(slow_tokens);
+            const SlowToken t = slow_token(m.lens, (static_cast<uint64_t>(bits_hi) << 32) | bits,
+                                           br.real_left());
+            used = t.used;
+            is_match = t.kind == 2;
+            value = static_cast<uint32_t>(t.value);
+            dist = static_cast<uint32_t>(t.dist);
+            if (t.status != ST_SUCCESS || t.kind == 1) {  // failure, or end of block
+              status = t.status;
+              state = (t.status == ST_SUCCESS && !final_block) ? S_HEADER : S_DONE;
+              dec = false;
+              // (the end-of-block code is consumed: the next header starts right behind it)
+              if (t.status == ST_SUCCESS) br.skip(used);
+            }
           }
         }
         if (dec) br.skip(used);

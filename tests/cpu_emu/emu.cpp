@@ -10,7 +10,7 @@
 // the kernel's dynamic shared memory: one emulated lane, laid out exactly as on the device
 static thread_local uint16_t* emu_smem = nullptr;
 #define SFB_EMU_SMEM emu_smem
-static unsigned long long emu_stat_tokens = 0, emu_stat_slow_tokens = 0;
+static unsigned long long emu_stat_tokens = 0, emu_stat_slow_tokens = 0, emu_stat_long_tokens = 0;
 #define SFB_STAT(name) (++emu_stat_##name)
 #include "../../starflate_b200/csrc/huff_lanes.cuh"
 
@@ -132,4 +132,5 @@ extern "C" void emu_stats(unsigned long long* out)
   out[0] = emu_stat_tokens;
   out[1] = emu_stat_slow_tokens;
   out[2] = emu_stat_deferred;
+  out[3] = emu_stat_long_tokens;
 }

@@ -50,6 +50,6 @@ class Emu:
         return st, wr
 
     def stats(self):
-        out = (C.c_ulonglong * 3)()
+        out = (C.c_ulonglong * 4)()
         self.lib.emu_stats(out)
-        return {"tokens": out[0], "slow_tokens": out[1], "deferred": out[2]}
+        return {"tokens": out[0], "slow_tokens": out[1], "deferred": out[2], "long_tokens": out[3]}
