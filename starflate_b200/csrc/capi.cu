@@ -22,7 +22,7 @@ namespace {
 #define SFB_WARPS 4
 #endif
 #ifndef SFB_LZ_CTAS_PER_SM
-#define SFB_LZ_CTAS_PER_SM 0  /* 0 = as many as fit */
+#define SFB_LZ_CTAS_PER_SM 6  /* pass-2 CTAs per SM (0 = as many as fit); see lz_warp.cuh */
 #endif
 // Two LUT geometries for pass 1.  LaneCfg holds any block's codes (8/6-bit roots,
 // 896 B of shared memory per lane, 8 warps per SM).  SmallCfg (6/5-bit roots, 448 B per lane,

@@ -81,7 +81,9 @@ __device__ __forceinline__ uint32_t lz_mod_small(uint32_t k, uint32_t d)
   return k - ((k * inv) >> 20) * d;
 }
 
-__global__ void __launch_bounds__(LZ_THREADS) lz_resolve_kernel(const ResolveArgs a)
+// (launched with 6 CTAs = 48 warps per SM: measured best on C2 — with 64 the streams in flight push
+//  each other out of the L2, and squeezing the code under 40 registers costs more than it gains)
+__global__ void __launch_bounds__(LZ_THREADS, 5) lz_resolve_kernel(const ResolveArgs a)
 {
   constexpr unsigned FULL = 0xffffffffu;
   const uint32_t lane = threadIdx.x & 31u;
@@ -150,25 +152,40 @@ __global__ void __launch_bounds__(LZ_THREADS) lz_resolve_kernel(const ResolveArg
         c_d = (pk >> 15) + 1u;
       }
       // ---- chunks that lie wholly inside one long match (no head, interior of the stream):
-      //      every source is below P, no per-byte bookkeeping is needed -----------------------
-      if (interior && hm == 0 && c_end >= P + 128u && c_o < P) {  // (warp-uniform)
+      //      every source is below the match start, hence below P and final; no per-byte
+      //      bookkeeping is needed -----------------------------------------------------------
+      if (interior && hm == 0 && c_end >= P + 128u && c_o < P && (c_d == 1u || c_d >= 4u)) {  // (warp-uniform)
+        uint32_t v;
         if (c_d == 1u) {  // a run: all bytes equal the one before the match
-          const uint32_t v = base[c_o - 1u];
-          *reinterpret_cast<uint32_t*>(base + wp) = v * 0x01010101u;
-          __syncwarp();
-          cw = ncw; ncw = nncw; mw = nmw; nmw = nnmw;
-          continue;
+          v = base[c_o - 1u] * 0x01010101u;
+        } else {
+          // byte 0 of my word is k bytes into the match: its source is start - d + (k mod d),
+          // and so on round the period for the other three
+          const uint32_t k = wp - c_o;
+          const uint32_t m = k >= c_d ? lz_mod_small(k, c_d) : k;
+          const uint32_t s0 = c_o - c_d + m;
+          if (m + 3u < c_d) {  // four consecutive sources: one unaligned word
+            const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(base + (s0 & ~3u));
+            const uint32_t lo = wsrc[0];
+            const uint32_t hi = (s0 & 3u) ? wsrc[1] : 0u;
+            v = lz_funnel(lo, hi, 8u * (s0 & 3u));
+          } else {  // the period wraps inside my word (at most once: d >= 4)
+            v = 0;
+#pragma unroll
+            for (uint32_t b = 0; b < 4; ++b) {
+              uint32_t mb = m + b;
+              if (mb >= c_d) mb -= c_d;
+              v |= static_cast<uint32_t>(base[c_o - c_d + mb]) << (8u * b);
+            }
+          }
         }
-        if (c_d >= 128u && c_end - c_o <= c_d) {  // a far, non-overlapping copy: unaligned word gather
-          const uint32_t s0 = wp - c_d;
-          const uint32_t* wsrc = reinterpret_cast<const uint32_t*>(base + (s0 & ~3u));
-          const uint32_t lo = wsrc[0];
-          const uint32_t hi = (s0 & 3u) ? wsrc[1] : 0u;
-          *reinterpret_cast<uint32_t*>(base + wp) = lz_funnel(lo, hi, 8u * (s0 & 3u));
-          __syncwarp();
-          cw = ncw; ncw = nncw; mw = nmw; nmw = nnmw;
-          continue;
-        }
+        *reinterpret_cast<uint32_t*>(base + wp) = v;
+        __syncwarp();
+        cw = ncw;
+        ncw = nncw;
+        mw = nmw;
+        nmw = nnmw;
+        continue;
       }
       // ---- walk my 4 bytes, switching to my own heads as I pass them -------------------------
       uint32_t src[4];
