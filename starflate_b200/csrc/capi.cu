@@ -49,6 +49,8 @@ struct sfb200_ctx {
   int small_regs_per_thread = 0;
   uint32_t* d_defer = nullptr;  // streams handed from the small to the large geometry
   uint64_t d_defer_n = 0;
+  uint32_t* d_order = nullptr;  // processing order (streams sorted by first block type)
+  uint64_t d_order_n = 0;
   unsigned long long* d_counter = nullptr;  // 2 * kMaxWaves work counters
   uint32_t* d_lens = nullptr;  // per-resident-lane code-length scratch
   uint32_t* d_bits = nullptr;  // match-head bitmap: 1 bit per dst byte (grown on demand)
@@ -156,7 +158,7 @@ int sfb200_create(int device, sfb200_ctx** out)
     if (cudaFuncGetAttributes(&lfa, sfb::lz_resolve_kernel) == cudaSuccess)
       ctx->lz_regs_per_thread = lfa.numRegs;
   }
-  if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_counter), kCountersPerWave * kMaxWaves * sizeof(unsigned long long)) !=
+  if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_counter), (kCountersPerWave * kMaxWaves + 8) * sizeof(unsigned long long)) !=
       cudaSuccess)
     return bail(SFB200_RC_OUT_OF_MEMORY);
   {
@@ -199,6 +201,7 @@ void sfb200_destroy(sfb200_ctx* ctx)
   cudaFree(ctx->d_bits);
   cudaFree(ctx->d_written);
   cudaFree(ctx->d_defer);
+  cudaFree(ctx->d_order);
   cudaFree(ctx->d_src);
   cudaFree(ctx->d_dst);
   cudaFree(ctx->d_meta);
@@ -319,7 +322,35 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
   SFB_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
   SFB_TRY(ctx, cudaMemsetAsync(ctx->d_counter, 0,
                                kCountersPerWave * std::max<uint64_t>(n_waves, 1) * sizeof(unsigned long long), st));
+  SFB_TRY(ctx, cudaMemsetAsync(ctx->d_counter + kCountersPerWave * kMaxWaves, 0, 8 * sizeof(unsigned long long), st));
   SFB_TRY(ctx, cudaMemsetAsync(ctx->d_bits, 0, bits_words * sizeof(uint32_t), st));
+  // Order the streams by the type of their first block (see lz_warp.cuh: PrepArgs)
+  bool sorted = n >= 64 && n < 0xffffffffull;
+  if (const char* e = std::getenv("SFB200_NO_SORT"))
+    if (e[0] == '1') sorted = false;
+  if (sorted) {
+    if (n > ctx->d_order_n) {
+      if (ctx->d_order) SFB_TRY(ctx, cudaFree(ctx->d_order));
+      ctx->d_order = nullptr;
+      ctx->d_order_n = 0;
+      const uint64_t want = n + n / 8 + 64;
+      SFB_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_order), want * sizeof(uint32_t)));
+      ctx->d_order_n = want;
+    }
+    sfb::PrepArgs pa;
+    pa.src_base = src_base;
+    pa.src_off = src_off;
+    pa.src_len = src_len;
+    pa.n = n;
+    pa.type_count = ctx->d_counter + kCountersPerWave * kMaxWaves;
+    pa.type_cursor = pa.type_count + 4;
+    pa.order = ctx->d_order;
+    const unsigned grid = static_cast<unsigned>((n + sfb::PREP_THREADS - 1) / sfb::PREP_THREADS);
+    sfb::prep_count_kernel<<<grid, sfb::PREP_THREADS, 0, st>>>(pa);
+    sfb::prep_scatter_kernel<<<grid, sfb::PREP_THREADS, 0, st>>>(pa);
+    SFB_TRY(ctx, cudaGetLastError());
+    ctx->launches += 2;
+  }
   SFB_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
   if (overlap) {
     SFB_TRY(ctx, cudaEventRecord(ctx->wave_ev[n_waves], st));
@@ -330,23 +361,25 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
     const uint64_t first = k * per_wave;
     const uint64_t cnt = std::min(per_wave, n - first);
     unsigned long long* const ctr = ctx->d_counter + kCountersPerWave * k;
+    const uint32_t* const order = sorted ? ctx->d_order + first : nullptr;
     // pass 1: Huffman layer, one lane per stream
     sfb::BatchArgs a;
     a.src_base = src_base;
-    a.src_off = src_off + first;
-    a.src_len = src_len + first;
+    a.src_off = src_off;
+    a.src_len = src_len;
     a.dst_base = dst_base;
     a.dst_delta = delta;
-    a.dst_off = dst_off + first;
-    a.dst_cap = dst_cap + first;
-    a.status = status + first;
-    a.written = written + first;
+    a.dst_off = dst_off;
+    a.dst_cap = dst_cap;
+    a.status = status;
+    a.written = written;
     a.n = cnt;
+    a.idx_base = first;
     a.lens_scratch = ctx->d_lens;
     a.match_bits = ctx->d_bits;
     a.defer_list = nullptr;
     a.defer_count = nullptr;
-    a.todo_list = nullptr;
+    a.todo_list = order;
     a.todo_count = nullptr;
     const uint64_t groups = (cnt + 31) / 32;
     if (use_small) {
@@ -385,10 +418,12 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
     sfb::ResolveArgs r;
     r.dst_base = dst_base;
     r.dst_delta = delta;
-    r.dst_off = dst_off + first;
-    r.written = written + first;
+    r.dst_off = dst_off;
+    r.written = written;
     r.match_bits = ctx->d_bits;
     r.n = cnt;
+    r.idx_base = first;
+    r.todo_list = order;
     r.stream_counter = ctr + 2;
     {
       constexpr uint64_t wpc = sfb::LZ_THREADS / 32;

@@ -55,7 +55,8 @@ struct BatchArgs {
   const uint64_t* dst_cap;
   uint8_t* status;
   uint64_t* written;  // never null here (the resolve pass reads it)
-  uint64_t n;
+  uint64_t n;                         // streams of this launch: indices idx_base .. idx_base + n - 1,
+  uint64_t idx_base;                  // or todo_list[0 .. n) when a list is given
   unsigned long long* group_counter;  // dynamic work distribution (zeroed before launch)
   uint32_t* lens_scratch;             // gridDim.x * WARPS * SCRATCH_WORDS * 32 words
   uint32_t* match_bits;               // match-head bitmap, bit k <-> dst_base[k] (zeroed before launch)
@@ -63,8 +64,8 @@ struct BatchArgs {
   // block's codes do not fit its tables to a launch with the large one.
   uint32_t* defer_list;                     // out (small geometry): indices of the streams handed on; else null
   unsigned long long* defer_count;          // out: how many
-  const uint32_t* todo_list;                // in (large geometry): the streams to do (null: all n)
-  const unsigned long long* todo_count;     // in: how many
+  const uint32_t* todo_list;                // in: the streams to do, in this order (null: idx_base + 0 .. n)
+  const unsigned long long* todo_count;     // in: how many of them (null: n)
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -214,7 +214,7 @@ huff_lanes_kernel(const BatchArgs a)
   const saddr_t ring = to_saddr(warp_smem + C::WARP_U16 * 2 + lane * 16);
 
   // the streams of this launch: all n, or the ones an earlier launch handed on
-  const uint64_t n_todo = a.todo_list ? static_cast<uint64_t>(*a.todo_count) : a.n;
+  const uint64_t n_todo = a.todo_count ? static_cast<uint64_t>(*a.todo_count) : a.n;
   const uint64_t n_groups = (n_todo + 31) / 32;
   for (;;) {
     unsigned long long g = 0;
@@ -222,7 +222,7 @@ huff_lanes_kernel(const BatchArgs a)
     g = __shfl_sync(FULL, g, 0);
     if (g >= n_groups) break;
     const uint64_t slot = g * 32 + static_cast<uint64_t>(lane);
-    const uint64_t idx = (a.todo_list && slot < n_todo) ? a.todo_list[slot] : slot;
+    const uint64_t idx = a.todo_list ? (slot < n_todo ? a.todo_list[slot] : 0) : a.idx_base + slot;
 
     int state = S_DONE;
     int status = ST_SUCCESS;

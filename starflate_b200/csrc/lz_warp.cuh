@@ -39,9 +39,73 @@ struct ResolveArgs {
   const uint64_t* dst_off;
   const uint64_t* written;
   const uint32_t* match_bits;  // bit k <-> dst_base[k]
-  uint64_t n;
+  uint64_t n;                          // streams of this launch: idx_base .. idx_base + n - 1,
+  uint64_t idx_base;                   // or todo_list[0 .. n) when a list is given
+  const uint32_t* todo_list;
   unsigned long long* stream_counter;  // zeroed before launch
 };
+
+// ---------------------------------------------------------------------------------------------
+// Batch preparation: order the streams by the type of their first block (dynamic, fixed, other,
+// stored) so that the 32 streams a pass-1 warp decodes together do the same kind of work — in a
+// mixed batch (BASELINE config 3) a third of the lanes would otherwise sit out the token loop
+// because their stream was a stored block, and the dynamic ones, which take longest, start
+// first.  Two small kernels: count per type, then scatter (block-wise reserved ranges).
+struct PrepArgs {
+  const uint8_t* src_base;
+  const uint64_t* src_off;
+  const uint64_t* src_len;
+  uint64_t n;
+  unsigned long long* type_count;   // [4] zeroed before launch, in the order of lz_type_rank()
+  unsigned long long* type_cursor;  // [4] zeroed before launch
+  uint32_t* order;                  // out: n stream indices
+};
+
+// rank of a stream in the processing order, from the BTYPE bits of its first byte
+__device__ __forceinline__ uint32_t lz_type_rank(const PrepArgs& a, uint64_t i)
+{
+  if (a.src_len[i] == 0) return 2u;
+  const uint32_t btype = (a.src_base[a.src_off[i]] >> 1) & 3u;
+  return btype == 2u ? 0u : btype == 1u ? 1u : btype == 3u ? 2u : 3u;  // dynamic, fixed, invalid, stored
+}
+
+constexpr int PREP_THREADS = 256;
+
+#ifndef SFB_CPU_EMU  // (block-level kernels: exercised on the device only)
+
+__global__ void __launch_bounds__(PREP_THREADS) prep_count_kernel(const PrepArgs a)
+{
+  __shared__ unsigned int cnt[4];
+  if (threadIdx.x < 4) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * PREP_THREADS + threadIdx.x;
+  if (i < a.n) atomicAdd(&cnt[lz_type_rank(a, i)], 1u);
+  __syncthreads();
+  if (threadIdx.x < 4 && cnt[threadIdx.x]) atomicAdd(&a.type_count[threadIdx.x], static_cast<unsigned long long>(cnt[threadIdx.x]));
+}
+
+__global__ void __launch_bounds__(PREP_THREADS) prep_scatter_kernel(const PrepArgs a)
+{
+  __shared__ unsigned int cnt[4];
+  __shared__ unsigned long long base[4];
+  if (threadIdx.x < 4) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint64_t i = static_cast<uint64_t>(blockIdx.x) * PREP_THREADS + threadIdx.x;
+  uint32_t t = 0, r = 0;
+  if (i < a.n) {
+    t = lz_type_rank(a, i);
+    r = atomicAdd(&cnt[t], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    unsigned long long start = 0;
+    for (unsigned k = 0; k < threadIdx.x; ++k) start += a.type_count[k];
+    base[threadIdx.x] = start + (cnt[threadIdx.x] ? atomicAdd(&a.type_cursor[threadIdx.x], static_cast<unsigned long long>(cnt[threadIdx.x])) : 0ull);
+  }
+  __syncthreads();
+  if (i < a.n) a.order[base[t] + r] = static_cast<uint32_t>(i);
+}
+#endif  // SFB_CPU_EMU
 
 constexpr int LZ_THREADS = 256;
 
@@ -95,6 +159,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 5) lz_resolve_kernel(const Resolve
     if (lane == 0) si = atomicAdd(a.stream_counter, 1ull);
     si = __shfl_sync(FULL, si, 0);
     if (si >= a.n) break;
+    si = a.todo_list ? a.todo_list[si] : a.idx_base + si;
     const uint64_t off = a.dst_off[si] + a.dst_delta;
     const uint64_t wr = a.written[si];
     if (wr == 0) continue;

@@ -89,6 +89,7 @@ extern "C" int emu_decompress_batch(const uint8_t* src, const uint64_t* src_off,
     a.status = &status[i];
     a.written = &wr;
     a.n = 1;
+    a.idx_base = 0;
     a.group_counter = &counter;
     a.lens_scratch = lens.data();
     a.match_bits = bits.data();

@@ -21,6 +21,8 @@ extern "C" void emu_lz_resolve(uint8_t* dst_base, const uint64_t* dst_off, const
   a.written = written;
   a.match_bits = match_bits;
   a.n = n;
+  a.idx_base = 0;
+  a.todo_list = nullptr;
   a.stream_counter = &counter;
   std::vector<std::thread> lanes;
   for (unsigned l = 0; l < 32; ++l)
