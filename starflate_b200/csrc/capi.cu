@@ -295,7 +295,11 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
                              LaneCfg::WARPS * 32;
   const uint64_t small_lanes = static_cast<uint64_t>(ctx->sm_count) *
                                static_cast<uint64_t>(ctx->small_ctas_per_sm) * SmallCfg::WARPS * 32;
-  const uint64_t wave = use_small ? small_lanes : big_lanes;
+  // (a launch takes one wave of streams, or several when the batch has more than eight waves:
+  //  inside a launch warps pull groups dynamically, which evens out unequal streams and lets a
+  //  lane keep its fixed-Huffman tables from one stream to the next)
+  const uint64_t lanes = use_small ? small_lanes : big_lanes;
+  const uint64_t wave = lanes * std::max<uint64_t>(1, (n + 8 * lanes - 1) / (8 * lanes));
   uint64_t n_waves = (n + wave - 1) / wave;
   if (const char* e = std::getenv("SFB200_NO_OVERLAP"))
     if (e[0] == '1') n_waves = 1;

@@ -766,7 +766,7 @@ __device__ __forceinline__ int parse_block_header(BitReader& br, const LaneMem& 
                                                   const uint8_t*& copy_src, uint32_t& copy_left,
                                                   int* status, uint32_t* lost_out,
                                                   LongTab<C::ROOT_LIT>& lt_lit,
-                                                  LongTab<C::ROOT_DIST>& lt_dist)
+                                                  LongTab<C::ROOT_DIST>& lt_dist, bool& tables_fixed)
 {
   *lost_out = 0;
   int err = -1;           // DecompressStatus once the stream is known to end here
@@ -816,23 +816,30 @@ __device__ __forceinline__ int parse_block_header(BitReader& br, const LaneMem& 
       }
     }
   } else if (err < 0) {
+    // `tables_fixed`: this lane's LUTs, scratch arrays and LongTabs already hold the fixed codes
+    // (the previous block it decoded — of this or of an earlier stream — was a fixed one):
+    // nothing to build.  Batches sorted by type give whole warps of such streams.
+    const bool reuse = type == 1 && tables_fixed;
     if (type == 1) {
       // fixed codes: src/decompress.cpp:25-40
       n_lit = 288;
       n_dist = 32;
+      if (!reuse) {
 #pragma unroll 1
-      for (int j = 0; j < LENS_WORDS; ++j) {
-        const int s = j * 8;
-        uint32_t v;
-        if (s < 144) v = 0x88888888u;
-        else if (s < 256) v = 0x99999999u;
-        else if (s < 280) v = 0x77777777u;
-        else if (s < 288) v = 0x88888888u;
-        else v = 0x55555555u;
-        m.lens[j * 32] = v;
+        for (int j = 0; j < LENS_WORDS; ++j) {
+          const int s = j * 8;
+          uint32_t v;
+          if (s < 144) v = 0x88888888u;
+          else if (s < 256) v = 0x99999999u;
+          else if (s < 280) v = 0x77777777u;
+          else if (s < 288) v = 0x88888888u;
+          else v = 0x55555555u;
+          m.lens[j * 32] = v;
+        }
       }
     } else {
-      // dynamic codes
+      // dynamic codes (from here on the lane's tables and scratch are being overwritten)
+      tables_fixed = false;
       br.norm();
       int n_cl = 0;
       if (br.real_left() < 14) {
@@ -940,7 +947,9 @@ __device__ __forceinline__ int parse_block_header(BitReader& br, const LaneMem& 
         if (err < 0) lw.finish();
       }
     }
-    if (err < 0) {
+    if (err < 0 && reuse) br.norm();
+    if (err < 0 && !reuse) {
+      tables_fixed = type == 1;
       int pool_at = C::POOL_OFF;
       uint32_t lost = 0;
       build_lut<C::ROOT_LIT, true, C::POOL_OFF>(m, 0, n_lit, C::LIT_OFF, C::POOL_OFF + C::POOL, pool_at,

@@ -216,6 +216,16 @@ huff_lanes_kernel(const BatchArgs a)
   // the streams of this launch: all n, or the ones an earlier launch handed on
   const uint64_t n_todo = a.todo_count ? static_cast<uint64_t>(*a.todo_count) : a.n;
   const uint64_t n_groups = (n_todo + 31) / 32;
+  // per-lane table state that outlives a stream (see parse_block_header)
+  bool tables_fixed = false;
+  LongTab<C::ROOT_LIT> lt_lit;     // canonical first/count of the codes longer than the LUT roots
+  LongTab<C::ROOT_DIST> lt_dist;
+  lt_lit.usable = lt_dist.usable = false;
+#pragma unroll
+  for (int i = 0; i < 15 - C::ROOT_LIT; ++i) lt_lit.fc[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 15 - C::ROOT_DIST; ++i) lt_dist.fc[i] = 0;
+  lt_lit.off0 = lt_dist.off0 = 0;
   for (;;) {
     unsigned long long g = 0;
     if (lane == 0) g = atomicAdd(a.group_counter, 1ull);
@@ -233,14 +243,6 @@ huff_lanes_kernel(const BatchArgs a)
     ow.park();
     uint32_t final_block = 0;
     int n_lit = 0, n_dist = 0;
-    LongTab<C::ROOT_LIT> lt_lit;     // canonical first/count of the codes longer than the LUT roots
-    LongTab<C::ROOT_DIST> lt_dist;
-    lt_lit.usable = lt_dist.usable = false;
-#pragma unroll
-    for (int i = 0; i < 15 - C::ROOT_LIT; ++i) lt_lit.fc[i] = 0;
-#pragma unroll
-    for (int i = 0; i < 15 - C::ROOT_DIST; ++i) lt_dist.fc[i] = 0;
-    lt_lit.off0 = lt_dist.off0 = 0;
     const uint8_t* copy_src = nullptr;
     uint32_t copy_left = 0;
     bool live = slot < n_todo;
@@ -263,7 +265,7 @@ huff_lanes_kernel(const BatchArgs a)
       if (state == S_HEADER) {
         uint32_t lost = 0;
         state = parse_block_header<C>(br, m, ow.room(), final_block, n_lit, n_dist, copy_src,
-                                      copy_left, &status, &lost, lt_lit, lt_dist);
+                                      copy_left, &status, &lost, lt_lit, lt_dist, tables_fixed);
         // A small-geometry launch hands the stream on when the codes of its FIRST block do not
         // fit the tables well (more than ~2^-9 of the code space would take the exact slow
         // path): nothing has been written for it yet.  Later blocks just live with it.
