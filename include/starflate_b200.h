@@ -71,6 +71,12 @@ int sfb200_abi_version(void);
  * Semantics preserved per stream: first error wins, bytes already produced stay in dst,
  * dst beyond `written` is never touched, trailing src bytes after the final block are ignored.
  * Precondition: src_len[i], dst_cap[i] < 2^32 - 256 (else status[i] = SFB200_ERROR).
+ * Memory touched: src is read in aligned 16-byte blocks, never past a stream's last byte and at
+ * most 15 bytes before its first (inside the same 16-byte block); dst is read and written in
+ * aligned words, only words that hold at least one byte of a stream's region, and only the
+ * region's own bytes are ever modified.
+ * Threading: a context serves one call at a time (it owns scratch buffers and streams); use one
+ * context per thread or serialise calls, as the C++ layer does.
  * `cuda_stream` is a cudaStream_t (NULL = default stream); the call is asynchronous. */
 int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
                                    const uint64_t* src_off, const uint64_t* src_len,

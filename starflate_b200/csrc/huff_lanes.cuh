@@ -290,7 +290,13 @@ huff_lanes_kernel(const BatchArgs a)
           // dst-aligned 32-bit words, each funnelled from the two aligned src words it spans
           // (src words are only read where they hold at least one payload byte)
           const uint32_t head = min(len, static_cast<uint32_t>(-reinterpret_cast<intptr_t>(d)) & 3u);
-          const uint32_t nwords = (len - head) >> 2;
+          const uint8_t* sb0 = s + head;
+          // (when src and dst are not congruent mod 4 a dst word spans two src words, and the
+          //  second one of the LAST dst word could reach past the payload — i.e. past the end
+          //  of the caller's buffer: leave that word to the byte loop)
+          const bool skew = ((reinterpret_cast<uintptr_t>(sb0)) & 3u) != 0;
+          uint32_t nwords = (len - head) >> 2;
+          if (skew && nwords) --nwords;
           const uint32_t tail0 = head + 4u * nwords;
           for (uint32_t i = static_cast<uint32_t>(lane); i < head; i += LANES) d[i] = s[i];
           const uint8_t* sb = s + head;
