@@ -119,6 +119,9 @@ typedef struct sfb200_launch_info {
   int small_warps_per_cta;
   int small_ctas_per_sm;
   int small_regs_per_thread;
+  /* pass 1 in single-stream mode, huff_stream_kernel (one warp per stream; few, large streams) */
+  int stream_ctas_per_sm;
+  int stream_regs_per_thread;
   /* pass 2, lz_resolve_kernel (one warp per stream) */
   int lz_threads_per_cta;
   int lz_ctas_per_sm;

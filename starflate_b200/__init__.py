@@ -36,6 +36,7 @@ class _LaunchInfo(C.Structure):
                 ("smem_bytes_per_cta", C.c_int), ("regs_per_thread", C.c_int),
                 ("small_warps_per_cta", C.c_int), ("small_ctas_per_sm", C.c_int),
                 ("small_regs_per_thread", C.c_int),
+                ("stream_ctas_per_sm", C.c_int), ("stream_regs_per_thread", C.c_int),
                 ("lz_threads_per_cta", C.c_int), ("lz_ctas_per_sm", C.c_int),
                 ("lz_regs_per_thread", C.c_int), ("kernel_launches", C.c_uint64)]
 

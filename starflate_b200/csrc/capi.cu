@@ -3,6 +3,7 @@
 // exists anywhere in this library: without a CUDA device every call fails.
 #include "../../include/starflate_b200.h"
 #include "huff_lanes.cuh"
+#include "huff_stream.cuh"
 #include "lz_warp.cuh"
 
 #include <cstdio>
@@ -31,6 +32,8 @@ namespace {
 // block does not fit is handed to a LaneCfg launch.
 using LaneCfg = sfb::Cfg<SFB_ROOT_LIT, SFB_ROOT_DIST, SFB_POOL, SFB_WARPS>;
 using SmallCfg = sfb::Cfg<6, 5, 96, 8, 2>;
+// single-stream mode (huff_stream.cuh): one warp per CTA, the large geometry
+using StreamCfg = sfb::Cfg<SFB_ROOT_LIT, SFB_ROOT_DIST, SFB_POOL, 1>;
 // work counters per call, four per wave k: [4k] small pass 1, [4k+1] large pass 1, [4k+2] pass 2,
 // [4k+3] number of streams handed from the small to the large geometry
 constexpr uint64_t kMaxWaves = 256;
@@ -47,6 +50,8 @@ struct sfb200_ctx {
   int lz_regs_per_thread = 0;
   int small_ctas_per_sm = 0;   // SmallCfg pass 1 (0: not usable)
   int small_regs_per_thread = 0;
+  int stream_ctas_per_sm = 0;  // huff_stream_kernel (0: not usable)
+  int stream_regs_per_thread = 0;
   uint32_t* d_defer = nullptr;  // streams handed from the small to the large geometry
   uint64_t d_defer_n = 0;
   uint32_t* d_order = nullptr;  // processing order (streams sorted by first block type)
@@ -175,7 +180,21 @@ int sfb200_create(int device, sfb200_ctx** out)
     if (cudaFuncGetAttributes(&sfa, sk) == cudaSuccess) ctx->small_regs_per_thread = sfa.numRegs;
     cudaGetLastError();
   }
-  const size_t big_warps = static_cast<size_t>(per_sm) * LaneCfg::WARPS;
+  {
+    auto sk = sfb::huff_stream_kernel<StreamCfg>;
+    int sp = 0;
+    if (cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, StreamCfg::SMEM_BYTES) ==
+            cudaSuccess &&
+        cudaFuncSetAttribute(sk, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sp, sk, 32, StreamCfg::SMEM_BYTES) == cudaSuccess)
+      ctx->stream_ctas_per_sm = sp;
+    cudaFuncAttributes sfa;
+    if (cudaFuncGetAttributes(&sfa, sk) == cudaSuccess) ctx->stream_regs_per_thread = sfa.numRegs;
+    cudaGetLastError();
+  }
+  const size_t big_warps = std::max(static_cast<size_t>(per_sm) * LaneCfg::WARPS,
+                                    static_cast<size_t>(ctx->stream_ctas_per_sm));
   const size_t small_warps = static_cast<size_t>(ctx->small_ctas_per_sm) * SmallCfg::WARPS;
   const size_t lens_bytes = static_cast<size_t>(ctx->sm_count) * std::max(big_warps, small_warps) *
                             sfb::SCRATCH_WORDS * 32 * sizeof(uint32_t);
@@ -232,6 +251,8 @@ int sfb200_get_launch_info(sfb200_ctx* ctx, sfb200_launch_info* out)
   out->small_warps_per_cta = SmallCfg::WARPS;
   out->small_ctas_per_sm = ctx->small_ctas_per_sm;
   out->small_regs_per_thread = ctx->small_regs_per_thread;
+  out->stream_ctas_per_sm = ctx->stream_ctas_per_sm;
+  out->stream_regs_per_thread = ctx->stream_regs_per_thread;
   out->kernel_launches = ctx->launches;
   return SFB200_RC_OK;
 }
@@ -271,6 +292,12 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
     }
     written = ctx->d_written;
   }
+  // Few streams: a lane per stream would leave the GPU empty, so each stream gets a warp that
+  // decodes 32 spans of it speculatively (huff_stream.cuh).  Same results, by construction.
+  bool stream_mode = ctx->stream_ctas_per_sm > 0 &&
+                     n * 32 <= static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->ctas_per_sm) *
+                                   LaneCfg::WARPS * 32;
+  if (const char* e = std::getenv("SFB200_STREAM_MODE")) stream_mode = e[0] == '1' && ctx->stream_ctas_per_sm > 0;
   // Geometry.  Measured on C2 (profiles/r01_small_geometry_c2.md): with 16 warps per SM the small
   // geometry makes pass 1 issue-bound (63 % of issue slots, 11.1 ms against 12.1 ms for the
   // large one), and the few percent of streams it hands on cost a whole extra stream latency
@@ -304,6 +331,7 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
   if (const char* e = std::getenv("SFB200_NO_OVERLAP"))
     if (e[0] == '1') n_waves = 1;
   if (n_waves > kMaxWaves) n_waves = 1;  // (counters are a fixed array: enormous batches run unsplit)
+  if (stream_mode) n_waves = 1;
   // With two waves the overlapped part (pass 1 of the second, pass 2 of the first) wants ~95 % of
   // the issue slots and pass 1, which is latency-bound, slows down by more than pass 2 gains
   // (C2: 21.8 ms overlapped, 20.2 ms back to back); from three waves on it pays (131 072 streams:
@@ -329,7 +357,7 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
   SFB_TRY(ctx, cudaMemsetAsync(ctx->d_counter + kCountersPerWave * kMaxWaves, 0, 8 * sizeof(unsigned long long), st));
   SFB_TRY(ctx, cudaMemsetAsync(ctx->d_bits, 0, bits_words * sizeof(uint32_t), st));
   // Order the streams by the type of their first block (see lz_warp.cuh: PrepArgs)
-  bool sorted = n >= 64 && n < 0xffffffffull;
+  bool sorted = n >= 64 && n < 0xffffffffull && !stream_mode;
   if (const char* e = std::getenv("SFB200_NO_SORT"))
     if (e[0] == '1') sorted = false;
   if (sorted) {
@@ -386,7 +414,30 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
     a.todo_list = order;
     a.todo_count = nullptr;
     const uint64_t groups = (cnt + 31) / 32;
-    if (use_small) {
+    if (stream_mode) {
+      sfb::StreamArgs sa;
+      sa.src_base = src_base;
+      sa.src_off = src_off;
+      sa.src_len = src_len;
+      sa.dst_base = dst_base;
+      sa.dst_delta = delta;
+      sa.dst_off = dst_off;
+      sa.dst_cap = dst_cap;
+      sa.status = status;
+      sa.written = written;
+      sa.list = nullptr;
+      sa.idx_base = first;
+      sa.n = cnt;
+      sa.stream_counter = ctr + 0;
+      sa.lens_scratch = ctx->d_lens;
+      sa.match_bits = ctx->d_bits;
+      const uint64_t resident =
+          static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->stream_ctas_per_sm);
+      const unsigned grid = static_cast<unsigned>(cnt < resident ? cnt : resident);
+      sfb::huff_stream_kernel<StreamCfg><<<grid, 32, StreamCfg::SMEM_BYTES, s1>>>(sa);
+      SFB_TRY(ctx, cudaGetLastError());
+      ctx->launches += 1;
+    } else if (use_small) {
       a.group_counter = ctr + 0;
       a.defer_list = ctx->d_defer + first;
       a.defer_count = ctr + 3;
@@ -403,7 +454,7 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
       a.todo_list = ctx->d_defer + first;
       a.todo_count = ctr + 3;
     }
-    {
+    if (!stream_mode) {
       a.group_counter = ctr + 1;
       const uint64_t want = (groups + LaneCfg::WARPS - 1) / LaneCfg::WARPS;
       const uint64_t resident =

@@ -293,6 +293,10 @@ struct BitReader {
   __device__ __forceinline__ void init_at(uint32_t at, unsigned skip_bits)
   {
     const uint32_t x0 = at >> 2;
+    // copies still in flight from before the jump target the same ring slots: let them land
+    // first, or one of them could overwrite a block staged below
+    cp_async_commit();
+    cp_async_wait<0>();
     rp = x0;
     pfb = x0 >> 2;
     fill_sync();
@@ -365,6 +369,11 @@ struct BitReader {
   }
   // some word already in the window reaches past the end of the stream
   __device__ __forceinline__ bool tail() const { return 4u * rp > iend; }
+  // continue at bit `bit` of the stream (synchronous staging)
+  __device__ __forceinline__ void seek_bit(uint64_t bit)
+  {
+    init_at(lead0 + static_cast<uint32_t>(bit >> 3), static_cast<unsigned>(bit & 7));
+  }
 };
 
 // ---------------------------------------------------------------------------------------------

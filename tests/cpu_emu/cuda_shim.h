@@ -13,7 +13,7 @@
 #define __global__
 #define __host__
 #define __forceinline__ inline
-#define __noinline__ __attribute__((noinline))
+#define __noinline__ inline __attribute__((noinline))
 #define __constant__ static const
 #define __shared__
 #define __align__(n) __attribute__((aligned(n)))

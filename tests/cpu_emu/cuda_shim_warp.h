@@ -15,8 +15,11 @@
 #define __global__
 #define __host__
 #define __forceinline__ inline
-#define __noinline__ __attribute__((noinline))
+#define __noinline__ inline __attribute__((noinline))
 #define __launch_bounds__(...)
+#define __constant__ static const
+#define __shared__
+#define __align__(n) __attribute__((aligned(n)))
 
 struct emu_dim3 { unsigned x = 0, y = 0, z = 0; };
 static thread_local emu_dim3 threadIdx, blockIdx;
@@ -61,6 +64,22 @@ static inline unsigned __ballot_sync(unsigned, int p)
 static inline int __any_sync(unsigned mask, int p) { return __ballot_sync(mask, p) != 0; }
 static inline int __all_sync(unsigned mask, int p) { return __ballot_sync(mask, p) == 0xffffffffu; }
 static inline void __syncwarp() { emu_warp->bar.arrive_and_wait(); }
+static inline void __syncthreads() { emu_warp->bar.arrive_and_wait(); }  // (one warp per block here)
+template <class T> static inline T __shfl_up_sync(unsigned, T v, unsigned d)
+{
+  const unsigned lane = threadIdx.x & 31u;
+  return emu_exchange(v, lane >= d ? lane - d : lane);
+}
+static inline unsigned __brev(unsigned v)
+{
+  v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+  v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+  v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
+  v = ((v >> 8) & 0x00FF00FFu) | ((v & 0x00FF00FFu) << 8);
+  return (v >> 16) | (v << 16);
+}
+static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+static inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz(static_cast<unsigned>(v)); }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v)

@@ -1,0 +1,86 @@
+// TEST INFRASTRUCTURE ONLY — the single-stream pass-1 kernel (huff_stream.cuh: 32 lanes decode 32
+// spans of one block speculatively) run on the host, one warp = 32 threads in lock-step through
+// real barriers (see cuda_shim_warp.h).
+#define SFB_CPU_EMU 1
+#include "cuda_shim_warp.h"
+
+#include <thread>
+#include <vector>
+
+static uint16_t* emu_stream_smem = nullptr;  // one warp's shared memory, seen by all its lanes
+#define SFB_EMU_SMEM emu_stream_smem
+#include "../../starflate_b200/csrc/huff_stream.cuh"
+
+using StreamCfg = sfb::Cfg<8, 6, 96, 1>;
+
+// one stream; dst_base must be 128-byte aligned, the stream's region starts at dst_base + dst_off
+extern "C" void emu_huff_stream(const uint8_t* src, uint64_t src_len, uint8_t* dst_base, uint64_t dst_off,
+                                uint64_t dst_cap, uint32_t* match_bits, uint8_t* status, uint64_t* written)
+{
+  EmuWarp warp;
+  emu_warp = &warp;
+  std::vector<uint16_t> smem(StreamCfg::SMEM_BYTES / 2 + 64, 0xDEAD);
+  std::vector<uint32_t> lens(sfb::SCRATCH_WORDS * 32, 0xDEADBEEFu);
+  emu_stream_smem = smem.data();
+  unsigned long long counter = 0;
+  const uint64_t zero = 0;
+  sfb::StreamArgs a;
+  a.src_base = src;
+  a.src_off = &zero;
+  a.src_len = &src_len;
+  a.dst_base = dst_base;
+  a.dst_delta = 0;
+  a.dst_off = &dst_off;
+  a.dst_cap = &dst_cap;
+  a.status = status;
+  a.written = written;
+  a.list = nullptr;
+  a.idx_base = 0;
+  a.n = 1;
+  a.stream_counter = &counter;
+  a.lens_scratch = lens.data();
+  a.match_bits = match_bits;
+  std::vector<std::thread> lanes;
+  for (unsigned l = 0; l < 32; ++l)
+    lanes.emplace_back([&a, l] {
+      threadIdx.x = l;
+      blockIdx.x = 0;
+      blockDim.x = 32;
+      gridDim.x = 1;
+      sfb::huff_stream_kernel<StreamCfg>(a);
+    });
+  for (auto& t : lanes) t.join();
+  emu_warp = nullptr;
+  emu_stream_smem = nullptr;
+}
+
+extern "C" void emu_lz_resolve(uint8_t* dst_base, const uint64_t* dst_off, const uint64_t* written,
+                               const uint32_t* match_bits, uint64_t n);
+
+// One stream through the single-stream pass 1 (above) and the real pass 2 (emu_lz.cpp), in a
+// private padded copy of dst with canaries.  `dst_phase` (0..127) places the region relative to a
+// 128-byte boundary.  Returns 0, or 1 if anything outside [dst, dst+cap) changed.
+extern "C" int emu_stream_decompress(const uint8_t* src, uint64_t src_len, uint8_t* dst, uint64_t dst_cap,
+                                     uint32_t dst_phase, uint8_t* status, uint64_t* written)
+{
+  constexpr size_t PAD = 512;
+  std::vector<uint8_t> sbuf(src_len + 64, 0xEE);
+  if (src_len) std::memcpy(sbuf.data() + 16, src, src_len);
+  std::vector<uint8_t> dbuf(dst_cap + 2 * PAD + 256, 0xC3);
+  uint8_t* dbase = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dbuf.data()) + PAD) & ~uintptr_t{127});
+  const uint64_t doff = dst_phase & 127u;
+  uint8_t* dp = dbase + doff;
+  if (dst_cap) std::memcpy(dp, dst, dst_cap);
+  std::vector<uint32_t> bits((doff + dst_cap) / 32 + 8, 0u);
+  uint64_t wr = 0;
+  emu_huff_stream(sbuf.data() + 16, src_len, dbase, doff, dst_cap, bits.data(), status, &wr);
+  if (wr > dst_cap) return 2;
+  emu_lz_resolve(dbase, &doff, &wr, bits.data(), 1);
+  *written = wr;
+  for (uint8_t* q = dbuf.data(); q < dp; ++q)
+    if (*q != 0xC3) return 1;
+  for (uint8_t* q = dp + dst_cap; q < dbuf.data() + dbuf.size(); ++q)
+    if (*q != 0xC3) return 1;
+  if (dst_cap) std::memcpy(dst, dp, dst_cap);
+  return 0;
+}

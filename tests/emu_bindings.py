@@ -19,14 +19,14 @@ def build(root_lit=8, root_dist=6, pool=96) -> str:
     out = os.path.join(HERE, "cpu_emu", f"libemu_{root_lit}_{root_dist}_{pool}.so")
     emu = os.path.join(HERE, "cpu_emu")
     csrc = os.path.join(ROOT, "starflate_b200", "csrc")
-    srcs = [os.path.join(emu, "emu.cpp"), os.path.join(emu, "emu_lz.cpp"),
+    srcs = [os.path.join(emu, "emu.cpp"), os.path.join(emu, "emu_lz.cpp"), os.path.join(emu, "emu_stream.cpp"),
             os.path.join(emu, "cuda_shim.h"), os.path.join(emu, "cuda_shim_warp.h"),
             os.path.join(csrc, "deflate_lane.cuh"), os.path.join(csrc, "huff_lanes.cuh"),
-            os.path.join(csrc, "lz_warp.cuh")]
+            os.path.join(csrc, "lz_warp.cuh"), os.path.join(csrc, "huff_stream.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         subprocess.check_call(["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-pthread",
                                f"-DSFB_EMU_ROOT_LIT={root_lit}", f"-DSFB_EMU_ROOT_DIST={root_dist}",
-                               f"-DSFB_EMU_POOL={pool}", "-o", out, srcs[0], srcs[1]])
+                               f"-DSFB_EMU_POOL={pool}", "-o", out, srcs[0], srcs[1], srcs[2]])
     return out
 
 
@@ -48,6 +48,21 @@ class Emu:
                                            int(small_first))
         assert rc == 0, f"emulated kernel wrote outside a dst region (code {rc})"
         return st, wr
+
+    def stream_decompress(self, src: bytes, cap: int, phase: int = 0, fill: int = 0xA5):
+        """One stream through the single-stream pass 1 (huff_stream.cuh, 32 host threads) and the
+        real pass 2. -> (status, dst bytes, written)"""
+        self.lib.emu_stream_decompress.argtypes = [_u8p, C.c_uint64, _u8p, C.c_uint64, C.c_uint32,
+                                                   _u8p, _u64p]
+        s = np.frombuffer(src, dtype=np.uint8) if len(src) else np.zeros(1, np.uint8)
+        d = np.full(max(cap, 1), fill, dtype=np.uint8)
+        st = np.zeros(1, np.uint8)
+        wr = np.zeros(1, np.uint64)
+        p = lambda a, t: a.ctypes.data_as(t)
+        rc = self.lib.emu_stream_decompress(p(s, _u8p), len(src), p(d, _u8p), cap, phase, p(st, _u8p),
+                                            p(wr, _u64p))
+        assert rc == 0, f"emulated stream kernel wrote outside its dst region (code {rc})"
+        return int(st[0]), d[:cap].tobytes(), int(wr[0])
 
     def stats(self):
         out = (C.c_ulonglong * 4)()

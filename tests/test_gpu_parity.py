@@ -174,6 +174,46 @@ def test_crafted_lz_shapes_and_unaligned_dst_base(ctx, oracle):
             assert (got[:shift] == 0xA5).all() and (got[shift + b.dst_total:] == 0xA5).all()
 
 
+@pytest.mark.parametrize("mode", ["1", "0"])
+def test_single_stream_mode_and_batch_mode_agree_with_golden(oracle, golden, monkeypatch, mode):
+    """SFB200_STREAM_MODE=1 forces the speculative one-warp-per-stream pass 1 (huff_stream.cuh) on
+    batches of any size, =0 forces the lane-per-stream pass 1 even on a handful of streams: both
+    must reproduce the reference's answers."""
+    import starflate_b200 as S
+    monkeypatch.setenv("SFB200_STREAM_MODE", mode)
+    c = S.Context(0)
+    try:
+        for name in ("known_answers", "cut7_starfleet_dynamic", "cut1_multiblock_12000", "cap_dynamic_4096",
+                     "crafted_dynamic_headers", "flip_repetitive_70000", "cap_stored_4096", "cut1_fixed_4096"):
+            if name in golden.families:
+                _check_family(c, oracle, golden, name, dst_align=1 if mode == "1" else 8)
+    finally:
+        c.close()
+
+
+def test_large_single_streams(ctx, oracle):
+    """C1-like shapes: a few multi-megabyte multi-block streams (single-stream mode picks them up),
+    every byte against the oracle."""
+    streams, caps, plains = [], [], []
+    for kind, size, seed in (("dynamic", 3 << 20, 1), ("multiblock", 1 << 20, 2), ("repetitive", 4 << 20, 3),
+                             ("dynamic", 1 << 20, 4)):
+        plain, comp = T.make_stream(kind, size, 8800 + seed)
+        streams.append(comp)
+        caps.append(len(plain))
+        plains.append(plain)
+    streams.append(streams[0][: len(streams[0]) // 2])   # truncated in the middle of a block
+    caps.append(caps[0])
+    streams.append(streams[3])                            # destination too small
+    caps.append(caps[3] - 12345)
+    b = T.Batch(streams, caps, dst_align=1)
+    st, wr, dst = gpu_util.run_device(ctx, b)
+    dst_o = b.new_dst()
+    ost, owr, _ = oracle.decompress_batch(b.src, b.src_off, b.src_len, dst_o, b.dst_off, b.dst_cap, 8)
+    assert (st == ost).all() and (wr == owr).all()
+    assert (dst == dst_o).all()
+    assert list(st[:4]) == [0, 0, 0, 0] and st[4] != 0 and st[5] == 4
+
+
 def test_one_bad_stream_does_not_affect_neighbours(ctx, oracle):
     plain, comp = T.make_stream("dynamic", 30000, 1)
     streams = [comp, comp[:100], comp, b"\x07", comp]

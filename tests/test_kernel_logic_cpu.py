@@ -126,3 +126,28 @@ def test_crafted_lz_shapes_on_warp_emulation(emu, oracle):
     assert (ost == 0).all() and (owr == b.dst_cap).all()
     assert (st == ost).all() and (wr == owr).all()
     assert (dst_e == dst_o).all()
+
+
+def test_single_stream_speculative_pass1(emu, oracle, golden):
+    """huff_stream.cuh — 32 lanes decode 32 spans of one block speculatively, starts corrected until
+    they agree, then emit at prefix-summed positions — on 32 host threads, followed by the real
+    pass 2: golden families (truncations, short destinations, crafted headers, bit flips) and
+    multi-window streams, at several dst phases."""
+    k = 0
+    for name, stride in (("known_answers", 1), ("crafted_dynamic_headers", 1), ("cut7_starfleet_dynamic", 331),
+                         ("cut1_multiblock_12000", 997), ("cap_dynamic_4096", 331), ("cap_stored_4096", 331),
+                         ("flip_dynamic_4096", 499), ("cap_repetitive_70000", 4999), ("cut7_starfleet_fixed", 499)):
+        if name not in golden.families:
+            continue
+        for i, src, cap in golden.cases(name, stride):
+            want_st, want_wr, want_hash, cls = golden.expected(name, i)
+            st, dst, wr = emu.stream_decompress(src, cap, phase=(7 * k) % 128)
+            k += 1
+            assert (st, wr) == (want_st, want_wr), (name, i, cls)
+            assert "%016x" % oracle.fnv1a64(dst) == want_hash, (name, i, cls)
+    for kind, size, seed in (("dynamic", 40000, 1), ("multiblock", 24000, 2), ("repetitive", 50000, 3)):
+        plain, comp = T.make_stream(kind, size, 7000 + seed)
+        for cap in (len(plain) - 1000,) if seed != 1 else (len(plain), len(plain) - 1000):
+            st, dst, wr = emu.stream_decompress(comp, cap, phase=seed * 31)
+            ost, odst, owr, _ = oracle.decompress(comp, cap)
+            assert (st, wr) == (ost, owr) and dst == odst, (kind, cap)
