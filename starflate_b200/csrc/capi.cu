@@ -5,6 +5,7 @@
 #include "huff_lanes.cuh"
 #include "huff_stream.cuh"
 #include "lz_warp.cuh"
+#include "lz_jump.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -60,6 +61,8 @@ struct sfb200_ctx {
   uint32_t* d_lens = nullptr;  // per-resident-lane code-length scratch
   uint32_t* d_bits = nullptr;  // match-head bitmap: 1 bit per dst byte (grown on demand)
   uint64_t d_bits_words = 0;
+  uint8_t* d_jump = nullptr;  // single-stream pass 2 (lz_jump.cuh): pointers, tile flags, round flags
+  uint64_t d_jump_cap = 0;
   uint64_t* d_written = nullptr;  // pass-1 -> pass-2 sizes when the caller passes written == NULL
   uint64_t d_written_n = 0;
   uint64_t launches = 0;
@@ -219,6 +222,7 @@ void sfb200_destroy(sfb200_ctx* ctx)
   cudaFree(ctx->d_lens);
   cudaFree(ctx->d_bits);
   cudaFree(ctx->d_written);
+  cudaFree(ctx->d_jump);
   cudaFree(ctx->d_defer);
   cudaFree(ctx->d_order);
   cudaFree(ctx->d_src);
@@ -298,6 +302,16 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
                      n * 32 <= static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->ctas_per_sm) *
                                    LaneCfg::WARPS * 32;
   if (const char* e = std::getenv("SFB200_STREAM_MODE")) stream_mode = e[0] == '1' && ctx->stream_ctas_per_sm > 0;
+  // One stream: pass 2 works on the whole output at once (lz_jump.cuh) instead of one warp walking it
+  bool jump = n == 1 && stream_mode;
+  if (const char* e = std::getenv("SFB200_JUMP")) jump = jump && e[0] != '0';
+  uint64_t jump_tiles = 0;
+  if (jump) {
+    jump_tiles = (dst_bytes + delta + 128 + sfb::JUMP_TILE - 1) / sfb::JUMP_TILE + 1;
+    const uint64_t need = jump_tiles * sfb::JUMP_TILE * 4 + jump_tiles * 4 + (sfb::JUMP_MAX_ROUNDS + 1) * 4;
+    const int rc = grow(ctx, &ctx->d_jump, &ctx->d_jump_cap, need);
+    if (rc != SFB200_RC_OK) return rc;
+  }
   // Geometry.  Measured on C2 (profiles/r01_small_geometry_c2.md): with 16 warps per SM the small
   // geometry makes pass 1 issue-bound (63 % of issue slots, 11.1 ms against 12.1 ms for the
   // large one), and the few percent of streams it hands on cost a whole extra stream latency
@@ -480,7 +494,31 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
     r.idx_base = first;
     r.todo_list = order;
     r.stream_counter = ctr + 2;
-    {
+    if (jump) {
+      sfb::JumpArgs j;
+      j.dst_base = dst_base;
+      j.dst_delta = delta;
+      j.dst_off = dst_off;
+      j.written = written;
+      j.match_bits = ctx->d_bits;
+      j.idx = 0;
+      j.ptr = reinterpret_cast<uint32_t*>(ctx->d_jump);
+      j.tile_done = j.ptr + jump_tiles * sfb::JUMP_TILE;
+      j.todo = j.tile_done + jump_tiles;
+      SFB_TRY(ctx, cudaMemsetAsync(j.tile_done, 0, (jump_tiles + sfb::JUMP_MAX_ROUNDS + 1) * 4, s2));
+      constexpr uint64_t wpc = sfb::JUMP_THREADS / 32;
+      const uint64_t want = (jump_tiles + wpc - 1) / wpc;
+      const uint64_t resident = static_cast<uint64_t>(ctx->sm_count) * 8;
+      const unsigned grid = static_cast<unsigned>(want < resident ? want : resident);
+      j.round = 0;
+      sfb::lz_jump_init_kernel<<<grid, sfb::JUMP_THREADS, 0, s2>>>(j);
+      for (int r = 1; r <= sfb::JUMP_MAX_ROUNDS; ++r) {
+        j.round = static_cast<uint32_t>(r);
+        sfb::lz_jump_round_kernel<<<grid, sfb::JUMP_THREADS, 0, s2>>>(j);
+      }
+      SFB_TRY(ctx, cudaGetLastError());
+      ctx->launches += sfb::JUMP_MAX_ROUNDS;
+    } else {
       constexpr uint64_t wpc = sfb::LZ_THREADS / 32;
       const uint64_t want = (cnt + wpc - 1) / wpc;
       const uint64_t resident =

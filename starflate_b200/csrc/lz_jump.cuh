@@ -1,0 +1,214 @@
+// Pass 2 for ONE LARGE stream on sm_100a: LZ77 back-references resolved by POINTER JUMPING over
+// the whole output at once (the "two-pass LZ77 resolve" of BASELINE.json's single-stream mode).
+//
+// lz_warp.cuh gives a stream to one warp, which walks it front to back: right for a batch,
+// hopeless for a 1 GB stream.  Here every output byte gets a 32-bit pointer to the byte it is a
+// copy of:
+//   * a literal (or stored) byte points at itself — it is a ROOT and already holds its value;
+//   * byte k of a match (start s, distance d) points at  s - d + (k mod d)  — exactly the byte
+//     the reference's copy_from_before (src/decompress.cpp:388-398) would have read, because
+//     its forward-overlapping copy is periodic with period d.
+// Pointers always point backwards, so following them ends at a root after finitely many hops.
+// A round replaces every pointer by its target's pointer (ptr[i] <- ptr[ptr[i]]), halving the
+// number of hops: after r rounds every chain of at most 2^r hops is resolved, whatever the data
+// (a 1 GiB run of one byte is a chain of 2^30 hops: 30 rounds).  Concurrent updates are benign:
+// whatever a thread reads through ptr[p], old or new, is an ancestor of i.
+//
+// The output is cut into tiles of JUMP_TILE bytes, one warp per tile and round.  A tile in which a
+// round changed nothing has only roots as targets; roots never change, so the tile is FINAL: the
+// warp gathers its bytes (dst[i] <- dst[ptr[i]]; only roots are read and no root is rewritten
+// with a different value) and marks it done.  Text-like data is final after 4-6 rounds; each later
+// round only re-visits the tiles that are not.  The host enqueues JUMP_MAX_ROUNDS launches; a
+// launch whose predecessor left nothing to do exits at once (no host round trip).
+//
+// Positions are 32-bit offsets in the 128-byte aligned view of the stream (as in lz_warp.cuh):
+// the batch precondition (sizes < 0xffffff00) makes them fit.
+#pragma once
+
+#include "lz_warp.cuh"
+
+namespace sfb {
+
+constexpr uint32_t JUMP_TILE = 1024;      // bytes of output per warp and round
+constexpr int JUMP_MAX_ROUNDS = 32;       // 2^32 hops: more than a 32-bit position can chain
+constexpr int JUMP_THREADS = 256;
+
+struct JumpArgs {
+  uint8_t* dst_base;  // 128-byte aligned
+  uint64_t dst_delta;
+  const uint64_t* dst_off;
+  const uint64_t* written;
+  const uint32_t* match_bits;
+  uint64_t idx;         // the stream
+  uint32_t* ptr;        // one per byte of the view [0, q + written) rounded up to a tile
+  uint32_t* tile_done;  // one per tile, zeroed before the first round
+  uint32_t* todo;       // [JUMP_MAX_ROUNDS + 1] zeroed; todo[r] != 0: round r left tiles open
+  uint32_t round;       // 0 = set up the pointers, then 1 .. JUMP_MAX_ROUNDS
+};
+
+// Round 0: the pointers.  A warp takes a tile, finds the match that reaches into it from the
+// left (the last match head in the 258 bytes before the tile, if its length carries it that far)
+// and then walks the tile's chunks the way lz_resolve_kernel does.
+__global__ void __launch_bounds__(JUMP_THREADS) lz_jump_init_kernel(const JumpArgs a)
+{
+  constexpr unsigned FULL = 0xffffffffu;
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const int next_lane = static_cast<int>((lane + 1u) & 31u);
+  const uint32_t bit_sh = 4u * (lane & 7u);
+  const uint64_t off = a.dst_off[a.idx] + a.dst_delta;
+  const uint64_t wr = a.written[a.idx];
+  if (wr == 0) return;
+  uint8_t* const base = a.dst_base + (off & ~127ull);
+  const uint32_t q = static_cast<uint32_t>(off & 127u);
+  const uint32_t end = q + static_cast<uint32_t>(wr);
+  const uint32_t* const pw = reinterpret_cast<const uint32_t*>(base) + lane;
+  const uint32_t* const bm = a.match_bits + ((off & ~127ull) >> 5);
+  const uint32_t n_tiles = (end + JUMP_TILE - 1u) / JUMP_TILE;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < n_tiles; tile += warps) {
+    const uint32_t T = tile * JUMP_TILE;
+    // ---- the match carried in: last head in [T - 288, T), nine bitmap words, lanes 0..8 -----------
+    uint32_t c_o = 0, c_end = 0, c_d = 1;
+    if (T > q) {
+      const uint32_t w_hi = T >> 5;  // first word of the tile
+      uint32_t best = 0;             // (bit index + 1) of my word's top head, 0: none
+      if (lane < 9u && w_hi > lane) {
+        const uint32_t wi = w_hi - 1u - lane;
+        uint32_t w = bm[wi];
+        if (32u * wi < q) w &= q >= 32u * wi + 32u ? 0u : ~((1u << (q - 32u * wi)) - 1u);
+        if (w) best = 32u * wi + (31u - static_cast<uint32_t>(__clz(static_cast<int>(w)))) + 1u;
+      }
+      best = __reduce_max_sync(FULL, best);
+      if (best) {
+        const uint32_t h = best - 1u;
+        const uint32_t d = static_cast<uint32_t>(base[h]) | (static_cast<uint32_t>(base[h + 1u]) << 8) |
+                           (static_cast<uint32_t>(base[h + 2u]) << 16);
+        c_o = h;
+        c_end = h + (d & 255u) + 3u;
+        c_d = (d >> 8) + 1u;
+      }
+    }
+    auto load_w = [&](uint32_t P) -> uint32_t {
+      const uint32_t wp = P + 4u * lane;
+      return (wp + 4u > q && wp < end) ? pw[P >> 2] : 0u;
+    };
+    const uint32_t t_stop = T + JUMP_TILE < end ? T + JUMP_TILE : end;
+    uint32_t cw = load_w(T);
+    for (uint32_t P = T; P < t_stop; P += 128u) {
+      const uint32_t ncw = load_w(P + 128u);
+      const uint32_t mw = bm[(P >> 5) + (lane >> 3)];
+      const uint32_t wp = P + 4u * lane;
+      uint32_t vm = 15u;
+      if (!(P >= q && P + 128u <= end)) {
+        const uint32_t lo = q > wp ? (q - wp < 4u ? q - wp : 4u) : 0u;
+        const uint32_t hi = end > wp ? (end - wp < 4u ? end - wp : 4u) : 0u;
+        vm = hi > lo ? ((1u << hi) - 1u) & ~((1u << lo) - 1u) : 0u;
+      }
+      const uint32_t hb4 = (mw >> bit_sh) & vm;
+      const uint32_t t = __shfl_sync(FULL, cw, next_lane);
+      const uint32_t u = __shfl_sync(FULL, ncw, 0);
+      const uint32_t nx = lane == 31u ? u : t;
+      const uint32_t hl = 31u - static_cast<uint32_t>(__clz(static_cast<int>(hb4 | 1u)));
+      const uint32_t own_pack = (4u * lane + hl) | ((lz_funnel(cw, nx, 8u * hl) & 0xffffffu) << 7);
+      const uint32_t hm = __ballot_sync(FULL, hb4 != 0);
+      const uint32_t below = hm & lt_mask;
+      const uint32_t sl = 31u - static_cast<uint32_t>(__clz(static_cast<int>(below | 1u)));
+      const uint32_t in_pack = __shfl_sync(FULL, own_pack, static_cast<int>(sl));
+      uint32_t t_o = c_o, t_end = c_end, t_d = c_d;
+      if (below) {
+        t_o = P + (in_pack & 127u);
+        t_end = t_o + ((in_pack >> 7) & 255u) + 3u;
+        t_d = (in_pack >> 15) + 1u;
+      }
+      if (hm) {
+        const uint32_t top = 31u - static_cast<uint32_t>(__clz(static_cast<int>(hm)));
+        const uint32_t pk = __shfl_sync(FULL, own_pack, static_cast<int>(top));
+        c_o = P + (pk & 127u);
+        c_end = c_o + ((pk >> 7) & 255u) + 3u;
+        c_d = (pk >> 15) + 1u;
+      }
+      uint32_t src[4];
+#pragma unroll
+      for (uint32_t b = 0; b < 4; ++b) {
+        const uint32_t p = wp + b;
+        if ((hb4 >> b) & 1u) {
+          const uint32_t d = lz_funnel(cw, nx, 8u * b) & 0xffffffu;
+          t_o = p;
+          t_end = p + (d & 255u) + 3u;
+          t_d = (d >> 8) + 1u;
+        }
+        const bool cov = ((vm >> b) & 1u) && p < t_end;
+        uint32_t k = p - t_o;
+        if (cov && k >= t_d) k = lz_mod_small(k, t_d);  // (k < 258)
+        src[b] = cov ? t_o - t_d + k : p;
+      }
+      *reinterpret_cast<uint4*>(a.ptr + wp) = make_uint4(src[0], src[1], src[2], src[3]);
+      cw = ncw;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.todo[0] = 1u;
+}
+
+// Rounds 1 .. JUMP_MAX_ROUNDS.
+__global__ void __launch_bounds__(JUMP_THREADS) lz_jump_round_kernel(const JumpArgs a)
+{
+  constexpr unsigned FULL = 0xffffffffu;
+  if (a.todo[a.round - 1u] == 0u) return;  // everything was final before this round
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t off = a.dst_off[a.idx] + a.dst_delta;
+  const uint64_t wr = a.written[a.idx];
+  if (wr == 0) return;
+  uint8_t* const base = a.dst_base + (off & ~127ull);
+  const uint32_t q = static_cast<uint32_t>(off & 127u);
+  const uint32_t end = q + static_cast<uint32_t>(wr);
+  const uint32_t n_tiles = (end + JUMP_TILE - 1u) / JUMP_TILE;
+  const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+  bool open = false;
+  for (uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < n_tiles; tile += warps) {
+    if (a.tile_done[tile]) continue;  // (warp-uniform)
+    const uint32_t T = tile * JUMP_TILE;
+    bool ch = false;
+    uint4 pv[JUMP_TILE / 128];
+#pragma unroll
+    for (uint32_t j = 0; j < JUMP_TILE / 128u; ++j) {
+      const uint32_t wp = T + 128u * j + 4u * lane;
+      uint4 p = make_uint4(wp, wp + 1u, wp + 2u, wp + 3u);
+      if (wp < end) p = *reinterpret_cast<const uint4*>(a.ptr + wp);
+      uint4 g;
+      g.x = a.ptr[p.x];
+      g.y = a.ptr[p.y];
+      g.z = a.ptr[p.z];
+      g.w = a.ptr[p.w];
+      if (wp < end && ((g.x != p.x) | (g.y != p.y) | (g.z != p.z) | (g.w != p.w))) {
+        *reinterpret_cast<uint4*>(a.ptr + wp) = g;
+        ch = true;
+      }
+      pv[j] = p;
+    }
+    if (__any_sync(FULL, ch)) {
+      open = true;
+      continue;
+    }
+    // final: every target is a root
+#pragma unroll
+    for (uint32_t j = 0; j < JUMP_TILE / 128u; ++j) {
+      const uint32_t wp = T + 128u * j + 4u * lane;
+      if (wp >= end || wp + 4u <= q) continue;
+      const uint4 p = pv[j];
+      const uint32_t v = static_cast<uint32_t>(base[p.x]) | (static_cast<uint32_t>(base[p.y]) << 8) |
+                         (static_cast<uint32_t>(base[p.z]) << 16) | (static_cast<uint32_t>(base[p.w]) << 24);
+      if (wp >= q && wp + 4u <= end) {
+        *reinterpret_cast<uint32_t*>(base + wp) = v;
+      } else {  // first / last word of the stream: only our bytes
+#pragma unroll
+        for (uint32_t b = 0; b < 4; ++b)
+          if (wp + b >= q && wp + b < end) base[wp + b] = static_cast<uint8_t>(v >> (8u * b));
+      }
+    }
+    if (lane == 0) a.tile_done[tile] = 1u;
+  }
+  if (__any_sync(FULL, open) && lane == 0) a.todo[a.round] = 1u;
+}
+
+}  // namespace sfb
