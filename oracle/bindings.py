@@ -76,6 +76,19 @@ class Oracle:
         self.lib.sfo_decompress(_ptr(s, _u8p), len(src), _ptr(d, _u8p), dst_cap, C.byref(r))
         return r.status, d[:dst_cap].tobytes(), r.written, r.ref_undefined
 
+    def block_starts(self, src: bytes, dst_cap: int, max_starts: int = 1 << 16):
+        """Bit positions of the block headers the front-to-back decode reads."""
+        self.lib.sfo_block_starts.argtypes = [_u8p, C.c_size_t, _u8p, C.c_size_t, C.POINTER(_Result), _u64p,
+                                              C.c_size_t]
+        self.lib.sfo_block_starts.restype = C.c_size_t
+        s = np.frombuffer(src, dtype=np.uint8) if len(src) else np.zeros(1, np.uint8)
+        d = np.zeros(max(dst_cap, 1), np.uint8)
+        r = _Result()
+        out = np.zeros(max_starts, np.uint64)
+        k = self.lib.sfo_block_starts(_ptr(s, _u8p), len(src), _ptr(d, _u8p), dst_cap, C.byref(r),
+                                      _ptr(out, _u64p), max_starts)
+        return [int(x) for x in out[:k]]
+
     def fnv1a64(self, data) -> int:
         a = np.frombuffer(data, dtype=np.uint8) if len(data) else np.zeros(1, np.uint8)
         return int(self.lib.sfo_fnv1a64(_ptr(a, _u8p), len(data)))

@@ -301,8 +301,9 @@ static void fixed_tables(ctable_t* lit, ctable_t* dist)
   ctable_build(dist, lens, 32);
 }
 
-void sfo_decompress(const uint8_t* src, size_t src_len, uint8_t* dst,
-                    size_t dst_cap, sfo_result* res)
+static void decompress_impl(const uint8_t* src, size_t src_len, uint8_t* dst,
+                            size_t dst_cap, sfo_result* res, uint64_t* starts,
+                            size_t max_starts, size_t* n_starts)
 {
   bits_t b = {src, 0, (uint64_t)src_len * 8};
   uint64_t written = 0;
@@ -311,6 +312,7 @@ void sfo_decompress(const uint8_t* src, size_t src_len, uint8_t* dst,
   ctable_t lit, dist;
   for (int was_final = 0; !was_final;) {
     int type = 0;
+    if (starts && *n_starts < max_starts) starts[(*n_starts)++] = b.pos;
     status = read_header(&b, &was_final, &type);
     if (status != SFO_SUCCESS) break;
     if (type == 0) { /* stored: src/decompress.cpp:416-436 */
@@ -354,6 +356,21 @@ void sfo_decompress(const uint8_t* src, size_t src_len, uint8_t* dst,
   res->ref_undefined = (uint8_t)ub;
   res->written = written;
   res->bits_consumed = b.pos;
+}
+
+void sfo_decompress(const uint8_t* src, size_t src_len, uint8_t* dst,
+                    size_t dst_cap, sfo_result* res)
+{
+  decompress_impl(src, src_len, dst, dst_cap, res, NULL, 0, NULL);
+}
+
+size_t sfo_block_starts(const uint8_t* src, size_t src_len, uint8_t* dst,
+                        size_t dst_cap, sfo_result* res, uint64_t* starts,
+                        size_t max_starts)
+{
+  size_t n = 0;
+  decompress_impl(src, src_len, dst, dst_cap, res, starts, max_starts, &n);
+  return n;
 }
 
 size_t sfo_canonical_codes(const uint8_t* lens, size_t n, uint64_t* codes,

@@ -36,6 +36,12 @@ typedef struct sfo_result {
 void sfo_decompress(const uint8_t* src, size_t src_len, uint8_t* dst,
                     size_t dst_cap, sfo_result* res);
 
+/* The same, also reporting the bit position of every block header it read (test aid for the
+ * single-stream path, which decodes the blocks of one stream side by side). Returns their number. */
+size_t sfo_block_starts(const uint8_t* src, size_t src_len, uint8_t* dst,
+                        size_t dst_cap, sfo_result* res, uint64_t* starts,
+                        size_t max_starts);
+
 /* Batched driver: stream i = src[src_off[i] .. +src_len[i]) into
  * dst[dst_off[i] .. +dst_cap[i]); `threads` worker threads, static contiguous
  * partition. ub may be NULL. */

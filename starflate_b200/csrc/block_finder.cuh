@@ -1,0 +1,310 @@
+// Block finder and block chain for ONE LARGE stream on sm_100a (BASELINE.json's single-stream
+// mode): lets the blocks of a stream be decoded side by side although a block's start is only
+// KNOWN once the block before it has been decoded.
+//
+// DEFLATE has no block index, but a dynamic-Huffman block header (RFC 1951 §3.2.7, parsed by the
+// reference in src/decompress.cpp:314-367) is highly redundant.  Every bit position of the input
+// is tested, cheapest test first:
+//   find_candidates_kernel  BTYPE == 2, HLIT <= 29, HDIST <= 29 (17 bits, 22 % pass), then the
+//                           3-bit code-length-code lengths must form a COMPLETE prefix code
+//                           (Kraft sum exactly 1; about 1 in 150 of the rest);
+//   verify_candidates_kernel decodes the HLIT + HDIST code lengths with that code: no repeat
+//                           without a previous length, no run past the end, the literal/length
+//                           code complete and with an end-of-block symbol, the distance code
+//                           complete (or at most one code).  Random bits practically never pass.
+// What passes becomes a JOB: a warp decodes the block that starts there, counting only
+// (huff_stream.cuh, mode 1), and records where it ends and what it would produce.
+//
+// THE FINDER IS ONLY A HINT; what is decoded is decided by the chain.  chain_kernel starts at bit 0
+// (job 0, always there), and follows "this block ends at bit e" -> "the job that starts at bit
+// e".  A job is used only if the block before it ends exactly at its start, i.e. only if a
+// front-to-back decoder would have begun a block there too; its result then does not depend on
+// how its start was found.  Where the chain cannot go on — the next block is a stored or fixed
+// one (nothing to find), its header is one the finder is too strict for (zlib never writes one:
+// incomplete or over-subscribed codes, which the reference accepts), the block is the last, or it
+// fails — the job reached last becomes the TAIL: in the writing pass (mode 2) it decodes its
+// block and then simply carries on, block after block, to the end of the stream, like the plain
+// one-warp kernel.  So every input gives exactly the bytes, status and count of the front-to-back
+// decode; the finder only decides how much of it runs in parallel.
+#pragma once
+
+#include <cstdint>
+#ifndef SFB_CPU_EMU
+#include <cuda_runtime.h>
+#endif
+
+namespace sfb {
+
+constexpr uint64_t JOB_NONE = ~0ull;
+constexpr uint32_t JOB_ENDS = 1u;  // the stream ends in (or right after) this block, or it failed
+
+struct BlockJob {
+  uint64_t start_bit;  // where the block's header starts
+  uint64_t end_bit;    // mode 1: where the next header starts
+  uint64_t out;        // mode 1: bytes the block produces
+  uint64_t base;       // chain: the block's output position, JOB_NONE: not on the chain
+  uint32_t need;       // mode 1: the smallest base at which all its distances are in range
+  uint32_t flags;      // mode 1: JOB_ENDS
+  uint32_t next;       // mode 1: the job that starts at end_bit (0: none)
+  uint32_t pad;
+};
+
+struct FindArgs {
+  const uint8_t* src_base;
+  const uint64_t* src_off;
+  const uint64_t* src_len;
+  uint64_t idx;          // the stream
+  uint64_t* cand;        // bit positions that passed the quick tests
+  uint32_t* cand_count;  // zeroed
+  uint32_t cand_cap;
+  BlockJob* jobs;
+  uint32_t* job_count;   // set to 1 (job 0 = bit 0) by find_candidates_kernel
+  uint32_t job_cap;
+  uint32_t* job_tab;     // zeroed; open-addressing hash table start_bit -> job (see job_find)
+  uint32_t tab_mask;     // its size - 1 (a power of two, at least twice job_cap)
+  uint32_t* tail_job;    // chain: the job that runs to the end of the stream
+  const uint64_t* dst_cap;
+};
+
+// start_bit -> job: linear probing, a slot holds a job index (0: empty), the key is the job's
+// start_bit.  Two jobs with the same start are the same block twice: whichever is found will do.
+__device__ __forceinline__ uint32_t job_slot(uint64_t p, uint32_t mask)
+{
+  return static_cast<uint32_t>((p * 0x9E3779B97F4A7C15ull) >> 40) & mask;
+}
+__device__ __forceinline__ uint32_t job_find(const uint32_t* tab, uint32_t mask, const BlockJob* jobs,
+                                             uint32_t n_jobs, uint64_t p)
+{
+  uint32_t s = job_slot(p, mask);
+  for (uint32_t tries = 0; tries <= mask; ++tries) {
+    const uint32_t k = tab[s];
+    if (k == 0u) return 0u;
+    if (k < n_jobs && jobs[k].start_bit == p) return k;
+    s = (s + 1u) & mask;
+  }
+  return 0u;
+}
+
+// Follow the blocks from bit 0 (see the head of this file).  One thread: a step is one 48-byte
+// record, the links were looked up by the counting jobs.
+__global__ void chain_kernel(const FindArgs a)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const uint64_t cap = a.dst_cap[a.idx];
+  uint32_t n_jobs = *a.job_count;
+  if (n_jobs > a.job_cap) n_jobs = a.job_cap;
+  uint32_t j = 0;
+  uint64_t base = 0;
+  for (;;) {
+    const BlockJob jb = a.jobs[j];
+    a.jobs[j].base = base;
+    if ((jb.flags & JOB_ENDS) || jb.need > base || base + jb.out > cap || jb.next == 0u || jb.next >= n_jobs) break;
+    base += jb.out;
+    j = jb.next;
+  }
+  *a.tail_job = j;
+}
+
+#ifndef SFB_CPU_EMU
+
+constexpr int FIND_THREADS = 256;
+
+// 32-bit word i of the 4-byte aligned view of the stream, zero outside [src, src + slen)
+__device__ __forceinline__ uint32_t find_word(const uint8_t* src, uint64_t slen, uint32_t sh, uint64_t i)
+{
+  const int64_t b0 = static_cast<int64_t>(4ull * i) - static_cast<int64_t>(sh);  // stream offset of its first byte
+  if (b0 >= 0 && static_cast<uint64_t>(b0) + 4u <= slen) return *reinterpret_cast<const uint32_t*>(src + b0);
+  uint32_t w = 0;
+  for (int k = 0; k < 4; ++k) {
+    const int64_t b = b0 + k;
+    if (b >= 0 && static_cast<uint64_t>(b) < slen) w |= static_cast<uint32_t>(src[b]) << (8 * k);
+  }
+  return w;
+}
+
+__global__ void __launch_bounds__(FIND_THREADS) find_candidates_kernel(const FindArgs a)
+{
+  const uint8_t* const src = a.src_base + a.src_off[a.idx];
+  const uint64_t slen = a.src_len[a.idx];
+  const uint64_t gtid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gtid == 0) {
+    BlockJob j0;
+    j0.start_bit = 0;
+    j0.end_bit = 0;
+    j0.out = 0;
+    j0.base = JOB_NONE;
+    j0.need = 0;
+    j0.flags = JOB_ENDS;
+    j0.next = 0;
+    j0.pad = 0;
+    a.jobs[0] = j0;
+    *a.job_count = 1u;
+  }
+  if (slen >= 0xffffff00ull) return;
+  const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 3u);
+  const uint64_t total_bits = 8ull * slen;
+  const uint64_t n_words = (slen + sh + 3u) / 4u;
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t i = gtid; i < n_words; i += stride) {
+    const uint32_t w0 = find_word(src, slen, sh, i), w1 = find_word(src, slen, sh, i + 1);
+    // quick tests on the 32 positions that start in w0
+    uint32_t pass = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < 32; ++j) {
+      const uint32_t x = __funnelshift_r(w0, w1, j);
+      const bool ok = ((x >> 1) & 3u) == 2u && ((x >> 3) & 31u) <= 29u && ((x >> 8) & 31u) <= 29u;
+      pass |= static_cast<uint32_t>(ok) << j;
+    }
+    if (pass == 0) continue;
+    const uint32_t w2 = find_word(src, slen, sh, i + 2), w3 = find_word(src, slen, sh, i + 3);
+    const uint64_t lo64 = (static_cast<uint64_t>(w1) << 32) | w0, hi64 = (static_cast<uint64_t>(w3) << 32) | w2;
+    while (pass) {
+      const uint32_t j = static_cast<uint32_t>(__ffs(static_cast<int>(pass)) - 1);
+      pass &= pass - 1u;
+      const int64_t p = static_cast<int64_t>(32ull * i + j) - 8 * static_cast<int64_t>(sh);
+      if (p <= 0) continue;  // (bit 0 is job 0 anyway)
+      const uint32_t hclen = (__funnelshift_r(w0, w1, j) >> 13) & 15u;
+      const uint32_t ncl = hclen + 4u;
+      if (static_cast<uint64_t>(p) + 17u + 3u * ncl > total_bits) continue;
+      const uint32_t s = j + 17u;  // 17 .. 48
+      uint64_t v = (lo64 >> s) | (hi64 << (64u - s));
+      uint32_t kraft = 0, used = 0;
+#pragma unroll
+      for (uint32_t c = 0; c < 19; ++c) {
+        const uint32_t len = c < ncl ? static_cast<uint32_t>(v) & 7u : 0u;
+        kraft += len ? 128u >> len : 0u;
+        used += len != 0u;
+        v >>= 3;
+      }
+      if (kraft != 128u || used < 2u) continue;
+      const uint32_t at = atomicAdd(a.cand_count, 1u);
+      if (at < a.cand_cap) a.cand[at] = static_cast<uint64_t>(p);
+    }
+  }
+}
+
+// n <= 16 bits at bit position p (zero past the end)
+__device__ __forceinline__ uint32_t find_bits(const uint8_t* src, uint64_t slen, uint64_t p, uint32_t n)
+{
+  const uint64_t b = p >> 3;
+  uint32_t w = 0;
+  for (uint32_t k = 0; k < 3; ++k)
+    if (b + k < slen) w |= static_cast<uint32_t>(src[b + k]) << (8u * k);
+  return (w >> (p & 7u)) & ((1u << n) - 1u);
+}
+
+__global__ void __launch_bounds__(FIND_THREADS) verify_candidates_kernel(const FindArgs a)
+{
+  const uint8_t* const src = a.src_base + a.src_off[a.idx];
+  const uint64_t slen = a.src_len[a.idx];
+  const uint64_t total_bits = 8ull * slen;
+  uint32_t n_cand = *a.cand_count;
+  if (n_cand > a.cand_cap) n_cand = a.cand_cap;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x; ci < n_cand; ci += stride) {
+    const uint64_t p0 = a.cand[ci];
+    uint64_t p = p0 + 3u;
+    const uint32_t n_lit = find_bits(src, slen, p, 5) + 257u;
+    const uint32_t n_dist = find_bits(src, slen, p + 5u, 5) + 1u;
+    const uint32_t ncl = find_bits(src, slen, p + 10u, 4) + 4u;
+    p += 14u;
+    // the code-length code, canonical (RFC 1951 §3.2.2): per length the count and the symbols in order
+    const uint32_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    uint32_t cl[19];
+#pragma unroll
+    for (uint32_t c = 0; c < 19; ++c) cl[c] = 0;
+    for (uint32_t c = 0; c < ncl; ++c) cl[order[c]] = find_bits(src, slen, p + 3u * c, 3);
+    p += 3u * ncl;
+    uint32_t count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint32_t c = 0; c < 19; ++c) ++count[cl[c]];
+    uint32_t offs[8];
+    offs[1] = 0;
+    for (uint32_t l = 1; l < 7; ++l) offs[l + 1] = offs[l] + count[l];
+    uint32_t sorted[19];
+    for (uint32_t c = 0; c < 19; ++c)
+      if (cl[c]) sorted[offs[cl[c]]++] = c;
+    // the HLIT + HDIST lengths
+    const uint32_t total = n_lit + n_dist;
+    uint32_t i = 0, prev = 0, kraft_lit = 0, kraft_dist = 0, dist_codes = 0, eob_len = 0;
+    bool ok = true;
+    while (ok && i < total) {
+      // one code-length symbol, bit by bit
+      uint32_t code = 0, first = 0, index = 0, sym = 99, len = 1;
+      const uint32_t bits = find_bits(src, slen, p, 7);
+      for (; len <= 7; ++len) {
+        code |= (bits >> (len - 1u)) & 1u;
+        const uint32_t cnt = count[len];
+        if (code < first + cnt) {
+          sym = sorted[index + (code - first)];
+          break;
+        }
+        index += cnt;
+        first = (first + cnt) << 1;
+        code <<= 1;
+      }
+      if (sym > 18u) {
+        ok = false;
+        break;
+      }
+      p += len;
+      uint32_t rep = 1, val = sym;
+      if (sym == 16u) {
+        if (i == 0) {
+          ok = false;
+          break;
+        }
+        rep = 3u + find_bits(src, slen, p, 2);
+        p += 2u;
+        val = prev;
+      } else if (sym == 17u) {
+        rep = 3u + find_bits(src, slen, p, 3);
+        p += 3u;
+        val = 0;
+      } else if (sym == 18u) {
+        rep = 11u + find_bits(src, slen, p, 7);
+        p += 7u;
+        val = 0;
+      }
+      if (i + rep > total) {
+        ok = false;
+        break;
+      }
+      if (val) {
+        for (uint32_t r = 0; r < rep; ++r) {
+          const uint32_t at = i + r;
+          if (at < n_lit) {
+            kraft_lit += 32768u >> val;
+            if (at == 256u) eob_len = val;
+          } else {
+            kraft_dist += 32768u >> val;
+            ++dist_codes;
+          }
+        }
+      }
+      prev = val;
+      i += rep;
+    }
+    if (!ok || p > total_bits) continue;
+    if (kraft_lit != 32768u || eob_len == 0u) continue;
+    if (!(kraft_dist == 32768u || dist_codes <= 1u)) continue;
+    const uint32_t j = atomicAdd(a.job_count, 1u);
+    if (j >= a.job_cap) continue;
+    BlockJob jb;
+    jb.start_bit = p0;
+    jb.end_bit = p0;
+    jb.out = 0;
+    jb.base = JOB_NONE;
+    jb.need = 0;
+    jb.flags = JOB_ENDS;
+    jb.next = 0;
+    jb.pad = 0;
+    a.jobs[j] = jb;
+    __threadfence();  // the record before the table entry
+    uint32_t slot = job_slot(p0, a.tab_mask);
+    while (atomicCAS(a.job_tab + slot, 0u, j) != 0u) slot = (slot + 1u) & a.tab_mask;
+  }
+}
+
+#endif  // SFB_CPU_EMU
+
+}  // namespace sfb

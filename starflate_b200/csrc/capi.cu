@@ -61,6 +61,8 @@ struct sfb200_ctx {
   uint32_t* d_lens = nullptr;  // per-resident-lane code-length scratch
   uint32_t* d_bits = nullptr;  // match-head bitmap: 1 bit per dst byte (grown on demand)
   uint64_t d_bits_words = 0;
+  uint8_t* d_find = nullptr;  // single-stream pass 1 (block_finder.cuh): counters, hash table, jobs, candidates
+  uint64_t d_find_cap = 0;
   uint8_t* d_jump = nullptr;  // single-stream pass 2 (lz_jump.cuh): pointers, tile flags, round flags
   uint64_t d_jump_cap = 0;
   uint64_t* d_written = nullptr;  // pass-1 -> pass-2 sizes when the caller passes written == NULL
@@ -223,6 +225,7 @@ void sfb200_destroy(sfb200_ctx* ctx)
   cudaFree(ctx->d_bits);
   cudaFree(ctx->d_written);
   cudaFree(ctx->d_jump);
+  cudaFree(ctx->d_find);
   cudaFree(ctx->d_defer);
   cudaFree(ctx->d_order);
   cudaFree(ctx->d_src);
@@ -310,6 +313,22 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
     jump_tiles = (dst_bytes + delta + 128 + sfb::JUMP_TILE - 1) / sfb::JUMP_TILE + 1;
     const uint64_t need = jump_tiles * sfb::JUMP_TILE * 4 + jump_tiles * 4 + (sfb::JUMP_MAX_ROUNDS + 1) * 4;
     const int rc = grow(ctx, &ctx->d_jump, &ctx->d_jump_cap, need);
+    if (rc != SFB200_RC_OK) return rc;
+  }
+  // ... and pass 1 decodes its blocks side by side (block_finder.cuh).  The input's size is only known
+  // on the device; the scratch is sized for an input a little larger than the output, and block
+  // starts that do not fit are simply not found (their blocks are then decoded by the tail job).
+  bool blocks = jump;
+  if (const char* e = std::getenv("SFB200_BLOCKS")) blocks = blocks && e[0] != '0';
+  uint32_t cand_cap = 0, job_cap = 0, tab_size = 0;
+  if (blocks) {
+    const uint64_t src_bits_max = 8 * (dst_bytes + dst_bytes / 32 + 65536);
+    cand_cap = static_cast<uint32_t>(std::min<uint64_t>(src_bits_max / 128 + 4096, 1ull << 30));
+    job_cap = static_cast<uint32_t>(std::min<uint64_t>(src_bits_max / 2048 + 1024, 1ull << 27));
+    tab_size = 1024;
+    while (tab_size < 2 * job_cap) tab_size *= 2;
+    const uint64_t need = 64 + 4ull * tab_size + sizeof(sfb::BlockJob) * static_cast<uint64_t>(job_cap) + 8ull * cand_cap;
+    const int rc = grow(ctx, &ctx->d_find, &ctx->d_find_cap, need);
     if (rc != SFB200_RC_OK) return rc;
   }
   // Geometry.  Measured on C2 (profiles/r01_small_geometry_c2.md): with 16 warps per SM the small
@@ -445,12 +464,59 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
       sa.stream_counter = ctr + 0;
       sa.lens_scratch = ctx->d_lens;
       sa.match_bits = ctx->d_bits;
+      sa.mode = 0;
+      sa.jobs = nullptr;
+      sa.job_count = nullptr;
+      sa.job_cap = 0;
+      sa.job_tab = nullptr;
+      sa.tab_mask = 0;
+      sa.tail_job = nullptr;
       const uint64_t resident =
           static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->stream_ctas_per_sm);
-      const unsigned grid = static_cast<unsigned>(cnt < resident ? cnt : resident);
-      sfb::huff_stream_kernel<StreamCfg><<<grid, 32, StreamCfg::SMEM_BYTES, s1>>>(sa);
-      SFB_TRY(ctx, cudaGetLastError());
-      ctx->launches += 1;
+      if (blocks) {
+        // find block starts | count each candidate block | chain | write the chained blocks
+        uint32_t* const counters = reinterpret_cast<uint32_t*>(ctx->d_find);  // cand_count, job_count, tail_job
+        sfb::FindArgs f;
+        f.src_base = src_base;
+        f.src_off = src_off;
+        f.src_len = src_len;
+        f.idx = 0;
+        f.cand_count = counters + 0;
+        f.job_count = counters + 1;
+        f.tail_job = counters + 2;
+        f.job_tab = counters + 16;
+        f.tab_mask = tab_size - 1;
+        f.jobs = reinterpret_cast<sfb::BlockJob*>(ctx->d_find + 64 + 4ull * tab_size);
+        f.job_cap = job_cap;
+        f.cand = reinterpret_cast<uint64_t*>(ctx->d_find + 64 + 4ull * tab_size +
+                                             sizeof(sfb::BlockJob) * static_cast<uint64_t>(job_cap));
+        f.cand_cap = cand_cap;
+        f.dst_cap = dst_cap;
+        SFB_TRY(ctx, cudaMemsetAsync(ctx->d_find, 0, 64 + 4ull * tab_size, s1));
+        sfb::find_candidates_kernel<<<ctx->sm_count * 8, sfb::FIND_THREADS, 0, s1>>>(f);
+        sfb::verify_candidates_kernel<<<ctx->sm_count * 4, sfb::FIND_THREADS, 0, s1>>>(f);
+        sa.jobs = f.jobs;
+        sa.job_count = f.job_count;
+        sa.job_cap = job_cap;
+        sa.job_tab = f.job_tab;
+        sa.tab_mask = f.tab_mask;
+        sa.tail_job = f.tail_job;
+        sa.idx_base = 0;
+        sa.mode = 1;
+        const unsigned grid = static_cast<unsigned>(resident);
+        sfb::huff_stream_kernel<StreamCfg><<<grid, 32, StreamCfg::SMEM_BYTES, s1>>>(sa);
+        sfb::chain_kernel<<<1, 32, 0, s1>>>(f);
+        sa.mode = 2;
+        sa.stream_counter = ctr + 1;
+        sfb::huff_stream_kernel<StreamCfg><<<grid, 32, StreamCfg::SMEM_BYTES, s1>>>(sa);
+        SFB_TRY(ctx, cudaGetLastError());
+        ctx->launches += 5;
+      } else {
+        const unsigned grid = static_cast<unsigned>(cnt < resident ? cnt : resident);
+        sfb::huff_stream_kernel<StreamCfg><<<grid, 32, StreamCfg::SMEM_BYTES, s1>>>(sa);
+        SFB_TRY(ctx, cudaGetLastError());
+        ctx->launches += 1;
+      }
     } else if (use_small) {
       a.group_counter = ctr + 0;
       a.defer_list = ctx->d_defer + first;

@@ -29,6 +29,7 @@
 #pragma once
 
 #include "huff_lanes.cuh"
+#include "block_finder.cuh"
 
 namespace sfb {
 
@@ -50,6 +51,17 @@ struct StreamArgs {
   unsigned long long* stream_counter;  // zeroed before launch
   uint32_t* lens_scratch;              // gridDim.x * SCRATCH_WORDS * 32 words
   uint32_t* match_bits;
+  // Blocks of ONE stream (idx_base) side by side, see block_finder.cuh.  mode 0: whole streams as
+  // above.  mode 1: a warp per job decodes the block at jobs[k].start_bit COUNTING ONLY and
+  // records its end, size and reach.  mode 2: a warp per job that the chain gave a position
+  // writes its block there; the tail job carries on to the end of the stream and reports.
+  uint32_t mode;
+  BlockJob* jobs;
+  const uint32_t* job_count;
+  uint32_t job_cap;
+  const uint32_t* job_tab;
+  uint32_t tab_mask;
+  const uint32_t* tail_job;
 };
 
 struct Tok {
@@ -258,16 +270,24 @@ __global__ void __launch_bounds__(32) huff_stream_kernel(const StreamArgs a)
   for (int i = 0; i < 15 - C::ROOT_DIST; ++i) lt_dist.fc[i] = 0;
   lt_lit.off0 = lt_dist.off0 = 0;
 
+  const uint32_t mode = a.mode;  // (warp-uniform, like everything that steers the loops below)
+  unsigned long long n_units = a.n;
+  uint32_t tail = 0;
+  if (mode) {
+    const uint32_t nj = *a.job_count;
+    n_units = nj < a.job_cap ? nj : a.job_cap;
+    if (mode == 2u) tail = *a.tail_job;
+  }
   for (;;) {
     unsigned long long si = 0;
     if (lane == 0) si = atomicAdd(a.stream_counter, 1ull);
     si = __shfl_sync(FULL, si, 0);
-    if (si >= a.n) break;
-    const uint64_t idx = a.list ? a.list[si] : a.idx_base + si;
+    if (si >= n_units) break;
+    const uint64_t idx = mode ? a.idx_base : (a.list ? a.list[si] : a.idx_base + si);
     const uint64_t slen = a.src_len[idx];
-    const uint64_t cap = a.dst_cap[idx];
-    if (slen >= 0xffffff00ull || cap >= 0xffffff00ull) {
-      if (lane == 0) {
+    const uint64_t real_cap = a.dst_cap[idx];
+    if (slen >= 0xffffff00ull || real_cap >= 0xffffff00ull) {
+      if (lane == 0 && (mode == 0u || (mode == 2u && si == 0))) {
         a.status[idx] = ST_ERROR;  // outside the batch precondition
         a.written[idx] = 0;
       }
@@ -279,10 +299,32 @@ __global__ void __launch_bounds__(32) huff_stream_kernel(const StreamArgs a)
     uint64_t bitpos = 0;  // where the next block header starts (warp-uniform)
     uint64_t outpos = 0;  // bytes produced so far (warp-uniform)
     int status = -1;      // < 0: still going
+    bool one_block = false, stop = false;
+    uint64_t cap = real_cap;
+    uint32_t job_need = 0;
+    if (mode) {
+      bitpos = a.jobs[si].start_bit;
+      if (mode == 2u) {
+        outpos = a.jobs[si].base;
+        if (outpos == JOB_NONE) continue;  // not a block of the stream (or beyond its end)
+        one_block = si != tail;
+      } else {
+        one_block = true;
+        cap = 0xfffffff0ull;  // sizes are settled by the chain
+      }
+    }
+    const bool counting = mode == 1u;
     BitReader br;
     TokWin ow;
     ow.park();
-    while (status < 0) {
+    while (status < 0 && !stop) {
+      if (one_block) stop = true;  // (every way round the loop below ends a block)
+      if (outpos >= cap) {         // only a counting job that decodes garbage gets here
+        if (counting) {
+          status = ST_DST_TOO_SMALL;
+          break;
+        }
+      }
       // ---- block header, by every lane --------------------------------------------------------
       br.open(src, static_cast<uint32_t>(slen), ring);
       br.seek_bit(bitpos < total_bits ? bitpos : total_bits);
@@ -302,7 +344,8 @@ __global__ void __launch_bounds__(32) huff_stream_kernel(const StreamArgs a)
       }
       if (state == S_STORED) {  // src/decompress.cpp:434, by the whole warp
         uint8_t* d = a.dst_base + doff + outpos;
-        for (uint32_t i = lane; i < copy_left; i += 32u) d[i] = copy_src[i];
+        if (!counting)
+          for (uint32_t i = lane; i < copy_left; i += 32u) d[i] = copy_src[i];
         outpos += copy_left;
         bitpos = 8ull * static_cast<uint64_t>(copy_src + copy_left - br.begin());
         if (final_block) status = ST_SUCCESS;
@@ -349,6 +392,28 @@ __global__ void __launch_bounds__(32) huff_stream_kernel(const StreamArgs a)
                                   my_start + r.out > cap);
         const uint32_t bads = __ballot_sync(FULL, bad);
         const uint32_t last = bads ? static_cast<uint32_t>(__ffs(static_cast<int>(bads)) - 1) : cut;
+        if (counting) {  // (warp-uniform) no writing pass: note the reach, take the count pass's verdict
+          const uint32_t nd = live && r.need > 0 && static_cast<uint64_t>(r.need) > my_start
+                                  ? static_cast<uint32_t>(static_cast<uint64_t>(r.need) - my_start)
+                                  : 0u;
+          const uint32_t wmax = __reduce_max_sync(FULL, nd);
+          job_need = wmax > job_need ? wmax : job_need;
+          const uint32_t total_c = __shfl_sync(FULL, inc, 31);
+          outpos += total_c;
+          if (cut < 32u) {
+            bitpos = shfl_u64(s + r.rel, static_cast<int>(cut));
+            const uint32_t cflag = __shfl_sync(FULL, r.flag, static_cast<int>(cut));
+            if (cflag == 2u) status = __shfl_sync(FULL, r.st, static_cast<int>(cut));
+            else if (final_block) status = ST_SUCCESS;
+            break;
+          }
+          if (outpos >= cap) {
+            status = ST_DST_TOO_SMALL;
+            break;
+          }
+          b0 = shfl_u64(s + r.rel, 31);
+          continue;
+        }
         // ---- decode once more, writing --------------------------------------------------------
         const bool em = live && lane <= last;
         if (em) {
@@ -378,8 +443,17 @@ __global__ void __launch_bounds__(32) huff_stream_kernel(const StreamArgs a)
       }
     }
     if (lane == 0) {
-      a.status[idx] = static_cast<uint8_t>(status);
-      a.written[idx] = outpos;
+      if (counting) {
+        BlockJob* const jb = a.jobs + si;
+        jb->end_bit = bitpos;
+        jb->out = outpos;
+        jb->need = job_need;
+        jb->flags = status >= 0 ? JOB_ENDS : 0u;
+        jb->next = status < 0 ? job_find(a.job_tab, a.tab_mask, a.jobs, static_cast<uint32_t>(n_units), bitpos) : 0u;
+      } else if (!one_block) {
+        a.status[idx] = static_cast<uint8_t>(status);
+        a.written[idx] = outpos;
+      }
     }
   }
 }

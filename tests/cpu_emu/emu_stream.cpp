@@ -14,6 +14,100 @@ static uint16_t* emu_stream_smem = nullptr;  // one warp's shared memory, seen b
 using StreamCfg = sfb::Cfg<8, 6, 96, 1>;
 
 // one stream; dst_base must be 128-byte aligned, the stream's region starts at dst_base + dst_off
+static void run_warp(const sfb::StreamArgs& a)
+{
+  std::vector<std::thread> lanes;
+  for (unsigned l = 0; l < 32; ++l)
+    lanes.emplace_back([&a, l] {
+      threadIdx.x = l;
+      blockIdx.x = 0;
+      blockDim.x = 32;
+      gridDim.x = 1;
+      sfb::huff_stream_kernel<StreamCfg>(a);
+    });
+  for (auto& t : lanes) t.join();
+}
+
+// n_cand > 0: the blocks-side-by-side route of block_finder.cuh with the given candidate block
+// starts (bit positions; the GPU's finder kernels are replaced by the caller's list, which may
+// hold true starts, wrong ones and duplicates): count jobs, chain, writing jobs.
+// stats[0] = jobs on the chain, stats[1] = tail job
+extern "C" void emu_huff_stream_jobs(const uint8_t* src, uint64_t src_len, uint8_t* dst_base, uint64_t dst_off,
+                                     uint64_t dst_cap, uint32_t* match_bits, uint8_t* status, uint64_t* written,
+                                     const uint64_t* cand, uint32_t n_cand, uint32_t* stats)
+{
+  EmuWarp warp;
+  emu_warp = &warp;
+  std::vector<uint16_t> smem(StreamCfg::SMEM_BYTES / 2 + 64, 0xDEAD);
+  std::vector<uint32_t> lens(sfb::SCRATCH_WORDS * 32, 0xDEADBEEFu);
+  emu_stream_smem = smem.data();
+  const uint64_t zero = 0;
+  uint32_t tab_size = 64;
+  while (tab_size < 2 * (n_cand + 1)) tab_size *= 2;
+  std::vector<uint32_t> job_tab(tab_size, 0u);
+  std::vector<sfb::BlockJob> jobs(n_cand + 1);
+  for (uint32_t k = 0; k <= n_cand; ++k) {
+    sfb::BlockJob jb{};
+    jb.start_bit = k ? cand[k - 1] : 0;
+    jb.end_bit = jb.start_bit;
+    jb.base = sfb::JOB_NONE;
+    jb.flags = sfb::JOB_ENDS;
+    jobs[k] = jb;
+    if (k) {
+      uint32_t slot = sfb::job_slot(jb.start_bit, tab_size - 1);
+      while (job_tab[slot]) slot = (slot + 1) & (tab_size - 1);
+      job_tab[slot] = k;
+    }
+  }
+  uint32_t job_count = n_cand + 1, tail_job = 0;
+  sfb::StreamArgs a{};
+  a.src_base = src;
+  a.src_off = &zero;
+  a.src_len = &src_len;
+  a.dst_base = dst_base;
+  a.dst_delta = 0;
+  a.dst_off = &dst_off;
+  a.dst_cap = &dst_cap;
+  a.status = status;
+  a.written = written;
+  a.list = nullptr;
+  a.idx_base = 0;
+  a.n = 1;
+  a.lens_scratch = lens.data();
+  a.match_bits = match_bits;
+  a.jobs = jobs.data();
+  a.job_count = &job_count;
+  a.job_cap = n_cand + 1;
+  a.job_tab = job_tab.data();
+  a.tab_mask = tab_size - 1;
+  a.tail_job = &tail_job;
+  unsigned long long counter = 0;
+  a.stream_counter = &counter;
+  a.mode = 1;
+  run_warp(a);
+  sfb::FindArgs f{};
+  f.idx = 0;
+  f.jobs = jobs.data();
+  f.job_count = &job_count;
+  f.job_cap = n_cand + 1;
+  f.tail_job = &tail_job;
+  f.dst_cap = &dst_cap;
+  threadIdx.x = 0;
+  blockIdx.x = 0;
+  sfb::chain_kernel(f);
+  counter = 0;
+  a.mode = 2;
+  run_warp(a);
+  if (stats) {
+    uint32_t on = 0;
+    for (auto& jb : jobs) on += jb.base != sfb::JOB_NONE;
+    stats[0] = on;
+    stats[1] = tail_job;
+  }
+  emu_warp = nullptr;
+  emu_stream_smem = nullptr;
+}
+
 extern "C" void emu_huff_stream(const uint8_t* src, uint64_t src_len, uint8_t* dst_base, uint64_t dst_off,
                                 uint64_t dst_cap, uint32_t* match_bits, uint8_t* status, uint64_t* written)
 {
@@ -24,7 +118,7 @@ extern "C" void emu_huff_stream(const uint8_t* src, uint64_t src_len, uint8_t* d
   emu_stream_smem = smem.data();
   unsigned long long counter = 0;
   const uint64_t zero = 0;
-  sfb::StreamArgs a;
+  sfb::StreamArgs a{};
   a.src_base = src;
   a.src_off = &zero;
   a.src_len = &src_len;
@@ -40,16 +134,7 @@ extern "C" void emu_huff_stream(const uint8_t* src, uint64_t src_len, uint8_t* d
   a.stream_counter = &counter;
   a.lens_scratch = lens.data();
   a.match_bits = match_bits;
-  std::vector<std::thread> lanes;
-  for (unsigned l = 0; l < 32; ++l)
-    lanes.emplace_back([&a, l] {
-      threadIdx.x = l;
-      blockIdx.x = 0;
-      blockDim.x = 32;
-      gridDim.x = 1;
-      sfb::huff_stream_kernel<StreamCfg>(a);
-    });
-  for (auto& t : lanes) t.join();
+  run_warp(a);
   emu_warp = nullptr;
   emu_stream_smem = nullptr;
 }
@@ -60,8 +145,27 @@ extern "C" void emu_lz_resolve(uint8_t* dst_base, const uint64_t* dst_off, const
 // One stream through the single-stream pass 1 (above) and the real pass 2 (emu_lz.cpp), in a
 // private padded copy of dst with canaries.  `dst_phase` (0..127) places the region relative to a
 // 128-byte boundary.  Returns 0, or 1 if anything outside [dst, dst+cap) changed.
+static int stream_decompress_impl(const uint8_t* src, uint64_t src_len, uint8_t* dst, uint64_t dst_cap,
+                                  uint32_t dst_phase, uint8_t* status, uint64_t* written, const uint64_t* cand,
+                                  uint32_t n_cand, uint32_t* stats);
+
 extern "C" int emu_stream_decompress(const uint8_t* src, uint64_t src_len, uint8_t* dst, uint64_t dst_cap,
                                      uint32_t dst_phase, uint8_t* status, uint64_t* written)
+{
+  return stream_decompress_impl(src, src_len, dst, dst_cap, dst_phase, status, written, nullptr, 0, nullptr);
+}
+
+// the same through the blocks-side-by-side route, see emu_huff_stream_jobs
+extern "C" int emu_stream_decompress_jobs(const uint8_t* src, uint64_t src_len, uint8_t* dst, uint64_t dst_cap,
+                                          uint32_t dst_phase, uint8_t* status, uint64_t* written,
+                                          const uint64_t* cand, uint32_t n_cand, uint32_t* stats)
+{
+  return stream_decompress_impl(src, src_len, dst, dst_cap, dst_phase, status, written, cand, n_cand, stats);
+}
+
+static int stream_decompress_impl(const uint8_t* src, uint64_t src_len, uint8_t* dst, uint64_t dst_cap,
+                                  uint32_t dst_phase, uint8_t* status, uint64_t* written, const uint64_t* cand,
+                                  uint32_t n_cand, uint32_t* stats)
 {
   constexpr size_t PAD = 512;
   std::vector<uint8_t> sbuf(src_len + 64, 0xEE);
@@ -73,7 +177,11 @@ extern "C" int emu_stream_decompress(const uint8_t* src, uint64_t src_len, uint8
   if (dst_cap) std::memcpy(dp, dst, dst_cap);
   std::vector<uint32_t> bits((doff + dst_cap) / 32 + 8, 0u);
   uint64_t wr = 0;
-  emu_huff_stream(sbuf.data() + 16, src_len, dbase, doff, dst_cap, bits.data(), status, &wr);
+  if (cand)
+    emu_huff_stream_jobs(sbuf.data() + 16, src_len, dbase, doff, dst_cap, bits.data(), status, &wr, cand, n_cand,
+                         stats);
+  else
+    emu_huff_stream(sbuf.data() + 16, src_len, dbase, doff, dst_cap, bits.data(), status, &wr);
   if (wr > dst_cap) return 2;
   emu_lz_resolve(dbase, &doff, &wr, bits.data(), 1);
   *written = wr;

@@ -22,7 +22,8 @@ def build(root_lit=8, root_dist=6, pool=96) -> str:
     srcs = [os.path.join(emu, "emu.cpp"), os.path.join(emu, "emu_lz.cpp"), os.path.join(emu, "emu_stream.cpp"),
             os.path.join(emu, "cuda_shim.h"), os.path.join(emu, "cuda_shim_warp.h"),
             os.path.join(csrc, "deflate_lane.cuh"), os.path.join(csrc, "huff_lanes.cuh"),
-            os.path.join(csrc, "lz_warp.cuh"), os.path.join(csrc, "huff_stream.cuh")]
+            os.path.join(csrc, "lz_warp.cuh"), os.path.join(csrc, "huff_stream.cuh"),
+            os.path.join(csrc, "block_finder.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         subprocess.check_call(["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-pthread",
                                f"-DSFB_EMU_ROOT_LIT={root_lit}", f"-DSFB_EMU_ROOT_DIST={root_dist}",
@@ -63,6 +64,27 @@ class Emu:
                                             p(wr, _u64p))
         assert rc == 0, f"emulated stream kernel wrote outside its dst region (code {rc})"
         return int(st[0]), d[:cap].tobytes(), int(wr[0])
+
+    def stream_decompress_jobs(self, src: bytes, cap: int, cand, phase: int = 0, fill: int = 0xA5):
+        """One stream through the blocks-side-by-side route (block_finder.cuh): counting jobs at
+        the candidate block starts `cand` (bit positions; stands in for the GPU's finder kernels),
+        the chain, the writing jobs, the real pass 2.
+        -> (status, dst bytes, written, jobs on the chain, tail job)"""
+        self.lib.emu_stream_decompress_jobs.argtypes = [_u8p, C.c_uint64, _u8p, C.c_uint64, C.c_uint32,
+                                                        _u8p, _u64p, _u64p, C.c_uint32,
+                                                        C.POINTER(C.c_uint32)]
+        s = np.frombuffer(src, dtype=np.uint8) if len(src) else np.zeros(1, np.uint8)
+        d = np.full(max(cap, 1), fill, dtype=np.uint8)
+        st = np.zeros(1, np.uint8)
+        wr = np.zeros(1, np.uint64)
+        c = np.asarray(list(cand) + [0], dtype=np.uint64)
+        stats = np.zeros(2, np.uint32)
+        p = lambda a, t: a.ctypes.data_as(t)
+        rc = self.lib.emu_stream_decompress_jobs(p(s, _u8p), len(src), p(d, _u8p), cap, phase, p(st, _u8p),
+                                                 p(wr, _u64p), p(c, _u64p), len(cand),
+                                                 p(stats, C.POINTER(C.c_uint32)))
+        assert rc == 0, f"emulated stream kernel wrote outside its dst region (code {rc})"
+        return int(st[0]), d[:cap].tobytes(), int(wr[0]), int(stats[0]), int(stats[1])
 
     def stats(self):
         out = (C.c_ulonglong * 4)()

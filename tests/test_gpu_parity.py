@@ -3,6 +3,8 @@ reference's own results), the oracle on seeded batches, and size-independent pro
 BASELINE.json's full sizes.  Integer/byte work: the bar is bit-exact (bytes, status, written)."""
 import hashlib
 
+import zlib
+
 import numpy as np
 import pytest
 import torch
@@ -212,6 +214,77 @@ def test_large_single_streams(ctx, oracle):
     assert (st == ost).all() and (wr == owr).all()
     assert (dst == dst_o).all()
     assert list(st[:4]) == [0, 0, 0, 0] and st[4] != 0 and st[5] == 4
+
+
+def _one_stream_per_call(ctx, src_bytes, cap, phase=0, src_phase=0, fill=0xA5):
+    """n == 1: the single-stream route (block finder, a warp per block, pointer-jumping pass 2).
+    dst sits `phase` bytes into a padded device buffer; -> (status, written, dst bytes, padding intact)"""
+    import torch
+    dev = torch.device("cuda", ctx.device)
+    pad = 256
+    s = torch.frombuffer(bytearray(b"\xEE" * src_phase + src_bytes + b"\xEE" * 8), dtype=torch.uint8).to(dev)
+    big = torch.full((pad + phase + cap + pad,), fill, dtype=torch.uint8, device=dev)
+    one = lambda v: torch.tensor([v], dtype=torch.int64, device=dev)
+    status = torch.full((1,), 0xEE, dtype=torch.uint8, device=dev)
+    written = torch.full((1,), -1, dtype=torch.int64, device=dev)
+    ctx.decompress_batch_device(s, one(src_phase), one(len(src_bytes)), big[pad + phase:], one(0), one(cap), status,
+                                written)
+    torch.cuda.synchronize(dev)
+    got = big.cpu().numpy()
+    intact = bool((got[:pad + phase] == fill).all() and (got[pad + phase + cap:] == fill).all())
+    return int(status.item()), int(written.item()), got[pad + phase: pad + phase + cap].tobytes(), intact
+
+
+def test_single_stream_route_golden_one_call_per_stream(ctx, oracle, golden):
+    """Every 9th..61st case of the golden families, one call each (so each goes through the block
+    finder, the counting / chain / writing jobs and the pointer-jumping pass 2), at varying dst
+    and src phases."""
+    k = 0
+    for name, stride in (("known_answers", 1), ("crafted_dynamic_headers", 1), ("cut7_starfleet_dynamic", 17),
+                         ("cut7_starfleet_fixed", 61), ("cut1_multiblock_12000", 61), ("cap_dynamic_4096", 31),
+                         ("cap_stored_4096", 61), ("flip_dynamic_4096", 31), ("flip_repetitive_70000", 61),
+                         ("cap_repetitive_70000", 997)):
+        if name not in golden.families:
+            continue
+        for i, src, cap in golden.cases(name, stride):
+            want_st, want_wr, want_hash, cls = golden.expected(name, i)
+            st, wr, dst, intact = _one_stream_per_call(ctx, src, cap, phase=(7 * k) % 131, src_phase=k % 5)
+            k += 1
+            assert (st, wr) == (want_st, want_wr), (name, i, cls, st, wr)
+            assert "%016x" % oracle.fnv1a64(dst) == want_hash, (name, i, cls)
+            assert intact, (name, i)
+    assert k > 600
+
+
+@pytest.mark.parametrize("blocks", ["1", "0"])
+def test_single_stream_route_large(oracle, monkeypatch, blocks):
+    """C1-shaped inputs (about a megabyte and more, many dynamic blocks; also stored and fixed blocks in
+    between, a truncated input, a destination that is too small), blocks side by side
+    (SFB200_BLOCKS=1, the default) and front to back: all bytes against the oracle."""
+    import starflate_b200 as S
+    monkeypatch.setenv("SFB200_BLOCKS", blocks)
+    c = S.Context(0)
+    try:
+        inputs = []
+        for kind, size, seed in (("dynamic", 3 << 20, 1), ("multiblock", 1 << 20, 2), ("repetitive", 4 << 20, 3)):
+            plain, comp = T.make_stream(kind, size, 8800 + seed)
+            inputs.append((comp, len(plain)))
+        big_plain = b"".join(T.text_like(1 << 20, 50 + j) for j in range(6))
+        big = T.raw_deflate(big_plain, 6)
+        inputs += [(big, len(big_plain)), (big[: len(big) // 2], len(big_plain)), (big, len(big_plain) - 54321),
+                   (big, 1000)]
+        mixed = T.raw_deflate_multiblock([T.text_like(300000, 1), T.incompressible(70000, 2), T.text_like(200000, 3),
+                                          T.text_like(150000, 4)], [6, 0, 6, 9],
+                                         [zlib.Z_DEFAULT_STRATEGY, zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED,
+                                          zlib.Z_DEFAULT_STRATEGY])
+        inputs.append((mixed, 720000))
+        for k, (src, cap) in enumerate(inputs):
+            ost, odst, owr, _ = oracle.decompress(src, cap)
+            st, wr, dst, intact = _one_stream_per_call(c, src, cap, phase=(29 * k) % 128, src_phase=k % 4)
+            assert (st, wr) == (ost, owr), (k, st, wr, ost, owr)
+            assert dst == odst and intact, k
+    finally:
+        c.close()
 
 
 def test_one_bad_stream_does_not_affect_neighbours(ctx, oracle):

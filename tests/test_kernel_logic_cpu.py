@@ -3,6 +3,8 @@ for the host by tests/cpu_emu) against the golden fixtures and the oracle.  This
 of the decoder state machine, bit reader, LUT builder, in-place token writer and the
 warp-cooperative LZ77 resolve in the GPU-less container; the real parity tests are the `-m gpu`
 ones through the C ABI."""
+import zlib
+
 import numpy as np
 import pytest
 
@@ -151,3 +153,56 @@ def test_single_stream_speculative_pass1(emu, oracle, golden):
             st, dst, wr = emu.stream_decompress(comp, cap, phase=seed * 31)
             ost, odst, owr, _ = oracle.decompress(comp, cap)
             assert (st, wr) == (ost, owr) and dst == odst, (kind, cap)
+
+
+def test_single_stream_blocks_side_by_side(emu, oracle):
+    """block_finder.cuh + huff_stream.cuh modes 1/2 in emulation: a warp per candidate block start
+    counts, the chain keeps the candidates a front-to-back decode really reaches, a warp per kept
+    block writes, the tail carries on.  Candidates given here: all true block starts (from the
+    oracle's trace), a thinned-out subset of them, wrong positions, or none — the result must be
+    the front-to-back one every time, for complete, truncated and too-small-dst inputs."""
+    rng = np.random.default_rng(99)
+    chunks = [T.text_like(9000, 1), T.incompressible(700, 2), T.text_like(6000, 3), T.repetitive(20000, 4),
+              T.text_like(5000, 5)]
+    comp = T.raw_deflate_multiblock(chunks, [6, 0, 6, 9, 1], [zlib.Z_DEFAULT_STRATEGY, zlib.Z_DEFAULT_STRATEGY,
+                                                            zlib.Z_FIXED, zlib.Z_DEFAULT_STRATEGY,
+                                                            zlib.Z_DEFAULT_STRATEGY])
+    plain = b"".join(chunks)
+    starts = oracle.block_starts(comp, len(plain))
+    assert len(starts) >= 9 and starts[0] == 0
+    wrong = [int(x) for x in rng.integers(1, 8 * len(comp), 12)] + [starts[2] + 1, starts[3] - 1]
+    cases = [
+        (comp, len(plain), starts[1:]),                      # everything found
+        (comp, len(plain), starts[1:4] + starts[6:]),        # a gap: the tail takes over at block 3
+        (comp, len(plain), wrong),                           # nothing true: job 0 is the tail
+        (comp, len(plain), starts[1:] + wrong + starts[2:4]),  # true, wrong and duplicate starts mixed
+        (comp, len(plain) - 9000, starts[1:]),               # dst too small somewhere in the middle
+        (comp, 100, starts[1:]),                             # dst too small in block 0
+        (comp[: len(comp) * 2 // 3], len(plain), [s for s in starts[1:] if s < 8 * (len(comp) * 2 // 3)]),
+        (comp[:40], len(plain), []),
+    ]
+    for k, (src, cap, cand) in enumerate(cases):
+        ost, odst, owr, _ = oracle.decompress(src, cap)
+        st, dst, wr, on_chain, tail = emu.stream_decompress_jobs(src, cap, cand, phase=(37 * k) % 128)
+        assert (st, wr) == (ost, owr) and dst == odst, (k, st, wr, ost, owr)
+        if k == 0:
+            assert on_chain == len(starts)  # every block was decoded by its own job
+        if k == 2:
+            assert on_chain == 1 and tail == 0
+    # a distance that reaches before the start of the stream, in a later block: the chain must stop
+    # at that block and the tail must report the reference's InvalidDistance
+    w = T.BitWriter()
+    b = T.fixed_block(w, False)
+    for ch in b"abcdefgh":
+        b.literal(ch)
+    b.eob()
+    second = len(w)
+    b = T.fixed_block(w, True)
+    b.literal(ord("x"))
+    b.match(5, 20)  # 9 bytes written so far: distance 20 is out of range
+    b.eob()
+    src = w.tobytes()
+    ost, odst, owr, _ = oracle.decompress(src, 64)
+    assert ost == 7
+    st, dst, wr, on_chain, tail = emu.stream_decompress_jobs(src, 64, [second])
+    assert (st, wr) == (ost, owr) and dst == odst and on_chain == 2 and tail == 1

@@ -23,7 +23,7 @@ def text(n_bytes, seed):
     return b"".join(out)
 
 
-def run(mib, modes=("1", "0"), reps=3):
+def run(mib, modes=("blocks", "warp", "lane"), reps=3):
     plain = text(mib << 20, 4242)
     t0 = time.time()
     comp = T.raw_deflate(plain, 6)
@@ -37,7 +37,12 @@ def run(mib, modes=("1", "0"), reps=3):
     status, written = one(9, torch.uint8), one(0, torch.int64)
     want = torch.frombuffer(bytearray(plain), dtype=torch.uint8).to(dev)
     for mode in modes:
-        os.environ["SFB200_STREAM_MODE"] = mode
+        # blocks: finder + a warp per block + pointer jumping | warp: one warp front to back + pointer
+        # jumping | lane: the batch kernels (one lane, one warp)
+        os.environ["SFB200_STREAM_MODE"] = "0" if mode == "lane" else "1"
+        os.environ["SFB200_BLOCKS"] = "1" if mode == "blocks" else "0"
+        if mode == "lane" and mib > 64:
+            continue
         ctx = sfb.Context(0)
         best = None
         for _ in range(reps):
@@ -50,7 +55,7 @@ def run(mib, modes=("1", "0"), reps=3):
                 best = p
         ok = int(status.item()) == 0 and int(written.item()) == len(plain) and bool(torch.equal(dst[:len(plain)], want))
         ms = best[1] + best[2]
-        print(f"{mib} MiB plain, {len(comp)} B deflate (zlib {t_comp:.1f} s): stream_mode={mode} "
+        print(f"{mib} MiB plain, {len(comp)} B deflate (zlib {t_comp:.1f} s): route={mode} "
               f"pass1 {best[1]:.2f} ms pass2 {best[2]:.2f} ms -> {len(plain) / ms / 1e6:.3f} GB/s, "
               f"bit-exact vs zlib input: {ok}", flush=True)
         ctx.close()
