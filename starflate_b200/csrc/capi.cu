@@ -311,7 +311,8 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
   uint64_t jump_tiles = 0;
   if (jump) {
     jump_tiles = (dst_bytes + delta + 128 + sfb::JUMP_TILE - 1) / sfb::JUMP_TILE + 1;
-    const uint64_t need = jump_tiles * sfb::JUMP_TILE * 4 + jump_tiles * 4 + (sfb::JUMP_MAX_ROUNDS + 1) * 4;
+    const uint64_t need = jump_tiles * sfb::JUMP_TILE * 4 + jump_tiles * 4 * (1 + sfb::JUMP_TILE / 128) +
+                          (sfb::JUMP_MAX_ROUNDS + 1) * 4;
     const int rc = grow(ctx, &ctx->d_jump, &ctx->d_jump_cap, need);
     if (rc != SFB200_RC_OK) return rc;
   }
@@ -571,6 +572,7 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
       j.ptr = reinterpret_cast<uint32_t*>(ctx->d_jump);
       j.tile_done = j.ptr + jump_tiles * sfb::JUMP_TILE;
       j.todo = j.tile_done + jump_tiles;
+      j.open = j.todo + sfb::JUMP_MAX_ROUNDS + 1;
       SFB_TRY(ctx, cudaMemsetAsync(j.tile_done, 0, (jump_tiles + sfb::JUMP_MAX_ROUNDS + 1) * 4, s2));
       constexpr uint64_t wpc = sfb::JUMP_THREADS / 32;
       const uint64_t want = (jump_tiles + wpc - 1) / wpc;

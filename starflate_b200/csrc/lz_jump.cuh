@@ -17,8 +17,9 @@
 // The output is cut into tiles of JUMP_TILE bytes, one warp per tile and round.  A tile in which a
 // round changed nothing has only roots as targets; roots never change, so the tile is FINAL: the
 // warp gathers its bytes (dst[i] <- dst[ptr[i]]; only roots are read and no root is rewritten
-// with a different value) and marks it done.  Text-like data is final after 4-6 rounds; each later
-// round only re-visits the tiles that are not.  The host enqueues JUMP_MAX_ROUNDS launches; a
+// with a different value) and marks it done.  Most bytes of text are final after a few rounds
+// but the deepest chain of a tile takes ten and more, so a round only touches the pointers that
+// were not final after the one before (a bit per 4 bytes).  The host enqueues JUMP_MAX_ROUNDS launches; a
 // launch whose predecessor left nothing to do exits at once (no host round trip).
 //
 // Positions are 32-bit offsets in the 128-byte aligned view of the stream (as in lz_warp.cuh):
@@ -42,6 +43,7 @@ struct JumpArgs {
   uint64_t idx;         // the stream
   uint32_t* ptr;        // one per byte of the view [0, q + written) rounded up to a tile
   uint32_t* tile_done;  // one per tile, zeroed before the first round
+  uint32_t* open;       // JUMP_TILE / 128 words per tile: groups of 4 pointers that are not final yet
   uint32_t* todo;       // [JUMP_MAX_ROUNDS + 1] zeroed; todo[r] != 0: round r left tiles open
   uint32_t round;       // 0 = set up the pointers, then 1 .. JUMP_MAX_ROUNDS
 };
@@ -150,10 +152,13 @@ __global__ void __launch_bounds__(JUMP_THREADS) lz_jump_init_kernel(const JumpAr
   if (blockIdx.x == 0 && threadIdx.x == 0) a.todo[0] = 1u;
 }
 
-// Rounds 1 .. JUMP_MAX_ROUNDS.
+// Rounds 1 .. JUMP_MAX_ROUNDS.  Per tile, 8 words of `open` bits say which 16-byte groups of
+// pointers (4 output bytes) still had a non-root target after the previous round; only those are
+// visited, and each takes two hops at once (ptr <- ptr[ptr[ptr]]).
 __global__ void __launch_bounds__(JUMP_THREADS) lz_jump_round_kernel(const JumpArgs a)
 {
   constexpr unsigned FULL = 0xffffffffu;
+  constexpr uint32_t ROWS = JUMP_TILE / 128u;
   if (a.todo[a.round - 1u] == 0u) return;  // everything was final before this round
   const uint32_t lane = threadIdx.x & 31u;
   const uint64_t off = a.dst_off[a.idx] + a.dst_delta;
@@ -164,38 +169,52 @@ __global__ void __launch_bounds__(JUMP_THREADS) lz_jump_round_kernel(const JumpA
   const uint32_t end = q + static_cast<uint32_t>(wr);
   const uint32_t n_tiles = (end + JUMP_TILE - 1u) / JUMP_TILE;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  bool open = false;
+  const bool first = a.round == 1u;
+  bool open_any = false;
   for (uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < n_tiles; tile += warps) {
     if (a.tile_done[tile]) continue;  // (warp-uniform)
     const uint32_t T = tile * JUMP_TILE;
-    bool ch = false;
-    uint4 pv[JUMP_TILE / 128];
+    uint32_t* const om = a.open + static_cast<size_t>(tile) * ROWS;
+    // my row's mask of open groups (lane j < ROWS holds row j's)
+    uint32_t mine = first ? FULL : (lane < ROWS ? om[lane] : 0u);
+    uint32_t still = 0;  // row masks after this round, gathered in lane j
 #pragma unroll
-    for (uint32_t j = 0; j < JUMP_TILE / 128u; ++j) {
+    for (uint32_t j = 0; j < ROWS; ++j) {
+      const uint32_t mask = __shfl_sync(FULL, mine, static_cast<int>(j));
+      if (mask == 0u) continue;  // (warp-uniform)
       const uint32_t wp = T + 128u * j + 4u * lane;
-      uint4 p = make_uint4(wp, wp + 1u, wp + 2u, wp + 3u);
-      if (wp < end) p = *reinterpret_cast<const uint4*>(a.ptr + wp);
-      uint4 g;
-      g.x = a.ptr[p.x];
-      g.y = a.ptr[p.y];
-      g.z = a.ptr[p.z];
-      g.w = a.ptr[p.w];
-      if (wp < end && ((g.x != p.x) | (g.y != p.y) | (g.z != p.z) | (g.w != p.w))) {
-        *reinterpret_cast<uint4*>(a.ptr + wp) = g;
-        ch = true;
+      bool ch = false;
+      if (((mask >> lane) & 1u) && wp < end) {
+        const uint4 p = *reinterpret_cast<const uint4*>(a.ptr + wp);
+        uint4 g;
+        g.x = a.ptr[p.x];
+        g.y = a.ptr[p.y];
+        g.z = a.ptr[p.z];
+        g.w = a.ptr[p.w];
+        if ((g.x != p.x) | (g.y != p.y) | (g.z != p.z) | (g.w != p.w)) {
+          g.x = a.ptr[g.x];
+          g.y = a.ptr[g.y];
+          g.z = a.ptr[g.z];
+          g.w = a.ptr[g.w];
+          *reinterpret_cast<uint4*>(a.ptr + wp) = g;
+          ch = true;
+        }
       }
-      pv[j] = p;
+      const uint32_t nm = __ballot_sync(FULL, ch);
+      if (lane == j) still = nm;
     }
-    if (__any_sync(FULL, ch)) {
-      open = true;
+    const bool open_tile = __any_sync(FULL, still != 0u);
+    if (open_tile) {
+      if (lane < ROWS) om[lane] = still;
+      open_any = true;
       continue;
     }
     // final: every target is a root
 #pragma unroll
-    for (uint32_t j = 0; j < JUMP_TILE / 128u; ++j) {
+    for (uint32_t j = 0; j < ROWS; ++j) {
       const uint32_t wp = T + 128u * j + 4u * lane;
       if (wp >= end || wp + 4u <= q) continue;
-      const uint4 p = pv[j];
+      const uint4 p = *reinterpret_cast<const uint4*>(a.ptr + wp);
       const uint32_t v = static_cast<uint32_t>(base[p.x]) | (static_cast<uint32_t>(base[p.y]) << 8) |
                          (static_cast<uint32_t>(base[p.z]) << 16) | (static_cast<uint32_t>(base[p.w]) << 24);
       if (wp >= q && wp + 4u <= end) {
@@ -208,7 +227,7 @@ __global__ void __launch_bounds__(JUMP_THREADS) lz_jump_round_kernel(const JumpA
     }
     if (lane == 0) a.tile_done[tile] = 1u;
   }
-  if (__any_sync(FULL, open) && lane == 0) a.todo[a.round] = 1u;
+  if (__any_sync(FULL, open_any) && lane == 0) a.todo[a.round] = 1u;
 }
 
 }  // namespace sfb

@@ -17,10 +17,12 @@ import starflate_b200 as sfb  # noqa: E402
 
 
 def text(n_bytes, seed):
-    # distinct 4 MiB pieces: enough that no piece is a back-reference of another (32 KiB window)
+    # distinct 4 MiB pieces up to 32 MiB, then repeated: a repeat lies far outside DEFLATE's 32 KiB
+    # window, so it compresses (and decodes) exactly like fresh text
     piece = 4 << 20
-    out = [T.text_like(min(piece, n_bytes - o), seed + o // piece) for o in range(0, n_bytes, piece)]
-    return b"".join(out)
+    unique = min(n_bytes, 32 << 20)
+    out = b"".join(T.text_like(min(piece, unique - o), seed + o // piece) for o in range(0, unique, piece))
+    return (out * ((n_bytes + unique - 1) // unique))[:n_bytes]
 
 
 def run(mib, modes=("blocks", "warp", "lane"), reps=3):
@@ -64,5 +66,8 @@ def run(mib, modes=("blocks", "warp", "lane"), reps=3):
 
 
 if __name__ == "__main__":
-    for m in [int(a) for a in sys.argv[1:]] or [1, 16]:
-        run(m)
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    routes = [a.split("=", 1)[1].split(",") for a in sys.argv[1:] if a.startswith("--routes=")]
+    reps = [int(a.split("=", 1)[1]) for a in sys.argv[1:] if a.startswith("--reps=")]
+    for m in [int(a) for a in args] or [1, 16]:
+        run(m, *(routes[:1] or [("blocks", "warp", "lane")]), reps=(reps or [3])[0])
