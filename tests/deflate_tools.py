@@ -252,6 +252,16 @@ def text_like(n_bytes: int, seed: int, vocab_size: int = 8192) -> bytes:
     return out.tobytes()
 
 
+def big_text(n_bytes: int, seed: int) -> bytes:
+    """Text for one LARGE stream (BASELINE configs C1 / C5): distinct 4 MiB pieces of text_like up
+    to 32 MiB, then repeated — a repeat lies far outside DEFLATE's 32 KiB window, so it compresses
+    and decodes exactly like fresh text (and generating 1 GiB stays a matter of seconds)."""
+    piece = 4 << 20
+    unique = min(n_bytes, 32 << 20)
+    out = b"".join(text_like(min(piece, unique - o), seed + o // piece) for o in range(0, unique, piece))
+    return (out * ((n_bytes + unique - 1) // unique))[:n_bytes] if unique else b""
+
+
 def repetitive(n_bytes: int, seed: int) -> bytes:
     """Long single-byte runs (distance-1, length-258 matches), short-period patterns and far
     repeats up to 32 KiB."""

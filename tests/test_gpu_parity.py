@@ -349,3 +349,32 @@ def test_full_size_checksum_of_checksums(ctx, shape):
     ctx.checksum_batch_device(dst, dst_off, written, out)
     torch.cuda.synchronize(dev)
     assert (out.cpu().numpy().view(np.uint64) == want).all()
+
+
+@pytest.mark.parametrize("shape,size", [("C1", 1 << 20), ("C5", 1 << 30)])
+def test_full_size_single_stream_round_trip(ctx, shape, size):
+    """BASELINE configs C1 (one ~1 MiB text stream) and C5 (one 1 GiB text stream, ~12 000 dynamic
+    blocks) at full size through the device API: Success, written == size, and every byte equal
+    to the text that was compressed (compress -> decompress round trip; zlib made the stream, so
+    no oracle run is needed at this size), plus the position-weighted checksum of the output
+    against the same checksum of the input computed by the same kernel."""
+    plain = T.big_text(size, 777)
+    comp = T.raw_deflate(plain, 6)
+    dev = torch.device("cuda", ctx.device)
+    src = torch.frombuffer(bytearray(comp), dtype=torch.uint8).to(dev)
+    want = torch.frombuffer(bytearray(plain), dtype=torch.uint8).to(dev)
+    del plain
+    dst = torch.full((size + 100,), 0xA5, dtype=torch.uint8, device=dev)
+    one = lambda v: torch.tensor([v], dtype=torch.int64, device=dev)
+    status = torch.full((1,), 0xEE, dtype=torch.uint8, device=dev)
+    written = torch.full((1,), -1, dtype=torch.int64, device=dev)
+    ctx.decompress_batch_device(src, one(0), one(len(comp)), dst, one(0), one(size + 100), status, written)
+    torch.cuda.synchronize(dev)
+    assert (int(status.item()), int(written.item())) == (0, size)
+    assert torch.equal(dst[:size], want)
+    assert bool((dst[size:] == 0xA5).all())  # capacity beyond the decoded size is left alone
+    sums = torch.zeros(2, dtype=torch.int64, device=dev)
+    ctx.checksum_batch_device(dst, one(0), written, sums[:1])
+    ctx.checksum_batch_device(want, one(0), written, sums[1:])
+    torch.cuda.synchronize(dev)
+    assert int(sums[0].item()) == int(sums[1].item())

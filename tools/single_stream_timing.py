@@ -16,13 +16,7 @@ import deflate_tools as T  # noqa: E402
 import starflate_b200 as sfb  # noqa: E402
 
 
-def text(n_bytes, seed):
-    # distinct 4 MiB pieces up to 32 MiB, then repeated: a repeat lies far outside DEFLATE's 32 KiB
-    # window, so it compresses (and decodes) exactly like fresh text
-    piece = 4 << 20
-    unique = min(n_bytes, 32 << 20)
-    out = b"".join(T.text_like(min(piece, unique - o), seed + o // piece) for o in range(0, unique, piece))
-    return (out * ((n_bytes + unique - 1) // unique))[:n_bytes]
+text = T.big_text
 
 
 def run(mib, modes=("blocks", "warp", "lane"), reps=3):
