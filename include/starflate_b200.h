@@ -64,7 +64,9 @@ int sfb200_abi_version(void);
  * Stream i reads  src_base[src_off[i] .. src_off[i]+src_len[i])  and writes
  *                 dst_base[dst_off[i] .. dst_off[i]+dst_cap[i]);
  * `dst_bytes` is the size of the buffer at dst_base (every dst_off[i]+dst_cap[i] <= dst_bytes);
- * it sizes the only scratch the decoder needs, one bit per dst byte (kept in the context).
+ * it sizes the scratch the decoder needs (kept in the context): one bit per dst byte, and for a
+ * call with n == 1 — the single-stream route, which decodes the blocks of the stream side by side
+ * and resolves back-references over the whole output at once — about 4.5 bytes per dst byte more.
  * status[i] receives the DecompressStatus, written[i] (may be NULL) the bytes produced.
  * All six arrays are DEVICE pointers; regions of different streams must not overlap.
  * Replaces one reference call per stream: decompress(src_i, dst_i) (src/decompress.cpp:402).
