@@ -36,7 +36,10 @@
 namespace sfb {
 
 constexpr uint64_t JOB_NONE = ~0ull;
-constexpr uint32_t JOB_ENDS = 1u;  // the stream ends in (or right after) this block, or it failed
+constexpr uint32_t JOB_ENDS = 1u;   // the stream ends in (or right after) this block, or it failed
+constexpr uint32_t JOB_CLEAN = 2u;  // mode 1: a Huffman block decoded up to its end-of-block symbol
+constexpr uint32_t JOB_RECS = 4u;   // mode 1: ... and all its windows are on record (WinRec)
+constexpr uint32_t JOB_USE = 8u;    // chain: on the chain, sizes and distances fit: mode 2 may write from the records
 
 struct BlockJob {
   uint64_t start_bit;  // where the block's header starts
@@ -46,7 +49,17 @@ struct BlockJob {
   uint32_t need;       // mode 1: the smallest base at which all its distances are in range
   uint32_t flags;      // mode 1: JOB_ENDS
   uint32_t next;       // mode 1: the job that starts at end_bit (0: none)
-  uint32_t pad;
+  uint32_t first_rec;  // mode 1: 1 + index of its first window record (0: none)
+};
+
+// What the counting job found out about one window of 32 spans, so that the writing job need not
+// find it out again: where each lane's span really starts and where its output goes.
+struct WinRec {
+  uint64_t b0;         // the window's first bit
+  uint32_t cut;        // first lane that meets the end of the block (32: none)
+  uint32_t next;       // 1 + index of the block's next window (0: none)
+  uint32_t s_rel[32];  // lane's true start, bits after b0
+  uint32_t start[32];  // lane's output position, bytes after the block's
 };
 
 struct FindArgs {
@@ -98,6 +111,7 @@ __global__ void chain_kernel(const FindArgs a)
   for (;;) {
     const BlockJob jb = a.jobs[j];
     a.jobs[j].base = base;
+    if ((jb.flags & JOB_RECS) && jb.need <= base && base + jb.out <= cap) a.jobs[j].flags = jb.flags | JOB_USE;
     if ((jb.flags & JOB_ENDS) || jb.need > base || base + jb.out > cap || jb.next == 0u || jb.next >= n_jobs) break;
     base += jb.out;
     j = jb.next;
@@ -136,7 +150,7 @@ __global__ void __launch_bounds__(FIND_THREADS) find_candidates_kernel(const Fin
     j0.need = 0;
     j0.flags = JOB_ENDS;
     j0.next = 0;
-    j0.pad = 0;
+    j0.first_rec = 0;
     a.jobs[0] = j0;
     *a.job_count = 1u;
   }
@@ -297,7 +311,7 @@ __global__ void __launch_bounds__(FIND_THREADS) verify_candidates_kernel(const F
     jb.need = 0;
     jb.flags = JOB_ENDS;
     jb.next = 0;
-    jb.pad = 0;
+    jb.first_rec = 0;
     a.jobs[j] = jb;
     __threadfence();  // the record before the table entry
     uint32_t slot = job_slot(p0, a.tab_mask);

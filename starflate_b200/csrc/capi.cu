@@ -23,6 +23,9 @@ namespace {
 #define SFB_POOL 96
 #define SFB_WARPS 4
 #endif
+#ifndef SFB_LANE_CTAS
+#define SFB_LANE_CTAS 2
+#endif
 #ifndef SFB_LZ_CTAS_PER_SM
 #define SFB_LZ_CTAS_PER_SM 6  /* pass-2 CTAs per SM (0 = as many as fit); see lz_warp.cuh */
 #endif
@@ -31,7 +34,7 @@ namespace {
 // 16 warps per SM) is tried first: low-entropy alphabets — short codes — fit it, and twice the
 // lanes in flight is twice the throughput of this latency-bound pass; a stream whose first
 // block does not fit is handed to a LaneCfg launch.
-using LaneCfg = sfb::Cfg<SFB_ROOT_LIT, SFB_ROOT_DIST, SFB_POOL, SFB_WARPS>;
+using LaneCfg = sfb::Cfg<SFB_ROOT_LIT, SFB_ROOT_DIST, SFB_POOL, SFB_WARPS, SFB_LANE_CTAS>;
 using SmallCfg = sfb::Cfg<6, 5, 96, 8, 2>;
 // single-stream mode (huff_stream.cuh): one warp per CTA, the large geometry
 using StreamCfg = sfb::Cfg<SFB_ROOT_LIT, SFB_ROOT_DIST, SFB_POOL, 1>;
@@ -321,14 +324,16 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
   // starts that do not fit are simply not found (their blocks are then decoded by the tail job).
   bool blocks = jump;
   if (const char* e = std::getenv("SFB200_BLOCKS")) blocks = blocks && e[0] != '0';
-  uint32_t cand_cap = 0, job_cap = 0, tab_size = 0;
+  uint32_t cand_cap = 0, job_cap = 0, tab_size = 0, rec_cap = 0;
   if (blocks) {
     const uint64_t src_bits_max = 8 * (dst_bytes + dst_bytes / 32 + 65536);
     cand_cap = static_cast<uint32_t>(std::min<uint64_t>(src_bits_max / 128 + 4096, 1ull << 30));
     job_cap = static_cast<uint32_t>(std::min<uint64_t>(src_bits_max / 2048 + 1024, 1ull << 27));
     tab_size = 1024;
     while (tab_size < 2 * job_cap) tab_size *= 2;
-    const uint64_t need = 64 + 4ull * tab_size + sizeof(sfb::BlockJob) * static_cast<uint64_t>(job_cap) + 8ull * cand_cap;
+    rec_cap = static_cast<uint32_t>(std::min<uint64_t>(src_bits_max / (16 * sfb::SPAN_BITS) + 65536, 1ull << 26));
+    const uint64_t need = 64 + 4ull * tab_size + sizeof(sfb::BlockJob) * static_cast<uint64_t>(job_cap) +
+                          8ull * cand_cap + sizeof(sfb::WinRec) * static_cast<uint64_t>(rec_cap);
     const int rc = grow(ctx, &ctx->d_find, &ctx->d_find_cap, need);
     if (rc != SFB200_RC_OK) return rc;
   }
@@ -472,6 +477,9 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
       sa.job_tab = nullptr;
       sa.tab_mask = 0;
       sa.tail_job = nullptr;
+      sa.recs = nullptr;
+      sa.rec_count = nullptr;
+      sa.rec_cap = 0;
       const uint64_t resident =
           static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->stream_ctas_per_sm);
       if (blocks) {
@@ -493,6 +501,9 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
                                              sizeof(sfb::BlockJob) * static_cast<uint64_t>(job_cap));
         f.cand_cap = cand_cap;
         f.dst_cap = dst_cap;
+        sa.recs = reinterpret_cast<sfb::WinRec*>(reinterpret_cast<uint8_t*>(f.cand) + 8ull * cand_cap);
+        sa.rec_count = counters + 3;
+        sa.rec_cap = rec_cap;
         SFB_TRY(ctx, cudaMemsetAsync(ctx->d_find, 0, 64 + 4ull * tab_size, s1));
         sfb::find_candidates_kernel<<<ctx->sm_count * 8, sfb::FIND_THREADS, 0, s1>>>(f);
         sfb::verify_candidates_kernel<<<ctx->sm_count * 4, sfb::FIND_THREADS, 0, s1>>>(f);

@@ -62,6 +62,9 @@ struct StreamArgs {
   const uint32_t* job_tab;
   uint32_t tab_mask;
   const uint32_t* tail_job;
+  WinRec* recs;         // window records: written in mode 1, read in mode 2
+  uint32_t* rec_count;  // zeroed
+  uint32_t rec_cap;
 };
 
 struct Tok {
@@ -302,12 +305,15 @@ __global__ void __launch_bounds__(32) huff_stream_kernel(const StreamArgs a)
     bool one_block = false, stop = false;
     uint64_t cap = real_cap;
     uint32_t job_need = 0;
+    bool use_recs = false, recs_ok = true, clean = false;
+    uint32_t first_rec = 0, prev_rec = 0;
     if (mode) {
       bitpos = a.jobs[si].start_bit;
       if (mode == 2u) {
         outpos = a.jobs[si].base;
         if (outpos == JOB_NONE) continue;  // not a block of the stream (or beyond its end)
         one_block = si != tail;
+        use_recs = (a.jobs[si].flags & JOB_USE) != 0u;
       } else {
         one_block = true;
         cap = 0xfffffff0ull;  // sizes are settled by the chain
@@ -348,6 +354,31 @@ __global__ void __launch_bounds__(32) huff_stream_kernel(const StreamArgs a)
           for (uint32_t i = lane; i < copy_left; i += 32u) d[i] = copy_src[i];
         outpos += copy_left;
         bitpos = 8ull * static_cast<uint64_t>(copy_src + copy_left - br.begin());
+        if (final_block) status = ST_SUCCESS;
+        continue;
+      }
+      // ---- Huffman block whose windows the counting job left on record: write, nothing else ----
+      if (use_recs) {  // (warp-uniform; the job's first block only)
+        use_recs = false;
+        const BlockJob jb = a.jobs[si];
+        for (uint32_t ri = jb.first_rec; ri != 0u;) {
+          const WinRec* const rec = a.recs + (ri - 1u);
+          const uint64_t wb0 = rec->b0;
+          const uint64_t ws = wb0 + rec->s_rel[lane];
+          const uint64_t wlim = wb0 + static_cast<uint64_t>(lane + 1u) * SPAN_BITS;
+          const uint64_t wstart = outpos + rec->start[lane];
+          const bool em = lane <= rec->cut;
+          if (em) {
+            br.seek_bit(ws < total_bits ? ws : total_bits);
+            ow.open(a.dst_base, doff + wstart, static_cast<uint32_t>(cap - wstart), a.match_bits);
+          }
+          run_span<C, true>(br, em, static_cast<uint32_t>(wlim > ws ? wlim - ws : 0u), lutb, sdi, m, lt_lit, lt_dist,
+                            ow, wstart);
+          if (em) ow.flush_tail();
+          ri = rec->next;
+        }
+        outpos += jb.out;
+        bitpos = jb.end_bit;
         if (final_block) status = ST_SUCCESS;
         continue;
       }
@@ -398,13 +429,36 @@ __global__ void __launch_bounds__(32) huff_stream_kernel(const StreamArgs a)
                                   : 0u;
           const uint32_t wmax = __reduce_max_sync(FULL, nd);
           job_need = wmax > job_need ? wmax : job_need;
+          if (recs_ok) {  // leave the window on record for the writing job
+            uint32_t ri = 0;
+            if (lane == 0) ri = atomicAdd(a.rec_count, 1u);
+            ri = __shfl_sync(FULL, ri, 0);
+            if (ri >= a.rec_cap) {
+              recs_ok = false;
+            } else {
+              WinRec* const rec = a.recs + ri;
+              rec->s_rel[lane] = static_cast<uint32_t>(s - b0);
+              rec->start[lane] = static_cast<uint32_t>(my_start);
+              if (lane == 0) {
+                rec->b0 = b0;
+                rec->cut = cut;
+                rec->next = 0;
+                if (prev_rec) a.recs[prev_rec - 1u].next = ri + 1u;
+              }
+              if (!prev_rec) first_rec = ri + 1u;
+              prev_rec = ri + 1u;
+            }
+          }
           const uint32_t total_c = __shfl_sync(FULL, inc, 31);
           outpos += total_c;
           if (cut < 32u) {
             bitpos = shfl_u64(s + r.rel, static_cast<int>(cut));
             const uint32_t cflag = __shfl_sync(FULL, r.flag, static_cast<int>(cut));
             if (cflag == 2u) status = __shfl_sync(FULL, r.st, static_cast<int>(cut));
-            else if (final_block) status = ST_SUCCESS;
+            else {
+              clean = true;
+              if (final_block) status = ST_SUCCESS;
+            }
             break;
           }
           if (outpos >= cap) {
@@ -448,7 +502,8 @@ __global__ void __launch_bounds__(32) huff_stream_kernel(const StreamArgs a)
         jb->end_bit = bitpos;
         jb->out = outpos;
         jb->need = job_need;
-        jb->flags = status >= 0 ? JOB_ENDS : 0u;
+        jb->flags = (status >= 0 ? JOB_ENDS : 0u) | (clean ? JOB_CLEAN : 0u) | (clean && recs_ok ? JOB_RECS : 0u);
+        jb->first_rec = first_rec;
         jb->next = status < 0 ? job_find(a.job_tab, a.tab_mask, a.jobs, static_cast<uint32_t>(n_units), bitpos) : 0u;
       } else if (!one_block) {
         a.status[idx] = static_cast<uint8_t>(status);

@@ -92,6 +92,7 @@ static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
 static inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz(static_cast<unsigned>(v)); }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v)
 {
   return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);

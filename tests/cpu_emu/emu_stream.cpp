@@ -14,6 +14,9 @@ static uint16_t* emu_stream_smem = nullptr;  // one warp's shared memory, seen b
 using StreamCfg = sfb::Cfg<8, 6, 96, 1>;
 
 // one stream; dst_base must be 128-byte aligned, the stream's region starts at dst_base + dst_off
+static uint32_t emu_rec_cap = 1u << 16;
+extern "C" void emu_set_rec_cap(uint32_t cap) { emu_rec_cap = cap; }
+
 static void run_warp(const sfb::StreamArgs& a)
 {
   std::vector<std::thread> lanes;
@@ -59,7 +62,8 @@ extern "C" void emu_huff_stream_jobs(const uint8_t* src, uint64_t src_len, uint8
       job_tab[slot] = k;
     }
   }
-  uint32_t job_count = n_cand + 1, tail_job = 0;
+  uint32_t job_count = n_cand + 1, tail_job = 0, rec_count = 0;
+  std::vector<sfb::WinRec> recs(emu_rec_cap + 1);
   sfb::StreamArgs a{};
   a.src_base = src;
   a.src_off = &zero;
@@ -81,6 +85,9 @@ extern "C" void emu_huff_stream_jobs(const uint8_t* src, uint64_t src_len, uint8
   a.job_tab = job_tab.data();
   a.tab_mask = tab_size - 1;
   a.tail_job = &tail_job;
+  a.recs = recs.data();
+  a.rec_count = &rec_count;
+  a.rec_cap = emu_rec_cap;
   unsigned long long counter = 0;
   a.stream_counter = &counter;
   a.mode = 1;

@@ -65,6 +65,12 @@ class Emu:
         assert rc == 0, f"emulated stream kernel wrote outside its dst region (code {rc})"
         return int(st[0]), d[:cap].tobytes(), int(wr[0])
 
+    def set_rec_cap(self, cap: int):
+        """How many window records (block_finder.cuh: WinRec) the emulated counting jobs may leave
+        behind; when they run out the writing jobs find the span starts out again."""
+        self.lib.emu_set_rec_cap.argtypes = [C.c_uint32]
+        self.lib.emu_set_rec_cap(cap)
+
     def stream_decompress_jobs(self, src: bytes, cap: int, cand, phase: int = 0, fill: int = 0xA5):
         """One stream through the blocks-side-by-side route (block_finder.cuh): counting jobs at
         the candidate block starts `cand` (bit positions; stands in for the GPU's finder kernels),

@@ -181,14 +181,17 @@ def test_single_stream_blocks_side_by_side(emu, oracle):
         (comp[: len(comp) * 2 // 3], len(plain), [s for s in starts[1:] if s < 8 * (len(comp) * 2 // 3)]),
         (comp[:40], len(plain), []),
     ]
-    for k, (src, cap, cand) in enumerate(cases):
-        ost, odst, owr, _ = oracle.decompress(src, cap)
-        st, dst, wr, on_chain, tail = emu.stream_decompress_jobs(src, cap, cand, phase=(37 * k) % 128)
-        assert (st, wr) == (ost, owr) and dst == odst, (k, st, wr, ost, owr)
-        if k == 0:
-            assert on_chain == len(starts)  # every block was decoded by its own job
-        if k == 2:
-            assert on_chain == 1 and tail == 0
+    for rec_cap in (1 << 16, 3):  # window records for every block | for the first few windows only
+        emu.set_rec_cap(rec_cap)
+        for k, (src, cap, cand) in enumerate(cases):
+            ost, odst, owr, _ = oracle.decompress(src, cap)
+            st, dst, wr, on_chain, tail = emu.stream_decompress_jobs(src, cap, cand, phase=(37 * k) % 128)
+            assert (st, wr) == (ost, owr) and dst == odst, (rec_cap, k, st, wr, ost, owr)
+            if k == 0:
+                assert on_chain == len(starts)  # every block was decoded by its own job
+            if k == 2:
+                assert on_chain == 1 and tail == 0
+    emu.set_rec_cap(1 << 16)
     # a distance that reaches before the start of the stream, in a later block: the chain must stop
     # at that block and the tail must report the reference's InvalidDistance
     w = T.BitWriter()
