@@ -309,7 +309,9 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
                                    LaneCfg::WARPS * 32;
   if (const char* e = std::getenv("SFB200_STREAM_MODE")) stream_mode = e[0] == '1' && ctx->stream_ctas_per_sm > 0;
   // One stream: pass 2 works on the whole output at once (lz_jump.cuh) instead of one warp walking it
-  bool jump = n == 1 && stream_mode;
+  // (also a FEW large streams, one after the other: sizes are only known on the device, so "large" is
+  //  judged by the room the caller gave them)
+  bool jump = stream_mode && (n == 1 || (n <= 16 && dst_bytes / n >= (1ull << 20)));
   if (const char* e = std::getenv("SFB200_JUMP")) jump = jump && e[0] != '0';
   uint64_t jump_tiles = 0;
   if (jump) {
@@ -504,25 +506,30 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
         sa.recs = reinterpret_cast<sfb::WinRec*>(reinterpret_cast<uint8_t*>(f.cand) + 8ull * cand_cap);
         sa.rec_count = counters + 3;
         sa.rec_cap = rec_cap;
-        SFB_TRY(ctx, cudaMemsetAsync(ctx->d_find, 0, 64 + 4ull * tab_size, s1));
-        sfb::find_candidates_kernel<<<ctx->sm_count * 8, sfb::FIND_THREADS, 0, s1>>>(f);
-        sfb::verify_candidates_kernel<<<ctx->sm_count * 4, sfb::FIND_THREADS, 0, s1>>>(f);
         sa.jobs = f.jobs;
         sa.job_count = f.job_count;
         sa.job_cap = job_cap;
         sa.job_tab = f.job_tab;
         sa.tab_mask = f.tab_mask;
         sa.tail_job = f.tail_job;
-        sa.idx_base = 0;
-        sa.mode = 1;
         const unsigned grid = static_cast<unsigned>(resident);
-        sfb::huff_stream_kernel<StreamCfg><<<grid, 32, StreamCfg::SMEM_BYTES, s1>>>(sa);
-        sfb::chain_kernel<<<1, 32, 0, s1>>>(f);
-        sa.mode = 2;
-        sa.stream_counter = ctr + 1;
-        sfb::huff_stream_kernel<StreamCfg><<<grid, 32, StreamCfg::SMEM_BYTES, s1>>>(sa);
-        SFB_TRY(ctx, cudaGetLastError());
-        ctx->launches += 5;
+        for (uint64_t si = 0; si < cnt; ++si) {
+          f.idx = first + si;
+          sa.idx_base = first + si;
+          SFB_TRY(ctx, cudaMemsetAsync(ctx->d_find, 0, 64 + 4ull * tab_size, s1));
+          if (si) SFB_TRY(ctx, cudaMemsetAsync(ctr, 0, 2 * sizeof(unsigned long long), s1));
+          sfb::find_candidates_kernel<<<ctx->sm_count * 8, sfb::FIND_THREADS, 0, s1>>>(f);
+          sfb::verify_candidates_kernel<<<ctx->sm_count * 4, sfb::FIND_THREADS, 0, s1>>>(f);
+          sa.mode = 1;
+          sa.stream_counter = ctr + 0;
+          sfb::huff_stream_kernel<StreamCfg><<<grid, 32, StreamCfg::SMEM_BYTES, s1>>>(sa);
+          sfb::chain_kernel<<<1, 32, 0, s1>>>(f);
+          sa.mode = 2;
+          sa.stream_counter = ctr + 1;
+          sfb::huff_stream_kernel<StreamCfg><<<grid, 32, StreamCfg::SMEM_BYTES, s1>>>(sa);
+          SFB_TRY(ctx, cudaGetLastError());
+        }
+        ctx->launches += 5 * cnt;
       } else {
         const unsigned grid = static_cast<unsigned>(cnt < resident ? cnt : resident);
         sfb::huff_stream_kernel<StreamCfg><<<grid, 32, StreamCfg::SMEM_BYTES, s1>>>(sa);
@@ -579,24 +586,26 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
       j.dst_off = dst_off;
       j.written = written;
       j.match_bits = ctx->d_bits;
-      j.idx = 0;
       j.ptr = reinterpret_cast<uint32_t*>(ctx->d_jump);
       j.tile_done = j.ptr + jump_tiles * sfb::JUMP_TILE;
       j.todo = j.tile_done + jump_tiles;
       j.open = j.todo + sfb::JUMP_MAX_ROUNDS + 1;
-      SFB_TRY(ctx, cudaMemsetAsync(j.tile_done, 0, (jump_tiles + sfb::JUMP_MAX_ROUNDS + 1) * 4, s2));
       constexpr uint64_t wpc = sfb::JUMP_THREADS / 32;
       const uint64_t want = (jump_tiles + wpc - 1) / wpc;
       const uint64_t resident = static_cast<uint64_t>(ctx->sm_count) * 8;
       const unsigned grid = static_cast<unsigned>(want < resident ? want : resident);
-      j.round = 0;
-      sfb::lz_jump_init_kernel<<<grid, sfb::JUMP_THREADS, 0, s2>>>(j);
-      for (int r = 1; r <= sfb::JUMP_MAX_ROUNDS; ++r) {
-        j.round = static_cast<uint32_t>(r);
-        sfb::lz_jump_round_kernel<<<grid, sfb::JUMP_THREADS, 0, s2>>>(j);
+      for (uint64_t si = 0; si < cnt; ++si) {
+        j.idx = first + si;
+        SFB_TRY(ctx, cudaMemsetAsync(j.tile_done, 0, (jump_tiles + sfb::JUMP_MAX_ROUNDS + 1) * 4, s2));
+        j.round = 0;
+        sfb::lz_jump_init_kernel<<<grid, sfb::JUMP_THREADS, 0, s2>>>(j);
+        for (int r = 1; r <= sfb::JUMP_MAX_ROUNDS; ++r) {
+          j.round = static_cast<uint32_t>(r);
+          sfb::lz_jump_round_kernel<<<grid, sfb::JUMP_THREADS, 0, s2>>>(j);
+        }
+        SFB_TRY(ctx, cudaGetLastError());
       }
-      SFB_TRY(ctx, cudaGetLastError());
-      ctx->launches += sfb::JUMP_MAX_ROUNDS;
+      ctx->launches += (sfb::JUMP_MAX_ROUNDS + 1) * cnt;
     } else {
       constexpr uint64_t wpc = sfb::LZ_THREADS / 32;
       const uint64_t want = (cnt + wpc - 1) / wpc;
