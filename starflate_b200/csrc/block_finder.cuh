@@ -154,6 +154,17 @@ __global__ void __launch_bounds__(FIND_THREADS) find_candidates_kernel(const Fin
     a.jobs[0] = j0;
     *a.job_count = 1u;
   }
+  // three code-length-code lengths (9 bits) -> their Kraft sum in units of 2^-7 | number of codes << 16
+  __shared__ uint32_t s_kraft[512];
+  for (uint32_t x = threadIdx.x; x < 512u; x += blockDim.x) {
+    uint32_t e = 0;
+    for (uint32_t c = 0; c < 3; ++c) {
+      const uint32_t len = (x >> (3u * c)) & 7u;
+      if (len) e += (128u >> len) + 0x10000u;
+    }
+    s_kraft[x] = e;
+  }
+  __syncthreads();
   if (slen >= 0xffffff00ull) return;
   const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 3u);
   const uint64_t total_bits = 8ull * slen;
@@ -161,14 +172,11 @@ __global__ void __launch_bounds__(FIND_THREADS) find_candidates_kernel(const Fin
   const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
   for (uint64_t i = gtid; i < n_words; i += stride) {
     const uint32_t w0 = find_word(src, slen, sh, i), w1 = find_word(src, slen, sh, i + 1);
-    // quick tests on the 32 positions that start in w0
-    uint32_t pass = 0;
-#pragma unroll
-    for (uint32_t j = 0; j < 32; ++j) {
-      const uint32_t x = __funnelshift_r(w0, w1, j);
-      const bool ok = ((x >> 1) & 3u) == 2u && ((x >> 3) & 31u) <= 29u && ((x >> 8) & 31u) <= 29u;
-      pass |= static_cast<uint32_t>(ok) << j;
-    }
+    // quick tests on the 32 positions that start in w0, all at once: bit j of A(k) is bit k of
+    // position j's header.  BTYPE == 2: bit 1 clear, bit 2 set; HLIT (bits 3-7) and HDIST (bits
+    // 8-12) <= 29: their upper four bits not all set.
+    auto A = [&](uint32_t k) { return __funnelshift_r(w0, w1, k); };
+    uint32_t pass = ~A(1) & A(2) & ~(A(4) & A(5) & A(6) & A(7)) & ~(A(9) & A(10) & A(11) & A(12));
     if (pass == 0) continue;
     const uint32_t w2 = find_word(src, slen, sh, i + 2), w3 = find_word(src, slen, sh, i + 3);
     const uint64_t lo64 = (static_cast<uint64_t>(w1) << 32) | w0, hi64 = (static_cast<uint64_t>(w3) << 32) | w2;
@@ -181,16 +189,12 @@ __global__ void __launch_bounds__(FIND_THREADS) find_candidates_kernel(const Fin
       const uint32_t ncl = hclen + 4u;
       if (static_cast<uint64_t>(p) + 17u + 3u * ncl > total_bits) continue;
       const uint32_t s = j + 17u;  // 17 .. 48
-      uint64_t v = (lo64 >> s) | (hi64 << (64u - s));
-      uint32_t kraft = 0, used = 0;
+      // the ncl 3-bit lengths, three at a time through the table: Kraft sum and number of codes
+      const uint64_t v = ((lo64 >> s) | (hi64 << (64u - s))) & ((1ull << (3u * ncl)) - 1ull);
+      uint32_t acc = 0;
 #pragma unroll
-      for (uint32_t c = 0; c < 19; ++c) {
-        const uint32_t len = c < ncl ? static_cast<uint32_t>(v) & 7u : 0u;
-        kraft += len ? 128u >> len : 0u;
-        used += len != 0u;
-        v >>= 3;
-      }
-      if (kraft != 128u || used < 2u) continue;
+      for (uint32_t c = 0; c < 7; ++c) acc += s_kraft[static_cast<uint32_t>(v >> (9u * c)) & 511u];
+      if ((acc & 0xffffu) != 128u || (acc >> 16) < 2u) continue;
       const uint32_t at = atomicAdd(a.cand_count, 1u);
       if (at < a.cand_cap) a.cand[at] = static_cast<uint64_t>(p);
     }
