@@ -313,11 +313,16 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
   //  judged by the room the caller gave them)
   bool jump = stream_mode && (n == 1 || (n <= 16 && dst_bytes / n >= (1ull << 20)));
   if (const char* e = std::getenv("SFB200_JUMP")) jump = jump && e[0] != '0';
-  uint64_t jump_tiles = 0;
+  uint64_t jump_tiles = 0, stripe_tiles = 1ull << 23;  // (one stripe unless SFB200_JUMP_STRIPE_MB says otherwise)
   if (jump) {
     jump_tiles = (dst_bytes + delta + 128 + sfb::JUMP_TILE - 1) / sfb::JUMP_TILE + 1;
+    if (const char* e = std::getenv("SFB200_JUMP_STRIPE_MB")) {
+      const long mb = std::atol(e);
+      if (mb > 0) stripe_tiles = static_cast<uint64_t>(mb) * ((1u << 20) / sfb::JUMP_TILE);
+    }
+    const uint64_t stripes = (jump_tiles + stripe_tiles - 1) / stripe_tiles;
     const uint64_t need = jump_tiles * sfb::JUMP_TILE * 4 + jump_tiles * 4 * (1 + sfb::JUMP_TILE / 128) +
-                          (sfb::JUMP_MAX_ROUNDS + 1) * 4;
+                          stripes * (sfb::JUMP_MAX_ROUNDS + 1) * 4;
     const int rc = grow(ctx, &ctx->d_jump, &ctx->d_jump_cap, need);
     if (rc != SFB200_RC_OK) return rc;
   }
@@ -589,23 +594,40 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
       j.ptr = reinterpret_cast<uint32_t*>(ctx->d_jump);
       j.tile_done = j.ptr + jump_tiles * sfb::JUMP_TILE;
       j.todo = j.tile_done + jump_tiles;
-      j.open = j.todo + sfb::JUMP_MAX_ROUNDS + 1;
+      const uint64_t stripes = (jump_tiles + stripe_tiles - 1) / stripe_tiles;
+      uint32_t* const todo0 = j.todo;
+      j.open = j.todo + stripes * (sfb::JUMP_MAX_ROUNDS + 1);
       constexpr uint64_t wpc = sfb::JUMP_THREADS / 32;
-      const uint64_t want = (jump_tiles + wpc - 1) / wpc;
       const uint64_t resident = static_cast<uint64_t>(ctx->sm_count) * 8;
-      const unsigned grid = static_cast<unsigned>(want < resident ? want : resident);
       for (uint64_t si = 0; si < cnt; ++si) {
         j.idx = first + si;
-        SFB_TRY(ctx, cudaMemsetAsync(j.tile_done, 0, (jump_tiles + sfb::JUMP_MAX_ROUNDS + 1) * 4, s2));
+        SFB_TRY(ctx, cudaMemsetAsync(j.tile_done, 0, (jump_tiles + stripes * (sfb::JUMP_MAX_ROUNDS + 1)) * 4, s2));
+        // pointers of stripe sp + 1 are set up BEFORE the rounds of stripe sp: the match that reaches
+        // into a stripe from the left is read from its descriptor, which the rounds of the stripe
+        // before replace by the final bytes
+        auto set_stripe = [&](uint64_t sp) {
+          j.tile_lo = static_cast<uint32_t>(sp * stripe_tiles);
+          j.tile_hi = static_cast<uint32_t>(std::min<uint64_t>(jump_tiles, (sp + 1) * stripe_tiles));
+          j.todo = todo0 + sp * (sfb::JUMP_MAX_ROUNDS + 1);
+          const uint64_t want = (j.tile_hi - j.tile_lo + wpc - 1) / wpc;
+          return static_cast<unsigned>(want < resident ? want : resident);
+        };
         j.round = 0;
-        sfb::lz_jump_init_kernel<<<grid, sfb::JUMP_THREADS, 0, s2>>>(j);
-        for (int r = 1; r <= sfb::JUMP_MAX_ROUNDS; ++r) {
-          j.round = static_cast<uint32_t>(r);
-          sfb::lz_jump_round_kernel<<<grid, sfb::JUMP_THREADS, 0, s2>>>(j);
+        sfb::lz_jump_init_kernel<<<set_stripe(0), sfb::JUMP_THREADS, 0, s2>>>(j);
+        for (uint64_t sp = 0; sp < stripes; ++sp) {
+          if (sp + 1 < stripes) {
+            j.round = 0;
+            sfb::lz_jump_init_kernel<<<set_stripe(sp + 1), sfb::JUMP_THREADS, 0, s2>>>(j);
+          }
+          const unsigned grid = set_stripe(sp);
+          for (int r = 1; r <= sfb::JUMP_MAX_ROUNDS; ++r) {
+            j.round = static_cast<uint32_t>(r);
+            sfb::lz_jump_round_kernel<<<grid, sfb::JUMP_THREADS, 0, s2>>>(j);
+          }
+          SFB_TRY(ctx, cudaGetLastError());
         }
-        SFB_TRY(ctx, cudaGetLastError());
       }
-      ctx->launches += (sfb::JUMP_MAX_ROUNDS + 1) * cnt;
+      ctx->launches += (sfb::JUMP_MAX_ROUNDS + 1) * cnt * stripes;
     } else {
       constexpr uint64_t wpc = sfb::LZ_THREADS / 32;
       const uint64_t want = (cnt + wpc - 1) / wpc;

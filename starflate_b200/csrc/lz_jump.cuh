@@ -14,7 +14,13 @@
 // (a 1 GiB run of one byte is a chain of 2^30 hops: 30 rounds).  Concurrent updates are benign:
 // whatever a thread reads through ptr[p], old or new, is an ancestor of i.
 //
-// The output is cut into tiles of JUMP_TILE bytes, one warp per tile and round.  A tile in which a
+// The output can be done in STRIPES, one after the other, each to the end: every target in an
+// earlier stripe is then a final byte — a root — which bounds the chains by the stripe, and a small
+// stripe's pointers stay in the L2.  Measured on B200 (256 MiB of text): 8 MiB stripes 9.9 ms, one
+// stripe 6.0 ms — a round over a small stripe is a short kernel bound by launch and memory latency,
+// not by bandwidth — so the default is ONE stripe (SFB200_JUMP_STRIPE_MB sets another size).
+//
+// A stripe is cut into tiles of JUMP_TILE bytes, one warp per tile and round.  A tile in which a
 // round changed nothing has only roots as targets; roots never change, so the tile is FINAL: the
 // warp gathers its bytes (dst[i] <- dst[ptr[i]]; only roots are read and no root is rewritten
 // with a different value) and marks it done.  Most bytes of text are final after a few rounds
@@ -31,7 +37,7 @@
 namespace sfb {
 
 constexpr uint32_t JUMP_TILE = 1024;      // bytes of output per warp and round
-constexpr int JUMP_MAX_ROUNDS = 32;       // 2^32 hops: more than a 32-bit position can chain
+constexpr int JUMP_MAX_ROUNDS = 22;       // 3^21 hops > 2^32 positions, + 1 to see that nothing moved
 constexpr int JUMP_THREADS = 256;
 
 struct JumpArgs {
@@ -44,8 +50,10 @@ struct JumpArgs {
   uint32_t* ptr;        // one per byte of the view [0, q + written) rounded up to a tile
   uint32_t* tile_done;  // one per tile, zeroed before the first round
   uint32_t* open;       // JUMP_TILE / 128 words per tile: groups of 4 pointers that are not final yet
-  uint32_t* todo;       // [JUMP_MAX_ROUNDS + 1] zeroed; todo[r] != 0: round r left tiles open
+  uint32_t* todo;       // this stripe's [JUMP_MAX_ROUNDS + 1], zeroed; todo[r] != 0: round r left tiles open
   uint32_t round;       // 0 = set up the pointers, then 1 .. JUMP_MAX_ROUNDS
+  uint32_t tile_lo;     // the stripe: tiles [tile_lo, tile_hi); everything before it is final already
+  uint32_t tile_hi;
 };
 
 // Round 0: the pointers.  A warp takes a tile, finds the match that reaches into it from the
@@ -66,9 +74,10 @@ __global__ void __launch_bounds__(JUMP_THREADS) lz_jump_init_kernel(const JumpAr
   const uint32_t end = q + static_cast<uint32_t>(wr);
   const uint32_t* const pw = reinterpret_cast<const uint32_t*>(base) + lane;
   const uint32_t* const bm = a.match_bits + ((off & ~127ull) >> 5);
-  const uint32_t n_tiles = (end + JUMP_TILE - 1u) / JUMP_TILE;
+  const uint32_t all_tiles = (end + JUMP_TILE - 1u) / JUMP_TILE;
+  const uint32_t n_tiles = all_tiles < a.tile_hi ? all_tiles : a.tile_hi;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < n_tiles; tile += warps) {
+  for (uint32_t tile = a.tile_lo + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); tile < n_tiles; tile += warps) {
     const uint32_t T = tile * JUMP_TILE;
     // ---- the match carried in: last head in [T - 288, T), nine bitmap words, lanes 0..8 -----------
     uint32_t c_o = 0, c_end = 0, c_d = 1;
@@ -149,7 +158,7 @@ __global__ void __launch_bounds__(JUMP_THREADS) lz_jump_init_kernel(const JumpAr
       cw = ncw;
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) a.todo[0] = 1u;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.tile_lo < n_tiles) a.todo[0] = 1u;
 }
 
 // Rounds 1 .. JUMP_MAX_ROUNDS.  Per tile, 8 words of `open` bits say which 16-byte groups of
@@ -167,11 +176,13 @@ __global__ void __launch_bounds__(JUMP_THREADS) lz_jump_round_kernel(const JumpA
   uint8_t* const base = a.dst_base + (off & ~127ull);
   const uint32_t q = static_cast<uint32_t>(off & 127u);
   const uint32_t end = q + static_cast<uint32_t>(wr);
-  const uint32_t n_tiles = (end + JUMP_TILE - 1u) / JUMP_TILE;
+  const uint32_t all_tiles = (end + JUMP_TILE - 1u) / JUMP_TILE;
+  const uint32_t n_tiles = all_tiles < a.tile_hi ? all_tiles : a.tile_hi;
   const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
   const bool first = a.round == 1u;
+  const uint32_t lo = a.tile_lo * JUMP_TILE;  // targets below this are final bytes of earlier stripes: roots
   bool open_any = false;
-  for (uint32_t tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < n_tiles; tile += warps) {
+  for (uint32_t tile = a.tile_lo + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); tile < n_tiles; tile += warps) {
     if (a.tile_done[tile]) continue;  // (warp-uniform)
     const uint32_t T = tile * JUMP_TILE;
     uint32_t* const om = a.open + static_cast<size_t>(tile) * ROWS;
@@ -186,16 +197,17 @@ __global__ void __launch_bounds__(JUMP_THREADS) lz_jump_round_kernel(const JumpA
       bool ch = false;
       if (((mask >> lane) & 1u) && wp < end) {
         const uint4 p = *reinterpret_cast<const uint4*>(a.ptr + wp);
+        auto hop = [&](uint32_t t) { return t < lo ? t : a.ptr[t]; };
         uint4 g;
-        g.x = a.ptr[p.x];
-        g.y = a.ptr[p.y];
-        g.z = a.ptr[p.z];
-        g.w = a.ptr[p.w];
+        g.x = hop(p.x);
+        g.y = hop(p.y);
+        g.z = hop(p.z);
+        g.w = hop(p.w);
         if ((g.x != p.x) | (g.y != p.y) | (g.z != p.z) | (g.w != p.w)) {
-          g.x = a.ptr[g.x];
-          g.y = a.ptr[g.y];
-          g.z = a.ptr[g.z];
-          g.w = a.ptr[g.w];
+          g.x = hop(g.x);
+          g.y = hop(g.y);
+          g.z = hop(g.z);
+          g.w = hop(g.w);
           *reinterpret_cast<uint4*>(a.ptr + wp) = g;
           ch = true;
         }

@@ -378,3 +378,23 @@ def test_full_size_single_stream_round_trip(ctx, shape, size):
     ctx.checksum_batch_device(want, one(0), written, sums[1:])
     torch.cuda.synchronize(dev)
     assert int(sums[0].item()) == int(sums[1].item())
+
+
+@pytest.mark.parametrize("stripe_mb", ["0", "8"])
+def test_single_stream_route_across_pass2_stripes(monkeypatch, stripe_mb):
+    """Pass 2 of the single-stream route, in one piece (default) and in 8 MiB stripes
+    (SFB200_JUMP_STRIPE_MB): matches that straddle a stripe boundary (every boundary lies inside a
+    length-258 match here), chains as long as the output (a run of one byte), plain text."""
+    import starflate_b200 as S
+    monkeypatch.setenv("SFB200_JUMP_STRIPE_MB", stripe_mb)
+    ctx = S.Context(0)
+    size = 20 << 20
+    inputs = [b"abcdefg" * (size // 7), b"\x00" * size, T.big_text(24 << 20, 31),
+              (b"xy" * 70000 + T.text_like(100000, 5)) * (size // 240000)]
+    for k, plain in enumerate(inputs):
+        comp = T.raw_deflate(plain, 9 if k != 2 else 6)
+        st, wr, dst, intact = _one_stream_per_call(ctx, comp, len(plain) + 7, phase=(53 * k) % 128, src_phase=k)
+        assert (st, wr) == (0, len(plain)) and intact, (k, st, wr)
+        assert dst[: len(plain)] == plain, k
+        assert dst[len(plain):] == b"\xa5" * 7
+    ctx.close()

@@ -55,6 +55,10 @@ def run(mib, modes=("blocks", "warp", "lane"), reps=3):
               f"pass1 {best[1]:.2f} ms pass2 {best[2]:.2f} ms -> {len(plain) / ms / 1e6:.3f} GB/s, "
               f"bit-exact vs zlib input: {ok}", flush=True)
         ctx.close()
+        if not ok:
+            bad = torch.nonzero(dst[:len(plain)] != want).flatten()
+            print("status", int(status.item()), "written", int(written.item()), "mismatches", bad.numel(),
+                  "first", bad[:8].tolist(), "last", bad[-4:].tolist())
         assert ok
     assert zlib.decompress(comp, -15) == plain
 
