@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SFB200_ABI_VERSION 2
+#define SFB200_ABI_VERSION 3
 
 /* starflate::DecompressStatus, numeric values preserved (src/decompress.hpp:13-23). */
 enum sfb200_status {
@@ -101,6 +101,19 @@ int sfb200_decompress_batch_host(sfb200_ctx* ctx, const uint8_t* src, uint64_t s
  * DecompressStatus; *written (may be NULL) the bytes produced. */
 int sfb200_decompress(sfb200_ctx* ctx, const uint8_t* src, size_t src_len, uint8_t* dst,
                       size_t dst_cap, uint8_t* status, uint64_t* written);
+
+/* Size discovery (extension).  The reference's decompress() returns no size and
+ * requires the caller to bring a dst that is large enough (src/decompress.hpp:57-64).  This runs
+ * the Huffman layer of every stream without storing anything: size[i] receives the number of bytes
+ * decompress(src_i, dst) would produce into a dst without a limit, status[i] the status it would
+ * return (Success, or the error that ends the stream; size[i] is then the bytes produced before
+ * it).  No dst, no scratch.  All arrays are DEVICE pointers; asynchronous on `cuda_stream`.
+ * Precondition: src_len[i] < 2^32 - 256, decompressed size < 2^32 - 528 (else SFB200_ERROR or
+ * SFB200_DST_TOO_SMALL respectively). */
+int sfb200_decompressed_size_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
+                                          const uint64_t* src_off, const uint64_t* src_len,
+                                          uint8_t* status, uint64_t* size, uint64_t n,
+                                          void* cuda_stream);
 
 /* Position-weighted 64-bit checksum of each stream's output region [0, len[i]) computed on the
  * device (used by tests/bench to verify multi-GiB outputs without a device->host copy):

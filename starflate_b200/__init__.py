@@ -131,6 +131,23 @@ class Context:
             written.data_ptr() if written is not None else None, n, stream)
         self._check(rc, "sfb200_decompress_batch_device")
 
+    def decompressed_size_batch_device(self, src, src_off, src_len, status, size, stream=None):
+        """Size discovery: status[i] / size[i] of a decode into an unlimited dst; nothing is stored."""
+        import torch
+        n = src_off.numel()
+        assert src.is_cuda and src.dtype == torch.uint8
+        for t in (src_off, src_len, size):
+            assert t.is_cuda and t.dtype == torch.int64 and t.is_contiguous() and t.numel() == n
+        assert status.is_cuda and status.dtype == torch.uint8 and status.numel() == n
+        if stream is None:
+            stream = torch.cuda.current_stream(src.device).cuda_stream
+        self.lib.sfb200_decompressed_size_batch_device.argtypes = [C.c_void_p] * 6 + [C.c_uint64, C.c_void_p]
+        self.lib.sfb200_decompressed_size_batch_device.restype = C.c_int
+        rc = self.lib.sfb200_decompressed_size_batch_device(self.h, src.data_ptr(), src_off.data_ptr(),
+                                                            src_len.data_ptr(), status.data_ptr(),
+                                                            size.data_ptr(), n, stream)
+        self._check(rc, "sfb200_decompressed_size_batch_device")
+
     def checksum_batch_device(self, base, off, length, out, stream=None):
         import torch
         n = off.numel()

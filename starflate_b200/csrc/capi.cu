@@ -650,6 +650,54 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
   return SFB200_RC_OK;
 }
 
+int sfb200_decompressed_size_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
+                                          const uint64_t* src_off, const uint64_t* src_len,
+                                          uint8_t* status, uint64_t* size, uint64_t n,
+                                          void* cuda_stream)
+{
+  if (!ctx) return SFB200_RC_BAD_ARGUMENT;
+  if (n == 0) return SFB200_RC_OK;
+  if (!src_off || !src_len || !status || !size) return SFB200_RC_BAD_ARGUMENT;
+  SFB_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  ctx->ev_valid = false;
+  SFB_TRY(ctx, cudaMemsetAsync(ctx->d_counter, 0, kCountersPerWave * sizeof(unsigned long long), st));
+  sfb::BatchArgs a;
+  a.src_base = src_base;
+  a.src_off = src_off;
+  a.src_len = src_len;
+  a.dst_base = nullptr;  // the counting writer never touches dst, its capacities or the bitmap
+  a.dst_delta = 0;
+  a.dst_off = nullptr;
+  a.dst_cap = nullptr;
+  a.status = status;
+  a.written = size;
+  a.n = n;
+  a.idx_base = 0;
+  a.group_counter = ctx->d_counter + 1;
+  a.lens_scratch = ctx->d_lens;
+  a.match_bits = nullptr;
+  a.defer_list = nullptr;
+  a.defer_count = nullptr;
+  a.todo_list = nullptr;
+  a.todo_count = nullptr;
+  auto kern = sfb::huff_lanes_kernel<LaneCfg, true>;
+  static bool configured = false;  // (per process; the attribute belongs to the function)
+  if (!configured) {
+    SFB_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LaneCfg::SMEM_BYTES));
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    configured = true;
+  }
+  const uint64_t groups = (n + 31) / 32;
+  const uint64_t want = (groups + LaneCfg::WARPS - 1) / LaneCfg::WARPS;
+  const uint64_t resident = static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->ctas_per_sm);
+  const unsigned grid = static_cast<unsigned>(want < resident ? want : resident);
+  kern<<<grid, LaneCfg::WARPS * 32, LaneCfg::SMEM_BYTES, st>>>(a);
+  SFB_TRY(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  return SFB200_RC_OK;
+}
+
 int sfb200_last_pass_ms(sfb200_ctx* ctx, float* out3)
 {
   if (!ctx || !out3 || !ctx->ev_valid) return SFB200_RC_BAD_ARGUMENT;

@@ -48,6 +48,11 @@ namespace sfb {
 // Per-lane output window of pass 1.
 // Invariant: bytes [vpos & ~7, vpos) of the output live in the low bytes of `obuf`, its higher
 // bytes are zero; every byte below vpos & ~7 that pass 2 will not overwrite is in memory.
+struct TokWin;
+struct CountWin;
+template <bool COUNT> struct WinOf { using type = TokWin; };
+template <> struct WinOf<true> { using type = CountWin; };
+
 struct TokWin {
   uint8_t* al;      // 8-byte aligned address of virtual position 0
   uint32_t lead;    // dst start within the first word (0..7): virtual position of byte 0
@@ -163,6 +168,31 @@ struct TokWin {
   }
 };
 
+// The writer of the size-discovery mode (huff_lanes_kernel<C, true>): same interface, keeps only
+// the position — nothing is stored, dst and the bitmap are never touched.
+struct CountWin {
+  uint8_t* al;
+  uint32_t lead, vpos, vend;
+  __device__ __forceinline__ void open(uint8_t*, uint64_t, uint32_t cap, uint32_t*)
+  {
+    al = nullptr;
+    lead = 0;
+    vpos = 0;
+    vend = cap;
+  }
+  __device__ __forceinline__ void park()
+  {
+    al = nullptr;
+    lead = vpos = vend = 0;
+  }
+  __device__ __forceinline__ uint32_t written() const { return vpos; }
+  __device__ __forceinline__ uint32_t room() const { return vend - vpos; }
+  __device__ __forceinline__ void emit(uint32_t, uint32_t n, uint32_t skipn, bool) { vpos += n + skipn; }
+  __device__ __forceinline__ void spill_pending() const {}
+  __device__ __forceinline__ void jump(uint32_t n) { vpos += n; }
+  __device__ __forceinline__ void flush_tail() const {}
+};
+
 __device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src)
 {
   const uint32_t lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v), src);
@@ -187,7 +217,11 @@ constexpr uint32_t LANES = 32;
 //            exactly one token (literal | end of block | match) and emits it through the one
 //            emit() site; lanes waiting for the next header (or finished) idle until the
 //            round ends.
-template <class C>
+//
+// COUNT = true is the size-discovery mode (the reference returns no size and asks
+// the caller to know it): the same decode with a writer that stores nothing and no capacity
+// limit; status[i] / written[i] are what a decode into a large enough dst would return.
+template <class C, bool COUNT = false>
 __global__ void __launch_bounds__(C::WARPS * 32, C::CTAS)
 huff_lanes_kernel(const BatchArgs a)
 {
@@ -237,7 +271,7 @@ huff_lanes_kernel(const BatchArgs a)
     int state = S_DONE;
     int status = ST_SUCCESS;
     BitReader br;
-    TokWin ow;
+    typename WinOf<COUNT>::type ow;
     // lanes without a stream still run the (predicated-off) decode stage
     br.park(ring);
     ow.park();
@@ -249,14 +283,14 @@ huff_lanes_kernel(const BatchArgs a)
     bool first_header = true;  // nothing of this stream has been decided yet
     if (live) {
       const uint64_t slen = a.src_len[idx];
-      const uint64_t cap = a.dst_cap[idx];
+      const uint64_t cap = COUNT ? 0xfffffef0ull : a.dst_cap[idx];
       if (slen >= 0xffffff00ull || cap >= 0xffffff00ull) {
         a.status[idx] = ST_ERROR;  // outside the batch precondition
         a.written[idx] = 0;
         live = false;
       } else {
         br.open(a.src_base + a.src_off[idx], static_cast<uint32_t>(slen), ring);
-        ow.open(a.dst_base, a.dst_off[idx] + a.dst_delta, static_cast<uint32_t>(cap), a.match_bits);
+        ow.open(a.dst_base, COUNT ? 0ull : a.dst_off[idx] + a.dst_delta, static_cast<uint32_t>(cap), a.match_bits);
         state = S_HEADER;
       }
     }
@@ -286,7 +320,7 @@ huff_lanes_kernel(const BatchArgs a)
             shfl_u64(reinterpret_cast<uint64_t>(ow.al + ow.vpos), owner));
         const uint32_t len = __shfl_sync(FULL, copy_left, owner);
         __syncwarp();
-        {
+        if constexpr (!COUNT) {
           // dst-aligned 32-bit words, each funnelled from the two aligned src words it spans
           // (src words are only read where they hold at least one payload byte)
           const uint32_t head = min(len, static_cast<uint32_t>(-reinterpret_cast<intptr_t>(d)) & 3u);

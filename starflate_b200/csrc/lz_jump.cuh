@@ -187,32 +187,47 @@ __global__ void __launch_bounds__(JUMP_THREADS) lz_jump_round_kernel(const JumpA
     const uint32_t T = tile * JUMP_TILE;
     uint32_t* const om = a.open + static_cast<size_t>(tile) * ROWS;
     // my row's mask of open groups (lane j < ROWS holds row j's)
-    uint32_t mine = first ? FULL : (lane < ROWS ? om[lane] : 0u);
-    uint32_t still = 0;  // row masks after this round, gathered in lane j
+    const uint32_t mine = first ? FULL : (lane < ROWS ? om[lane] : 0u);
+    auto hop = [&](uint32_t t) { return t < lo ? t : a.ptr[t]; };
+    // All rows' loads are issued before anything is stored (the compiler must assume that a store
+    // to ptr[] changes what the next row reads, and would otherwise run the rows one after the
+    // other: eight chains of three dependent loads instead of one).
+    uint4 p[ROWS], g[ROWS];
+    bool act[ROWS], ch[ROWS];
 #pragma unroll
     for (uint32_t j = 0; j < ROWS; ++j) {
       const uint32_t mask = __shfl_sync(FULL, mine, static_cast<int>(j));
-      if (mask == 0u) continue;  // (warp-uniform)
       const uint32_t wp = T + 128u * j + 4u * lane;
-      bool ch = false;
-      if (((mask >> lane) & 1u) && wp < end) {
-        const uint4 p = *reinterpret_cast<const uint4*>(a.ptr + wp);
-        auto hop = [&](uint32_t t) { return t < lo ? t : a.ptr[t]; };
-        uint4 g;
-        g.x = hop(p.x);
-        g.y = hop(p.y);
-        g.z = hop(p.z);
-        g.w = hop(p.w);
-        if ((g.x != p.x) | (g.y != p.y) | (g.z != p.z) | (g.w != p.w)) {
-          g.x = hop(g.x);
-          g.y = hop(g.y);
-          g.z = hop(g.z);
-          g.w = hop(g.w);
-          *reinterpret_cast<uint4*>(a.ptr + wp) = g;
-          ch = true;
-        }
+      act[j] = ((mask >> lane) & 1u) && wp < end;
+      p[j] = make_uint4(wp, wp + 1u, wp + 2u, wp + 3u);
+      if (act[j]) p[j] = *reinterpret_cast<const uint4*>(a.ptr + wp);
+    }
+#pragma unroll
+    for (uint32_t j = 0; j < ROWS; ++j) {
+      g[j] = p[j];
+      if (act[j]) {
+        g[j].x = hop(p[j].x);
+        g[j].y = hop(p[j].y);
+        g[j].z = hop(p[j].z);
+        g[j].w = hop(p[j].w);
       }
-      const uint32_t nm = __ballot_sync(FULL, ch);
+    }
+#pragma unroll
+    for (uint32_t j = 0; j < ROWS; ++j) {
+      ch[j] = (g[j].x != p[j].x) | (g[j].y != p[j].y) | (g[j].z != p[j].z) | (g[j].w != p[j].w);
+      if (ch[j]) {
+        g[j].x = hop(g[j].x);
+        g[j].y = hop(g[j].y);
+        g[j].z = hop(g[j].z);
+        g[j].w = hop(g[j].w);
+      }
+    }
+    uint32_t still = 0;  // row masks after this round, gathered in lane j
+#pragma unroll
+    for (uint32_t j = 0; j < ROWS; ++j) {
+      const uint32_t wp = T + 128u * j + 4u * lane;
+      if (ch[j]) *reinterpret_cast<uint4*>(a.ptr + wp) = g[j];
+      const uint32_t nm = __ballot_sync(FULL, ch[j]);
       if (lane == j) still = nm;
     }
     const bool open_tile = __any_sync(FULL, still != 0u);
@@ -221,20 +236,32 @@ __global__ void __launch_bounds__(JUMP_THREADS) lz_jump_round_kernel(const JumpA
       open_any = true;
       continue;
     }
-    // final: every target is a root
+    // final: every target is a root.  (p[] holds the final pointers of the groups that were still
+    // open; the others are read again.)
+    uint32_t v[ROWS];
+#pragma unroll
+    for (uint32_t j = 0; j < ROWS; ++j) {
+      const uint32_t wp = T + 128u * j + 4u * lane;
+      if (!act[j] && wp < end) p[j] = *reinterpret_cast<const uint4*>(a.ptr + wp);
+    }
+#pragma unroll
+    for (uint32_t j = 0; j < ROWS; ++j) {
+      const uint32_t wp = T + 128u * j + 4u * lane;
+      v[j] = 0;
+      if (wp < end && wp + 4u > q)
+        v[j] = static_cast<uint32_t>(base[p[j].x]) | (static_cast<uint32_t>(base[p[j].y]) << 8) |
+               (static_cast<uint32_t>(base[p[j].z]) << 16) | (static_cast<uint32_t>(base[p[j].w]) << 24);
+    }
 #pragma unroll
     for (uint32_t j = 0; j < ROWS; ++j) {
       const uint32_t wp = T + 128u * j + 4u * lane;
       if (wp >= end || wp + 4u <= q) continue;
-      const uint4 p = *reinterpret_cast<const uint4*>(a.ptr + wp);
-      const uint32_t v = static_cast<uint32_t>(base[p.x]) | (static_cast<uint32_t>(base[p.y]) << 8) |
-                         (static_cast<uint32_t>(base[p.z]) << 16) | (static_cast<uint32_t>(base[p.w]) << 24);
       if (wp >= q && wp + 4u <= end) {
-        *reinterpret_cast<uint32_t*>(base + wp) = v;
+        *reinterpret_cast<uint32_t*>(base + wp) = v[j];
       } else {  // first / last word of the stream: only our bytes
 #pragma unroll
         for (uint32_t b = 0; b < 4; ++b)
-          if (wp + b >= q && wp + b < end) base[wp + b] = static_cast<uint8_t>(v >> (8u * b));
+          if (wp + b >= q && wp + b < end) base[wp + b] = static_cast<uint8_t>(v[j] >> (8u * b));
       }
     }
     if (lane == 0) a.tile_done[tile] = 1u;

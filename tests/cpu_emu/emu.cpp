@@ -128,6 +128,36 @@ extern "C" int emu_decompress_batch(const uint8_t* src, const uint64_t* src_off,
   return 0;
 }
 
+// Size discovery (huff_lanes_kernel<C, true>): no dst at all — every dst-side pointer is null, so
+// any store the counting mode did would crash the test.
+extern "C" void emu_decompressed_size(const uint8_t* src, const uint64_t* src_off, const uint64_t* src_len,
+                                      uint8_t* status, uint64_t* size, uint64_t n)
+{
+  std::vector<uint16_t> smem(EmuCfg::SMEM_BYTES / 2 + 64, 0xDEAD);
+  std::vector<uint32_t> lens(sfb::SCRATCH_WORDS * 32, 0xDEADBEEFu);
+  emu_smem = smem.data();
+  blockDim.x = 1;
+  gridDim.x = 1;
+  for (uint64_t i = 0; i < n; ++i) {
+    std::vector<uint8_t> sbuf(src_len[i] + 64, 0xEE);
+    if (src_len[i]) std::memcpy(sbuf.data() + 16, src + src_off[i], src_len[i]);
+    unsigned long long counter = 0;
+    const uint64_t zero = 0;
+    sfb::BatchArgs a{};
+    a.src_base = sbuf.data() + 16;
+    a.src_off = &zero;
+    a.src_len = &src_len[i];
+    a.status = &status[i];
+    a.written = &size[i];
+    a.n = 1;
+    a.group_counter = &counter;
+    a.lens_scratch = lens.data();
+    threadIdx.x = 0;
+    blockIdx.x = 0;
+    sfb::huff_lanes_kernel<EmuCfg, true>(a);
+  }
+}
+
 extern "C" void emu_stats(unsigned long long* out)
 {
   out[0] = emu_stat_tokens;

@@ -50,6 +50,16 @@ class Emu:
         assert rc == 0, f"emulated kernel wrote outside a dst region (code {rc})"
         return st, wr
 
+    def decompressed_size(self, b):
+        """Size discovery mode of pass 1 over a tests.deflate_tools.Batch -> (status, size)."""
+        self.lib.emu_decompressed_size.argtypes = [_u8p, _u64p, _u64p, _u8p, _u64p, C.c_uint64]
+        st = np.zeros(b.n, np.uint8)
+        sz = np.zeros(b.n, np.uint64)
+        p = lambda a, t: a.ctypes.data_as(t)
+        self.lib.emu_decompressed_size(p(b.src, _u8p), p(b.src_off, _u64p), p(b.src_len, _u64p), p(st, _u8p),
+                                       p(sz, _u64p), b.n)
+        return st, sz
+
     def stream_decompress(self, src: bytes, cap: int, phase: int = 0, fill: int = 0xA5):
         """One stream through the single-stream pass 1 (huff_stream.cuh, 32 host threads) and the
         real pass 2. -> (status, dst bytes, written)"""

@@ -398,3 +398,44 @@ def test_single_stream_route_across_pass2_stripes(monkeypatch, stripe_mb):
         assert dst[: len(plain)] == plain, k
         assert dst[len(plain):] == b"\xa5" * 7
     ctx.close()
+
+
+def test_size_discovery_matches_decode(ctx, oracle, golden):
+    """sfb200_decompressed_size_batch_device (extension): status and size of a decode
+    into an unlimited dst, without a dst — against the oracle with a large dst on golden families
+    (truncated, corrupt and crafted inputs included), and against the full decode on a C2-shaped
+    batch; sizing dst from it then lets every stream succeed."""
+    dev = torch.device("cuda", ctx.device)
+    as_i64 = lambda a: torch.from_numpy(a.view(np.int64)).to(dev)
+    for name, stride in (("known_answers", 1), ("crafted_dynamic_headers", 1), ("cut7_starfleet_dynamic", 7),
+                         ("cut1_multiblock_12000", 11), ("cap_stored_4096", 37), ("flip_dynamic_4096", 5),
+                         ("flip_repetitive_70000", 9), ("cut1_fixed_4096", 7)):
+        if name not in golden.families:
+            continue
+        cases = golden.cases(name, stride)
+        big = 1 << 18
+        b = T.Batch([c[1] for c in cases], [big] * len(cases))
+        status = torch.full((b.n,), 0xEE, dtype=torch.uint8, device=dev)
+        size = torch.full((b.n,), -1, dtype=torch.int64, device=dev)
+        ctx.decompressed_size_batch_device(torch.from_numpy(b.src).to(dev), as_i64(b.src_off), as_i64(b.src_len),
+                                           status, size)
+        torch.cuda.synchronize(dev)
+        dst_o = b.new_dst()
+        ost, owr, _ = oracle.decompress_batch(b.src, b.src_off, b.src_len, dst_o, b.dst_off, b.dst_cap, 8)
+        assert (status.cpu().numpy() == ost).all(), name
+        assert (size.cpu().numpy().view(np.uint64) == owr).all(), name
+    # sizes first, then a decode into exactly that much room
+    streams = [T.make_stream(["dynamic", "fixed", "stored", "multiblock", "repetitive"][i % 5], 100 + 977 * i, 40 + i)[1]
+               for i in range(300)]
+    b0 = T.Batch(streams, [0] * len(streams))
+    status = torch.zeros(b0.n, dtype=torch.uint8, device=dev)
+    size = torch.zeros(b0.n, dtype=torch.int64, device=dev)
+    ctx.decompressed_size_batch_device(torch.from_numpy(b0.src).to(dev), as_i64(b0.src_off), as_i64(b0.src_len),
+                                       status, size)
+    torch.cuda.synchronize(dev)
+    assert int(status.max()) == 0
+    b = T.Batch(streams, [int(x) for x in size.cpu().numpy()], dst_align=1)
+    st, wr, dst = gpu_util.run_device(ctx, b)
+    assert not st.any() and (wr == b.dst_cap).all()
+    for k in (0, 7, 150, 299):
+        assert b.dst_slice(dst, k).tobytes() == zlib.decompress(streams[k], -15)

@@ -209,3 +209,20 @@ def test_single_stream_blocks_side_by_side(emu, oracle):
     assert ost == 7
     st, dst, wr, on_chain, tail = emu.stream_decompress_jobs(src, 64, [second])
     assert (st, wr) == (ost, owr) and dst == odst and on_chain == 2 and tail == 1
+
+
+def test_size_discovery_mode(emu, oracle, golden):
+    """huff_lanes_kernel<C, true>: status and size of a decode into an unlimited dst, nothing stored
+    (every dst pointer is null in the emulation).  Expectation: the oracle with a large dst."""
+    for name, stride in (("known_answers", 1), ("crafted_dynamic_headers", 1), ("cut7_starfleet_dynamic", 97),
+                         ("cut1_multiblock_12000", 131), ("cap_stored_4096", 257), ("flip_dynamic_4096", 61),
+                         ("cut1_fixed_4096", 53)):
+        if name not in golden.families:
+            continue
+        cases = golden.cases(name, stride)
+        big = 1 << 18
+        b = T.Batch([c[1] for c in cases], [big] * len(cases))
+        st, sz = emu.decompressed_size(b)
+        for k, (i, src, cap) in enumerate(cases):
+            ost, _, owr, _ = oracle.decompress(src, big)
+            assert (int(st[k]), int(sz[k])) == (ost, owr), (name, i)
