@@ -115,6 +115,38 @@ int sfb200_decompressed_size_batch_device(sfb200_ctx* ctx, const uint8_t* src_ba
                                           uint8_t* status, uint64_t* size, uint64_t n,
                                           void* cuda_stream);
 
+/* The same for one stream in host memory (what dst.size() a caller of sfb200_decompress needs). */
+int sfb200_decompressed_size(sfb200_ctx* ctx, const uint8_t* src, size_t src_len, uint8_t* status,
+                             uint64_t* size);
+
+/* zlib (RFC 1950) and gzip (RFC 1952) containers (extension; SURVEY.md §8 f1 — the reference is
+ * raw-DEFLATE only).  Same arguments as sfb200_decompress_batch_device, each stream being a whole
+ * container: the header is parsed and the trailer's Adler-32 / CRC-32 (and gzip's ISIZE) verified
+ * against the produced bytes, all on the device.  `container`: SFB200_CONTAINER_*; AUTO decides
+ * per stream (gzip magic, else a valid zlib header, else raw).  status[i] is the DecompressStatus
+ * of the DEFLATE payload, or one of the values below.  One member per stream, no trailing bytes,
+ * no preset dictionary. */
+enum sfb200_container {
+  SFB200_CONTAINER_RAW = 0,
+  SFB200_CONTAINER_ZLIB = 1,
+  SFB200_CONTAINER_GZIP = 2,
+  SFB200_CONTAINER_AUTO = 3
+};
+enum sfb200_container_status {
+  SFB200_BAD_CONTAINER = 8,      /* malformed or unsupported header (nothing is written) */
+  SFB200_CHECKSUM_MISMATCH = 9,  /* the payload decoded, its Adler-32 / CRC-32 is not the trailer's */
+  SFB200_SIZE_MISMATCH = 10      /* gzip: ISIZE is not the decoded size modulo 2^32 */
+};
+int sfb200_decompress_container_batch_device(sfb200_ctx* ctx, int container, const uint8_t* src_base,
+                                             const uint64_t* src_off, const uint64_t* src_len,
+                                             uint8_t* dst_base, uint64_t dst_bytes,
+                                             const uint64_t* dst_off, const uint64_t* dst_cap,
+                                             uint8_t* status, uint64_t* written, uint64_t n,
+                                             void* cuda_stream);
+/* One container in host memory (the shape of sfb200_decompress). */
+int sfb200_decompress_container(sfb200_ctx* ctx, int container, const uint8_t* src, size_t src_len,
+                                uint8_t* dst, size_t dst_cap, uint8_t* status, uint64_t* written);
+
 /* Position-weighted 64-bit checksum of each stream's output region [0, len[i]) computed on the
  * device (used by tests/bench to verify multi-GiB outputs without a device->host copy):
  *   sum_j (byte_j + 1) * (0x9E3779B97F4A7C15 * (j + 1) | 1)   mod 2^64. */

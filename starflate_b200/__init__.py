@@ -131,6 +131,42 @@ class Context:
             written.data_ptr() if written is not None else None, n, stream)
         self._check(rc, "sfb200_decompress_batch_device")
 
+    RAW, ZLIB, GZIP, AUTO = 0, 1, 2, 3
+
+    def decompress_container_batch_device(self, container, src, src_off, src_len, dst, dst_off, dst_cap, status,
+                                          written=None, stream=None):
+        """zlib / gzip containers (or AUTO per stream): header, DEFLATE payload, trailer checksum."""
+        import torch
+        n = src_off.numel()
+        for t in (src_off, src_len, dst_off, dst_cap):
+            assert t.is_cuda and t.dtype == torch.int64 and t.is_contiguous() and t.numel() == n
+        assert src.is_cuda and src.dtype == torch.uint8 and dst.is_cuda and dst.dtype == torch.uint8
+        assert status.is_cuda and status.dtype == torch.uint8 and status.numel() == n
+        if stream is None:
+            stream = torch.cuda.current_stream(src.device).cuda_stream
+        f = self.lib.sfb200_decompress_container_batch_device
+        f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        f.restype = C.c_int
+        rc = f(self.h, container, src.data_ptr(), src_off.data_ptr(), src_len.data_ptr(), dst.data_ptr(),
+               dst.numel(), dst_off.data_ptr(), dst_cap.data_ptr(), status.data_ptr(),
+               written.data_ptr() if written is not None else None, n, stream)
+        self._check(rc, "sfb200_decompress_container_batch_device")
+
+    def decompress_container(self, container, src: bytes, dst_cap: int, fill: int = 0):
+        """One container in host memory -> (status, dst bytes, written)."""
+        s = np.frombuffer(src, dtype=np.uint8) if len(src) else np.zeros(1, np.uint8)
+        d = np.full(max(dst_cap, 1), fill, dtype=np.uint8)
+        st = C.c_uint8(0)
+        wr = C.c_uint64(0)
+        f = self.lib.sfb200_decompress_container
+        f.argtypes = [C.c_void_p, C.c_int, _u8p, C.c_size_t, _u8p, C.c_size_t, C.POINTER(C.c_uint8),
+                      C.POINTER(C.c_uint64)]
+        f.restype = C.c_int
+        rc = f(self.h, container, _p(s, _u8p), len(src), _p(d, _u8p), dst_cap, C.byref(st), C.byref(wr))
+        self._check(rc, "sfb200_decompress_container")
+        return st.value, d[:dst_cap].tobytes(), wr.value
+
     def decompressed_size_batch_device(self, src, src_off, src_len, status, size, stream=None):
         """Size discovery: status[i] / size[i] of a decode into an unlimited dst; nothing is stored."""
         import torch

@@ -79,6 +79,32 @@ auto decompress(std::span<const std::byte> src, std::span<std::byte> dst) -> Dec
   return static_cast<DecompressStatus>(status);
 }
 
+auto decompressed_size(std::span<const std::byte> src) -> std::expected<std::size_t, DecompressStatus>
+{
+  std::uint8_t status = 0;
+  std::uint64_t size = 0;
+  const std::lock_guard lock{context_mutex()};
+  const int rc = sfb200_decompressed_size(context(), reinterpret_cast<const std::uint8_t*>(src.data()), src.size(),
+                                          &status, &size);
+  if (rc != SFB200_RC_OK) die("sfb200_decompressed_size", rc);
+  if (status != 0) return std::unexpected{static_cast<DecompressStatus>(status)};
+  return static_cast<std::size_t>(size);
+}
+
+auto decompress_container(std::span<const std::byte> src, std::span<std::byte> dst, Container container,
+                          std::size_t* written) -> ContainerStatus
+{
+  std::uint8_t status = 0;
+  std::uint64_t wr = 0;
+  const std::lock_guard lock{context_mutex()};
+  const int rc = sfb200_decompress_container(context(), static_cast<int>(container),
+                                             reinterpret_cast<const std::uint8_t*>(src.data()), src.size(),
+                                             reinterpret_cast<std::uint8_t*>(dst.data()), dst.size(), &status, &wr);
+  if (rc != SFB200_RC_OK) die("sfb200_decompress_container", rc);
+  if (written) *written = static_cast<std::size_t>(wr);
+  return static_cast<ContainerStatus>(status);
+}
+
 auto decompress_batch(std::span<const std::span<const std::byte>> src,
                       std::span<const std::span<std::byte>> dst, std::span<DecompressStatus> status,
                       std::span<std::size_t> written) -> bool

@@ -63,6 +63,34 @@ auto decompress(const R& src, std::span<std::byte> dst)
   return decompress(std::span<const std::byte>{src.data(), src.size()}, dst);
 }
 
+// ---- extension: size discovery --------------------------------------------------------------
+/// The number of bytes decompress(src, dst) produces into a dst that is large enough — which the
+/// reference leaves to the caller to know — or the status that ends the stream.  Nothing is
+/// stored; one H2D copy of src, one kernel.
+auto decompressed_size(std::span<const std::byte> src) -> std::expected<std::size_t, DecompressStatus>;
+
+// ---- extension: zlib (RFC 1950) / gzip (RFC 1952) containers ----------------------------------
+enum class Container : std::uint8_t { Raw = 0, Zlib = 1, Gzip = 2, Auto = 3 };
+/// DecompressStatus (same values) plus what only a container can get wrong.
+enum class ContainerStatus : std::uint8_t
+{
+  Success = 0,
+  Error,
+  InvalidBlockHeader,
+  NoCompressionLenMismatch,
+  DstTooSmall,
+  SrcTooSmall,
+  InvalidLitOrLen,
+  InvalidDistance,
+  BadContainer,      // malformed or unsupported header
+  ChecksumMismatch,  // Adler-32 / CRC-32 of the output is not the trailer's
+  SizeMismatch,      // gzip ISIZE
+};
+/// decompress() for a whole zlib / gzip container: header, DEFLATE payload, trailer checksum
+/// (verified on the device).  `written`, if given, receives the number of bytes produced.
+auto decompress_container(std::span<const std::byte> src, std::span<std::byte> dst, Container container,
+                          std::size_t* written = nullptr) -> ContainerStatus;
+
 // ---- extension: the batched form the GPU is built for ------------------------------------------
 /// Stream i reads src[i] and writes dst[i] (host memory); status[i] / written[i] receive its
 /// result.  One call = one H2D copy, two kernels, one D2H copy.  Returns false on an

@@ -6,6 +6,7 @@
 #include "huff_stream.cuh"
 #include "lz_warp.cuh"
 #include "lz_jump.cuh"
+#include "container.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -64,6 +65,8 @@ struct sfb200_ctx {
   uint32_t* d_lens = nullptr;  // per-resident-lane code-length scratch
   uint32_t* d_bits = nullptr;  // match-head bitmap: 1 bit per dst byte (grown on demand)
   uint64_t d_bits_words = 0;
+  uint8_t* d_cont = nullptr;  // container route: payload offsets / sizes, kinds, trailer values, written
+  uint64_t d_cont_cap = 0;
   uint8_t* d_find = nullptr;  // single-stream pass 1 (block_finder.cuh): counters, hash table, jobs, candidates
   uint64_t d_find_cap = 0;
   uint8_t* d_jump = nullptr;  // single-stream pass 2 (lz_jump.cuh): pointers, tile flags, round flags
@@ -229,6 +232,7 @@ void sfb200_destroy(sfb200_ctx* ctx)
   cudaFree(ctx->d_written);
   cudaFree(ctx->d_jump);
   cudaFree(ctx->d_find);
+  cudaFree(ctx->d_cont);
   cudaFree(ctx->d_defer);
   cudaFree(ctx->d_order);
   cudaFree(ctx->d_src);
@@ -904,6 +908,104 @@ int sfb200_decompress(sfb200_ctx* ctx, const uint8_t* src, size_t src_len, uint8
   const uint64_t zero = 0, sl = src_len, dc = dst_cap;
   return sfb200_decompress_batch_host(ctx, src, sl, &zero, &sl, dst, dc, &zero, &dc, status,
                                       written, 1);
+}
+
+int sfb200_decompress_container_batch_device(sfb200_ctx* ctx, int container, const uint8_t* src_base,
+                                             const uint64_t* src_off, const uint64_t* src_len,
+                                             uint8_t* dst_base, uint64_t dst_bytes,
+                                             const uint64_t* dst_off, const uint64_t* dst_cap,
+                                             uint8_t* status, uint64_t* written, uint64_t n,
+                                             void* cuda_stream)
+{
+  if (!ctx || container < 0 || container > 3) return SFB200_RC_BAD_ARGUMENT;
+  if (n == 0) return SFB200_RC_OK;
+  if (!src_off || !src_len || !dst_off || !dst_cap || !status) return SFB200_RC_BAD_ARGUMENT;
+  if (container == SFB200_CONTAINER_RAW)
+    return sfb200_decompress_batch_device(ctx, src_base, src_off, src_len, dst_base, dst_bytes, dst_off, dst_cap,
+                                          status, written, n, cuda_stream);
+  SFB_TRY(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  int rc = grow(ctx, &ctx->d_cont, &ctx->d_cont_cap, n * 36 + 64);
+  if (rc != SFB200_RC_OK) return rc;
+  sfb::ContainerArgs c;
+  c.src_base = src_base;
+  c.src_off = src_off;
+  c.src_len = src_len;
+  c.container = static_cast<uint32_t>(container);
+  c.n = n;
+  c.pay_off = reinterpret_cast<uint64_t*>(ctx->d_cont);
+  c.pay_len = c.pay_off + n;
+  uint64_t* const own_written = c.pay_len + n;
+  c.kind = reinterpret_cast<uint32_t*>(own_written + n);
+  c.expect = c.kind + n;
+  c.isize = c.expect + n;
+  c.dst_base = dst_base;
+  c.dst_off = dst_off;
+  c.status = status;
+  c.written = written ? written : own_written;
+  const unsigned pgrid = static_cast<unsigned>((n + 127) / 128);
+  sfb::container_parse_kernel<<<pgrid, 128, 0, st>>>(c);
+  SFB_TRY(ctx, cudaGetLastError());
+  rc = sfb200_decompress_batch_device(ctx, src_base, c.pay_off, c.pay_len, dst_base, dst_bytes, dst_off, dst_cap,
+                                      status, c.written, n, cuda_stream);
+  if (rc != SFB200_RC_OK) return rc;
+  const uint64_t want = (n * 32 + sfb::CHECK_THREADS - 1) / sfb::CHECK_THREADS;
+  const uint64_t resident = static_cast<uint64_t>(ctx->sm_count) * 8;
+  sfb::container_check_kernel<<<static_cast<unsigned>(want < resident ? want : resident), sfb::CHECK_THREADS, 0, st>>>(c);
+  SFB_TRY(ctx, cudaGetLastError());
+  ctx->launches += 2;
+  return SFB200_RC_OK;
+}
+
+int sfb200_decompress_container(sfb200_ctx* ctx, int container, const uint8_t* src, size_t src_len,
+                                uint8_t* dst, size_t dst_cap, uint8_t* status, uint64_t* written)
+{
+  if (!ctx || !status || (!src && src_len) || (!dst && dst_cap)) return SFB200_RC_BAD_ARGUMENT;
+  SFB_TRY(ctx, cudaSetDevice(ctx->device));
+  const uint64_t meta_at = (static_cast<uint64_t>(src_len) + 15) & ~15ull;
+  int rc = grow(ctx, &ctx->d_src, &ctx->d_src_cap, meta_at + 64);
+  if (rc != SFB200_RC_OK) return rc;
+  rc = grow(ctx, &ctx->d_dst, &ctx->d_dst_cap, static_cast<uint64_t>(dst_cap) + 64);
+  if (rc != SFB200_RC_OK) return rc;
+  // metadata behind the stream in the staging buffer: src_off, src_len, dst_off, dst_cap, written (u64), status (u8)
+  uint64_t meta[5] = {0, static_cast<uint64_t>(src_len), 0, static_cast<uint64_t>(dst_cap), 0};
+  uint64_t* const d_m = reinterpret_cast<uint64_t*>(ctx->d_src + meta_at);
+  uint8_t* const d_st = reinterpret_cast<uint8_t*>(d_m + 5);
+  if (src_len) SFB_TRY(ctx, cudaMemcpyAsync(ctx->d_src, src, src_len, cudaMemcpyHostToDevice, nullptr));
+  SFB_TRY(ctx, cudaMemcpyAsync(d_m, meta, sizeof(meta), cudaMemcpyHostToDevice, nullptr));
+  rc = sfb200_decompress_container_batch_device(ctx, container, ctx->d_src, d_m, d_m + 1, ctx->d_dst, dst_cap, d_m + 2,
+                                                d_m + 3, d_st, d_m + 4, 1, nullptr);
+  if (rc != SFB200_RC_OK) return rc;
+  uint64_t wr = 0;
+  SFB_TRY(ctx, cudaMemcpyAsync(&wr, d_m + 4, 8, cudaMemcpyDeviceToHost, nullptr));
+  SFB_TRY(ctx, cudaMemcpyAsync(status, d_st, 1, cudaMemcpyDeviceToHost, nullptr));
+  SFB_TRY(ctx, cudaStreamSynchronize(nullptr));
+  if (wr > dst_cap) return SFB200_RC_CUDA_ERROR;  // (cannot happen)
+  if (wr) SFB_TRY(ctx, cudaMemcpy(dst, ctx->d_dst, wr, cudaMemcpyDeviceToHost));  // only what was produced
+  if (written) *written = wr;
+  return SFB200_RC_OK;
+}
+
+int sfb200_decompressed_size(sfb200_ctx* ctx, const uint8_t* src, size_t src_len, uint8_t* status,
+                             uint64_t* size)
+{
+  if (!ctx || !status || !size || (!src && src_len)) return SFB200_RC_BAD_ARGUMENT;
+  SFB_TRY(ctx, cudaSetDevice(ctx->device));
+  int rc = grow(ctx, &ctx->d_src, &ctx->d_src_cap, static_cast<uint64_t>(src_len) + 64);
+  if (rc != SFB200_RC_OK) return rc;
+  // metadata lives behind the stream in the same staging buffer: off, len, size (u64), status (u8)
+  const uint64_t meta_at = (static_cast<uint64_t>(src_len) + 15) & ~15ull;
+  uint64_t meta[3] = {0, static_cast<uint64_t>(src_len), 0};
+  uint64_t* const d_m = reinterpret_cast<uint64_t*>(ctx->d_src + meta_at);
+  uint8_t* const d_st = reinterpret_cast<uint8_t*>(d_m + 3);
+  if (src_len) SFB_TRY(ctx, cudaMemcpyAsync(ctx->d_src, src, src_len, cudaMemcpyHostToDevice, nullptr));
+  SFB_TRY(ctx, cudaMemcpyAsync(d_m, meta, sizeof(meta), cudaMemcpyHostToDevice, nullptr));
+  rc = sfb200_decompressed_size_batch_device(ctx, ctx->d_src, d_m, d_m + 1, d_st, d_m + 2, 1, nullptr);
+  if (rc != SFB200_RC_OK) return rc;
+  SFB_TRY(ctx, cudaMemcpyAsync(size, d_m + 2, 8, cudaMemcpyDeviceToHost, nullptr));
+  SFB_TRY(ctx, cudaMemcpyAsync(status, d_st, 1, cudaMemcpyDeviceToHost, nullptr));
+  SFB_TRY(ctx, cudaStreamSynchronize(nullptr));
+  return SFB200_RC_OK;
 }
 
 }  // extern "C"

@@ -200,6 +200,28 @@ void test_decompress_gpu(const std::string& bases)
     EXPECT(decompress_batch(srcs, dsts, st, wr));
     EXPECT(st[0] == DecompressStatus::Success && wr[0] == 1 && da[0] == std::byte{'A'});
     EXPECT(st[1] == DecompressStatus::DstTooSmall && wr[1] == 1);
+    // size discovery extension: what the second stream needs, and a failing stream's status
+    const auto need = decompressed_size(b);
+    EXPECT(need.has_value() && *need == 259);
+    constexpr auto bad = huffman::byte_array(0x07);  // BTYPE 3
+    const auto none = decompressed_size(bad);
+    EXPECT(!none.has_value() && none.error() == DecompressStatus::InvalidBlockHeader);
+    const std::vector<std::byte> star = read_file(bases + "/starfleet_dynamic.deflate");
+    const auto star_size = decompressed_size(star);
+    EXPECT(star_size.has_value() && *star_size == 149618);
+  }
+  {  // container extension: zlib.compress(b"hello, hello") and the same with a broken Adler-32
+    constexpr auto z = huffman::byte_array(0x78, 0x9c, 0xcb, 0x48, 0xcd, 0xc9, 0xc9, 0xd7, 0x51, 0xc8, 0x00, 0x51,
+                                           0x00, 0x1c, 0xda, 0x04, 0x75);
+    std::array<std::byte, 16> out{};
+    std::size_t wr = 0;
+    EXPECT(decompress_container(z, out, Container::Zlib, &wr) == ContainerStatus::Success);
+    EXPECT(wr == 12 && std::memcmp(out.data(), "hello, hello", 12) == 0);
+    EXPECT(decompress_container(z, out, Container::Auto, &wr) == ContainerStatus::Success);
+    auto bad = z;
+    bad[16] = std::byte{0x5c};
+    EXPECT(decompress_container(bad, out, Container::Zlib, &wr) == ContainerStatus::ChecksumMismatch);
+    EXPECT(decompress_container(z, out, Container::Gzip, &wr) == ContainerStatus::BadContainer);
   }
 }
 }  // namespace
