@@ -50,23 +50,36 @@ def _html_plain(size: int, seed: int) -> bytes:
     return rep
 
 
+_CONTAINER = "raw"
+
+
+def _wrap(comp: bytes, plain: bytes) -> bytes:
+    if _CONTAINER == "zlib":
+        return b"\x78\x9c" + comp + zlib.adler32(plain).to_bytes(4, "big")
+    if _CONTAINER == "gzip":
+        return (b"\x1f\x8b\x08\x00\x00\x00\x00\x00\x00\x03" + comp + zlib.crc32(plain).to_bytes(4, "little") +
+                (len(plain) & 0xffffffff).to_bytes(4, "little"))
+    return comp
+
+
 def _gen_one(args):
-    kind, size, seed = args
+    global _CONTAINER
+    kind, size, seed, _CONTAINER = args
     if kind == "html":
         plain = _html_plain(size, seed)
         co = zlib.compressobj(6, zlib.DEFLATED, -15, 8, zlib.Z_DEFAULT_STRATEGY)
         comp = co.compress(plain) + co.flush()
-        return comp, zlib.crc32(plain), len(plain)
+        return _wrap(comp, plain), zlib.crc32(plain), len(plain)
     if kind == "single":
         plain = T.big_text(size, seed)
         comp = T.raw_deflate(plain, 6)
-        return comp, zlib.crc32(plain), len(plain)
+        return _wrap(comp, plain), zlib.crc32(plain), len(plain)
     plain, comp = T.make_stream(kind, size, seed)
     assert T.first_block_type(comp) == {"dynamic": 2, "fixed": 1, "stored": 0}.get(kind, 2) or kind in ("repetitive", "multiblock")
-    return comp, zlib.crc32(plain), len(plain)
+    return _wrap(comp, plain), zlib.crc32(plain), len(plain)
 
 
-def make_workload(name: str, n_streams: int, unique: int, rank: int):
+def make_workload(name: str, n_streams: int, unique: int, rank: int, container: str = "raw"):
     """-> dict(src u8, src_off, src_len, dst_off, dst_cap (u64 numpy), total_out, desc)."""
     if name == "c2":
         kind, size = "dynamic", 65536
@@ -86,7 +99,7 @@ def make_workload(name: str, n_streams: int, unique: int, rank: int):
     jobs = []
     for i in range(unique):
         k = kind if kind != "mixed" else ["stored", "fixed", "dynamic"][i % 3]
-        jobs.append((k, size, 1_000_003 * (rank + 1) + i))
+        jobs.append((k, size, 1_000_003 * (rank + 1) + i, container))
     workers = max(1, min(os.cpu_count() or 1, 64))
     t0 = time.time()
     with ProcessPoolExecutor(workers) as ex:
@@ -117,7 +130,8 @@ def make_workload(name: str, n_streams: int, unique: int, rank: int):
         "total_out": int(caps.sum()), "total_in": int(src_len.sum()), "n": n_streams,
         "crc": np.array([r[1] for r in res], dtype=np.uint64)[sel], "gen_s": gen_s,
         "desc": f"{name}: {n_streams} x {size} B {kind} level-{'9' if name == 'c4' else '6'} streams"
-                f" ({unique} unique seeds, zlib {zlib.ZLIB_RUNTIME_VERSION})",
+                f" ({unique} unique seeds, zlib {zlib.ZLIB_RUNTIME_VERSION})"
+                + ("" if container == "raw" else f", each in a {container} container (checksum verified on the device)"),
     }
 
 
@@ -223,6 +237,9 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5", "html"])
     ap.add_argument("--streams", type=int, default=0, help="streams per GPU (0 = the config's size)")
     ap.add_argument("--unique", type=int, default=0, help="distinct seeds (0 = all streams distinct)")
+    ap.add_argument("--container", default="raw", choices=["raw", "zlib", "gzip"],
+                    help="wrap every stream in a zlib / gzip container and verify its checksum on the device "
+                         "(extension; the BASELINE metric is raw)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
@@ -277,7 +294,7 @@ def main():
         dist.barrier()
     ctx = S.Context(local_rank)
 
-    w = make_workload(args.workload, n_streams, unique, rank)
+    w = make_workload(args.workload, n_streams, unique, rank, args.container)
     n = w["n"]
     to_i64 = lambda a: torch.from_numpy(a.view(np.int64))
     h_src = torch.from_numpy(w["src"]).pin_memory()
@@ -289,6 +306,11 @@ def main():
     d_written = torch.zeros(n, dtype=torch.int64, device=dev)
 
     def step():
+        if args.container != "raw":
+            ctx.decompress_container_batch_device({"zlib": ctx.ZLIB, "gzip": ctx.GZIP}[args.container], d_src,
+                                                  d_src_off, d_src_len, d_dst, d_dst_off, d_dst_cap, d_status,
+                                                  d_written)
+            return
         ctx.decompress_batch_device(d_src, d_src_off, d_src_len, d_dst, d_dst_off, d_dst_cap,
                                     d_status, d_written)
 
@@ -345,7 +367,7 @@ def main():
 
     # ---- end to end through the public host-buffer API (H2D + kernel + D2H every step) --------
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and args.container == "raw":
         h_dst = torch.empty(w["total_out"], dtype=torch.uint8).pin_memory()
         h_np_dst = h_dst.numpy()
         e_steps = max(1, min(args.steps, 3))
@@ -410,7 +432,7 @@ def main():
         "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
         "wall_s_timed_region": t_wall,
     }
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and args.container == "raw":
         line["cpu_baseline"], _ = cpu_baseline(w, args.cpu_seconds)
     if rank == 0:
         print(json.dumps(line))

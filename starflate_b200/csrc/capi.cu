@@ -949,9 +949,16 @@ int sfb200_decompress_container_batch_device(sfb200_ctx* ctx, int container, con
   rc = sfb200_decompress_batch_device(ctx, src_base, c.pay_off, c.pay_len, dst_base, dst_bytes, dst_off, dst_cap,
                                       status, c.written, n, cuda_stream);
   if (rc != SFB200_RC_OK) return rc;
+  static bool check_configured = false;  // (per process; the attribute belongs to the function)
+  if (!check_configured) {
+    SFB_TRY(ctx, cudaFuncSetAttribute(sfb::container_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      sfb::CHECK_SMEM_BYTES));
+    check_configured = true;
+  }
   const uint64_t want = (n * 32 + sfb::CHECK_THREADS - 1) / sfb::CHECK_THREADS;
-  const uint64_t resident = static_cast<uint64_t>(ctx->sm_count) * 8;
-  sfb::container_check_kernel<<<static_cast<unsigned>(want < resident ? want : resident), sfb::CHECK_THREADS, 0, st>>>(c);
+  const uint64_t resident = static_cast<uint64_t>(ctx->sm_count);  // (one block per SM: 128 KiB of tables)
+  sfb::container_check_kernel<<<static_cast<unsigned>(want < resident ? want : resident), sfb::CHECK_THREADS,
+                                sfb::CHECK_SMEM_BYTES, st>>>(c);
   SFB_TRY(ctx, cudaGetLastError());
   ctx->launches += 2;
   return SFB200_RC_OK;
