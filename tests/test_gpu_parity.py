@@ -235,10 +235,14 @@ def _one_stream_per_call(ctx, src_bytes, cap, phase=0, src_phase=0, fill=0xA5):
     return int(status.item()), int(written.item()), got[pad + phase: pad + phase + cap].tobytes(), intact
 
 
-def test_single_stream_route_golden_one_call_per_stream(ctx, oracle, golden):
+def test_single_stream_route_golden_one_call_per_stream(oracle, golden, monkeypatch):
     """Every 9th..61st case of the golden families, one call each (so each goes through the block
-    finder, the counting / chain / writing jobs and the pointer-jumping pass 2), at varying dst
-    and src phases."""
+    finder, the counting / chain / writing jobs and the pointer-jumping pass 2; SFB200_STREAM_MODE=1
+    because on its own the library takes that route only from 32 KiB of dst up), at varying dst and
+    src phases."""
+    import starflate_b200 as S
+    monkeypatch.setenv("SFB200_STREAM_MODE", "1")
+    ctx = S.Context(0)
     k = 0
     for name, stride in (("known_answers", 1), ("crafted_dynamic_headers", 1), ("cut7_starfleet_dynamic", 17),
                          ("cut7_starfleet_fixed", 61), ("cut1_multiblock_12000", 61), ("cap_dynamic_4096", 31),
@@ -254,6 +258,7 @@ def test_single_stream_route_golden_one_call_per_stream(ctx, oracle, golden):
             assert "%016x" % oracle.fnv1a64(dst) == want_hash, (name, i, cls)
             assert intact, (name, i)
     assert k > 600
+    ctx.close()
 
 
 @pytest.mark.parametrize("blocks", ["1", "0"])
