@@ -301,6 +301,10 @@ __global__ void __launch_bounds__(FIND_THREADS) verify_candidates_kernel(const F
       }
       prev = val;
       i += rep;
+      if (kraft_lit > 32768u || kraft_dist > 32768u) {  // over-subscribed already (random bits mostly are, early)
+        ok = false;
+        break;
+      }
     }
     if (!ok || p > total_bits) continue;
     if (kraft_lit != 32768u || eob_len == 0u) continue;
@@ -321,6 +325,93 @@ __global__ void __launch_bounds__(FIND_THREADS) verify_candidates_kernel(const F
     uint32_t slot = job_slot(p0, a.tab_mask);
     while (atomicCAS(a.job_tab + slot, 0u, j) != 0u) slot = (slot + 1u) & a.tab_mask;
   }
+}
+
+// The same chain, in parallel, by ONE block (the walk above takes 0.5 us per block of the stream:
+// 6 ms for the 12 000 blocks of a 1 GiB stream).  Pointer jumping over the jobs: J[j] = the job 2^k
+// blocks after j, W[j] = the bytes of those 2^k blocks.  In round k every job already known to be on
+// the chain (those up to 2^k - 1 blocks from job 0) marks J[j] and gives it its position base[j] +
+// W[j], then J and W double.  What the walk decides on the way — stop at a block whose distances or
+// size do not fit — is decided afterwards: among the marked jobs that do not fit, the one that
+// starts first is the tail, and everything after it is taken off the chain again.
+constexpr int CHAIN_THREADS = 1024;
+struct ChainScratch {
+  uint32_t* ja;  // [job_cap] each
+  uint32_t* jb;
+  uint64_t* wa;
+  uint64_t* wb;
+  uint32_t* mark;
+};
+
+__global__ void __launch_bounds__(CHAIN_THREADS) chain_parallel_kernel(const FindArgs a, const ChainScratch c)
+{
+  constexpr uint32_t NONE = 0xffffffffu;
+  __shared__ unsigned long long s_first_bad;  // smallest start_bit among the chain jobs that do not fit
+  __shared__ uint32_t s_tail;
+  const uint32_t tid = threadIdx.x;
+  const uint64_t cap = a.dst_cap[a.idx];
+  uint32_t n = *a.job_count;
+  if (n > a.job_cap) n = a.job_cap;
+  uint32_t* J = c.ja;
+  uint32_t* Jn = c.jb;
+  uint64_t* W = c.wa;
+  uint64_t* Wn = c.wb;
+  for (uint32_t j = tid; j < n; j += CHAIN_THREADS) {
+    const BlockJob jb = a.jobs[j];
+    const bool ends = (jb.flags & JOB_ENDS) || jb.next == 0u || jb.next >= n;
+    J[j] = ends ? NONE : jb.next;
+    W[j] = jb.out;
+    c.mark[j] = j == 0u ? 1u : 0u;  // 0: not on the chain, else 2 + the round that found it (job 0: 1)
+    if (j == 0u) a.jobs[0].base = 0;
+  }
+  if (tid == 0) {
+    s_first_bad = ~0ull;
+    s_tail = 0;
+  }
+  __syncthreads();
+  uint32_t rounds = 1;
+  while ((1u << rounds) < n && rounds < 31u) ++rounds;
+  for (uint32_t k = 0; k <= rounds; ++k) {
+    for (uint32_t j = tid; j < n; j += CHAIN_THREADS) {
+      const uint32_t t = J[j];
+      const uint32_t stamp = c.mark[j];
+      if (stamp != 0u && stamp < k + 2u && t != NONE) {  // on the chain since an EARLIER round (its base is settled)
+        a.jobs[t].base = a.jobs[j].base + W[j];
+        c.mark[t] = k + 2u;
+      }
+      Jn[j] = t == NONE ? NONE : J[t];
+      Wn[j] = t == NONE ? W[j] : W[j] + W[t];
+    }
+    __syncthreads();
+    uint32_t* tj = J;
+    J = Jn;
+    Jn = tj;
+    uint64_t* tw = W;
+    W = Wn;
+    Wn = tw;
+  }
+  // the first job on the chain that does not fit (or, if all fit, the one the chain ends with)
+  for (uint32_t j = tid; j < n; j += CHAIN_THREADS) {
+    if (!c.mark[j]) continue;
+    const BlockJob jb = a.jobs[j];
+    if (jb.need > jb.base || jb.base + jb.out > cap) atomicMin(&s_first_bad, static_cast<unsigned long long>(jb.start_bit));
+  }
+  __syncthreads();
+  const uint64_t first_bad = s_first_bad;
+  for (uint32_t j = tid; j < n; j += CHAIN_THREADS) {
+    if (!c.mark[j]) continue;
+    const BlockJob jb = a.jobs[j];
+    if (jb.start_bit > first_bad) {  // behind the tail: not decoded by a job of its own after all
+      a.jobs[j].base = JOB_NONE;
+      continue;
+    }
+    const bool fits = jb.need <= jb.base && jb.base + jb.out <= cap;
+    if ((jb.flags & JOB_RECS) && fits) a.jobs[j].flags = jb.flags | JOB_USE;
+    const bool ends = (jb.flags & JOB_ENDS) || jb.next == 0u || jb.next >= n;
+    if (jb.start_bit == first_bad || (first_bad == ~0ull && ends)) s_tail = j;
+  }
+  __syncthreads();
+  if (tid == 0) *a.tail_job = s_tail;
 }
 
 #endif  // SFB_CPU_EMU

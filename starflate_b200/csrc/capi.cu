@@ -65,6 +65,7 @@ struct sfb200_ctx {
   uint32_t* d_lens = nullptr;  // per-resident-lane code-length scratch
   uint32_t* d_bits = nullptr;  // match-head bitmap: 1 bit per dst byte (grown on demand)
   uint64_t d_bits_words = 0;
+  bool count_configured = false, check_configured = false;  // per-device function attributes set
   uint8_t* d_cont = nullptr;  // container route: payload offsets / sizes, kinds, trailer values, written
   uint64_t d_cont_cap = 0;
   uint8_t* d_find = nullptr;  // single-stream pass 1 (block_finder.cuh): counters, hash table, jobs, candidates
@@ -349,7 +350,8 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
     while (tab_size < 2 * job_cap) tab_size *= 2;
     rec_cap = static_cast<uint32_t>(std::min<uint64_t>(src_bits_max / (16 * sfb::SPAN_BITS) + 65536, 1ull << 26));
     const uint64_t need = 64 + 4ull * tab_size + sizeof(sfb::BlockJob) * static_cast<uint64_t>(job_cap) +
-                          8ull * cand_cap + sizeof(sfb::WinRec) * static_cast<uint64_t>(rec_cap);
+                          8ull * cand_cap + sizeof(sfb::WinRec) * static_cast<uint64_t>(rec_cap) +
+                          28ull * job_cap + 64;
     const int rc = grow(ctx, &ctx->d_find, &ctx->d_find_cap, need);
     if (rc != SFB200_RC_OK) return rc;
   }
@@ -520,6 +522,14 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
         sa.recs = reinterpret_cast<sfb::WinRec*>(reinterpret_cast<uint8_t*>(f.cand) + 8ull * cand_cap);
         sa.rec_count = counters + 3;
         sa.rec_cap = rec_cap;
+        sfb::ChainScratch cs;  // behind the window records (8-byte aligned: WinRec is 272 bytes)
+        cs.wa = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sa.recs) + sizeof(sfb::WinRec) * static_cast<uint64_t>(rec_cap));
+        cs.wb = cs.wa + job_cap;
+        cs.ja = reinterpret_cast<uint32_t*>(cs.wb + job_cap);
+        cs.jb = cs.ja + job_cap;
+        cs.mark = cs.jb + job_cap;
+        bool seq_chain = false;
+        if (const char* e = std::getenv("SFB200_CHAIN")) seq_chain = e[0] == 's';
         sa.jobs = f.jobs;
         sa.job_count = f.job_count;
         sa.job_cap = job_cap;
@@ -537,7 +547,8 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
           sa.mode = 1;
           sa.stream_counter = ctr + 0;
           sfb::huff_stream_kernel<StreamCfg><<<grid, 32, StreamCfg::SMEM_BYTES, s1>>>(sa);
-          sfb::chain_kernel<<<1, 32, 0, s1>>>(f);
+          if (seq_chain) sfb::chain_kernel<<<1, 32, 0, s1>>>(f);
+          else sfb::chain_parallel_kernel<<<1, sfb::CHAIN_THREADS, 0, s1>>>(f, cs);
           sa.mode = 2;
           sa.stream_counter = ctr + 1;
           sfb::huff_stream_kernel<StreamCfg><<<grid, 32, StreamCfg::SMEM_BYTES, s1>>>(sa);
@@ -691,11 +702,10 @@ int sfb200_decompressed_size_batch_device(sfb200_ctx* ctx, const uint8_t* src_ba
   a.todo_list = nullptr;
   a.todo_count = nullptr;
   auto kern = sfb::huff_lanes_kernel<LaneCfg, true>;
-  static bool configured = false;  // (per process; the attribute belongs to the function)
-  if (!configured) {
+  if (!ctx->count_configured) {  // (function attributes are per device)
     SFB_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LaneCfg::SMEM_BYTES));
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    configured = true;
+    ctx->count_configured = true;
   }
   const uint64_t groups = (n + 31) / 32;
   const uint64_t want = (groups + LaneCfg::WARPS - 1) / LaneCfg::WARPS;
@@ -954,11 +964,10 @@ int sfb200_decompress_container_batch_device(sfb200_ctx* ctx, int container, con
   rc = sfb200_decompress_batch_device(ctx, src_base, c.pay_off, c.pay_len, dst_base, dst_bytes, dst_off, dst_cap,
                                       status, c.written, n, cuda_stream);
   if (rc != SFB200_RC_OK) return rc;
-  static bool check_configured = false;  // (per process; the attribute belongs to the function)
-  if (!check_configured) {
+  if (!ctx->check_configured) {  // (function attributes are per device)
     SFB_TRY(ctx, cudaFuncSetAttribute(sfb::container_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       sfb::CHECK_SMEM_BYTES));
-    check_configured = true;
+    ctx->check_configured = true;
   }
   const uint64_t want = (n * 32 + sfb::CHECK_THREADS - 1) / sfb::CHECK_THREADS;
   const uint64_t resident = static_cast<uint64_t>(ctx->sm_count);  // (one block per SM: 128 KiB of tables)

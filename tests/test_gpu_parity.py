@@ -261,13 +261,14 @@ def test_single_stream_route_golden_one_call_per_stream(oracle, golden, monkeypa
     ctx.close()
 
 
-@pytest.mark.parametrize("blocks", ["1", "0"])
-def test_single_stream_route_large(oracle, monkeypatch, blocks):
+@pytest.mark.parametrize("blocks,chain", [("1", "parallel"), ("1", "sequential"), ("0", "parallel")])
+def test_single_stream_route_large(oracle, monkeypatch, blocks, chain):
     """C1-shaped inputs (about a megabyte and more, many dynamic blocks; also stored and fixed blocks in
     between, a truncated input, a destination that is too small), blocks side by side
     (SFB200_BLOCKS=1, the default) and front to back: all bytes against the oracle."""
     import starflate_b200 as S
     monkeypatch.setenv("SFB200_BLOCKS", blocks)
+    monkeypatch.setenv("SFB200_CHAIN", chain)  # the chain of blocks by one block of threads | by one thread
     c = S.Context(0)
     try:
         inputs = []
