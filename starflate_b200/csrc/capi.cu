@@ -640,7 +640,13 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
             sfb::lz_jump_init_kernel<<<set_stripe(sp + 1), sfb::JUMP_THREADS, 0, s2>>>(j);
           }
           const unsigned grid = set_stripe(sp);
-          for (int r = 1; r <= sfb::JUMP_MAX_ROUNDS; ++r) {
+          // a chain inside a stripe has fewer hops than the stripe has bytes, and a round divides
+          // them by three: no more launches than that can need (+ 1 to see that nothing moved)
+          int max_rounds = 2;
+          for (uint64_t reach = 3; reach < static_cast<uint64_t>(j.tile_hi - j.tile_lo) * sfb::JUMP_TILE; reach *= 3)
+            ++max_rounds;
+          if (max_rounds > sfb::JUMP_MAX_ROUNDS) max_rounds = sfb::JUMP_MAX_ROUNDS;
+          for (int r = 1; r <= max_rounds; ++r) {
             j.round = static_cast<uint32_t>(r);
             sfb::lz_jump_round_kernel<<<grid, sfb::JUMP_THREADS, 0, s2>>>(j);
           }
