@@ -391,8 +391,10 @@ huff_lanes_kernel(const BatchArgs a)
         // anything that is not a plain literal / length+distance — end of block included — is
         // redone exactly, from the same 64 window bits
         // (near the end of the input the token must also fit into the real bits that are left)
-        const int32_t left32 = static_cast<int32_t>(br.ebits - 32u * br.rp - bo0);  // (meaningful when `tail`)
-        if (dec & ((L == 0) | (is_match & (dL == 0)) | (tail & (static_cast<int32_t>(used) > left32)))) {
+        // (the last few tokens of a stream — `tail` — all go the exact way, whether they fit or not:
+        //  cheaper than asking every token of the stream whether it fits)
+        if (dec & ((L == 0) | (is_match & (dL == 0)) | tail)) {
+          const int32_t left32 = static_cast<int32_t>(br.ebits - 32u * br.rp - bo0);
           // (a) a valid code longer than the tables hold: canonical decode in registers
           bool done = false;
           if (lt_lit.usable & lt_dist.usable) {

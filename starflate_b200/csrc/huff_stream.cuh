@@ -100,8 +100,8 @@ __device__ __forceinline__ Tok decode_token(const BitReader& br, saddr_t lutb, s
   const uint32_t dxb = dinfo >> 16;
   t.dist = (dinfo & 0xffffu) + ((dbits >> dL) & ~(0xffffffffu << dxb));
   t.used = used1 + (t.is_match ? dL + dxb : 0u);
-  const int32_t left32 = static_cast<int32_t>(br.ebits - 32u * br.rp - bo0);
-  if ((L == 0) | (t.is_match & (dL == 0)) | (tail & (static_cast<int32_t>(t.used) > left32))) {
+  if ((L == 0) | (t.is_match & (dL == 0)) | tail) {
+    const int32_t left32 = static_cast<int32_t>(br.ebits - 32u * br.rp - bo0);
     bool done = false;
     if (lt_lit.usable & lt_dist.usable) {
       const uint16_t* sorted = reinterpret_cast<const uint16_t*>(m.lens + SCR_SORTED * 32);
