@@ -119,8 +119,6 @@ __global__ void chain_kernel(const FindArgs a)
   *a.tail_job = j;
 }
 
-#ifndef SFB_CPU_EMU
-
 constexpr int FIND_THREADS = 256;
 
 // 32-bit word i of the 4-byte aligned view of the stream, zero outside [src, src + slen)
@@ -164,7 +162,9 @@ __global__ void __launch_bounds__(FIND_THREADS) find_candidates_kernel(const Fin
     }
     s_kraft[x] = e;
   }
+#ifndef SFB_CPU_EMU
   __syncthreads();
+#endif
   if (slen >= 0xffffff00ull) return;
   const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 3u);
   const uint64_t total_bits = 8ull * slen;
@@ -326,6 +326,8 @@ __global__ void __launch_bounds__(FIND_THREADS) verify_candidates_kernel(const F
     while (atomicCAS(a.job_tab + slot, 0u, j) != 0u) slot = (slot + 1u) & a.tab_mask;
   }
 }
+
+#ifndef SFB_CPU_EMU  // (tests/cpu_emu runs the finder kernels on one host thread and the walk above)
 
 // The same chain, in parallel, by ONE block (the walk above takes 0.5 us per block of the stream:
 // 6 ms for the 12 000 blocks of a 1 GiB stream).  Pointer jumping over the jobs: J[j] = the job 2^k

@@ -91,6 +91,16 @@ static inline unsigned __brev(unsigned v)
 static inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
 static inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned s)
+{
+  return static_cast<unsigned>(((static_cast<uint64_t>(hi) << 32) | lo) >> (s & 31u));
+}
+static inline unsigned atomicCAS(unsigned* p, unsigned expect, unsigned v)
+{
+  __atomic_compare_exchange_n(p, &expect, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED);
+  return expect;
+}
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline int __clz(int v) { return v == 0 ? 32 : __builtin_clz(static_cast<unsigned>(v)); }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v)

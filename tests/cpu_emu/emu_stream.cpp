@@ -31,6 +31,45 @@ static void run_warp(const sfb::StreamArgs& a)
   for (auto& t : lanes) t.join();
 }
 
+// The GPU's block finder (find_candidates_kernel, verify_candidates_kernel) on one host thread:
+// the bit positions it accepts as dynamic-block headers -> out[0 .. return value)
+extern "C" uint32_t emu_find_blocks(const uint8_t* src, uint64_t src_len, uint64_t* out, uint32_t max_out)
+{
+  std::vector<uint8_t> sbuf(src_len + 64, 0xEE);  // as the decoder sees it: not 4-byte aligned
+  if (src_len) std::memcpy(sbuf.data() + 17, src, src_len);
+  const uint64_t zero = 0;
+  const uint32_t cand_cap = static_cast<uint32_t>(8 * src_len / 16 + 64), job_cap = cand_cap;
+  std::vector<uint64_t> cand(cand_cap);
+  std::vector<sfb::BlockJob> jobs(job_cap);
+  uint32_t tab_size = 64;
+  while (tab_size < 2 * job_cap) tab_size *= 2;
+  std::vector<uint32_t> tab(tab_size, 0u);
+  uint32_t cand_count = 0, job_count = 0, tail = 0;
+  sfb::FindArgs f{};
+  f.src_base = sbuf.data() + 17;
+  f.src_off = &zero;
+  f.src_len = &src_len;
+  f.idx = 0;
+  f.cand = cand.data();
+  f.cand_count = &cand_count;
+  f.cand_cap = cand_cap;
+  f.jobs = jobs.data();
+  f.job_count = &job_count;
+  f.job_cap = job_cap;
+  f.job_tab = tab.data();
+  f.tab_mask = tab_size - 1;
+  f.tail_job = &tail;
+  threadIdx.x = 0;
+  blockIdx.x = 0;
+  blockDim.x = 1;
+  gridDim.x = 1;
+  sfb::find_candidates_kernel(f);
+  sfb::verify_candidates_kernel(f);
+  uint32_t n = 0;
+  for (uint32_t j = 1; j < job_count && j < job_cap && n < max_out; ++j) out[n++] = jobs[j].start_bit;
+  return n;
+}
+
 // n_cand > 0: the blocks-side-by-side route of block_finder.cuh with the given candidate block
 // starts (bit positions; the GPU's finder kernels are replaced by the caller's list, which may
 // hold true starts, wrong ones and duplicates): count jobs, chain, writing jobs.

@@ -75,6 +75,15 @@ class Emu:
         assert rc == 0, f"emulated stream kernel wrote outside its dst region (code {rc})"
         return int(st[0]), d[:cap].tobytes(), int(wr[0])
 
+    def find_blocks(self, src: bytes, max_out: int = 1 << 16):
+        """The GPU's block finder kernels on one host thread -> sorted bit positions it accepts."""
+        self.lib.emu_find_blocks.argtypes = [_u8p, C.c_uint64, _u64p, C.c_uint32]
+        self.lib.emu_find_blocks.restype = C.c_uint32
+        s = np.frombuffer(src, dtype=np.uint8) if len(src) else np.zeros(1, np.uint8)
+        out = np.zeros(max_out, np.uint64)
+        k = self.lib.emu_find_blocks(s.ctypes.data_as(_u8p), len(src), out.ctypes.data_as(_u64p), max_out)
+        return sorted(int(x) for x in out[:k])
+
     def set_rec_cap(self, cap: int):
         """How many window records (block_finder.cuh: WinRec) the emulated counting jobs may leave
         behind; when they run out the writing jobs find the span starts out again."""

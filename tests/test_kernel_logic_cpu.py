@@ -228,3 +228,27 @@ def test_size_discovery_mode(emu, oracle, golden):
         for k, (i, src, cap) in enumerate(cases):
             ost, _, owr, _ = oracle.decompress(src, big)
             assert (int(st[k]), int(sz[k])) == (ost, owr), (name, i)
+
+
+def test_block_finder_accepts_what_zlib_writes(emu, oracle):
+    """find_candidates_kernel + verify_candidates_kernel (block_finder.cuh) on one host thread: every
+    dynamic-Huffman block header that zlib wrote (levels 1, 6, 9; text, repetitive and mixed data)
+    must be among the positions the finder accepts, it must accept hardly anything else, and the
+    whole route fed with ITS candidates must give the oracle's result with every dynamic block
+    decoded by a job of its own."""
+    inputs = [(T.text_like(150000, 11), 6), (T.text_like(90000, 12), 1), (T.repetitive(200000, 13), 9),
+              (T.text_like(40000, 14) + T.incompressible(3000, 15) + T.text_like(60000, 16), 6)]
+    for k, (plain, level) in enumerate(inputs):
+        comp = T.raw_deflate(plain, level)
+        starts = oracle.block_starts(comp, len(plain))
+        dynamic = [s for s in starts if ((comp[s >> 3] | (comp[(s >> 3) + 1] << 8) | (comp[(s >> 3) + 2] << 16))
+                                         >> ((s & 7) + 1)) & 3 == 2]
+        found = emu.find_blocks(comp)
+        assert set(d for d in dynamic if d > 0) <= set(found), (k, sorted(set(dynamic) - set(found))[:5])
+        assert len(found) <= len(dynamic) + 2, (k, len(found), len(dynamic))  # false positives are very rare
+        if k in (0, 3):
+            ost, odst, owr, _ = oracle.decompress(comp, len(plain))
+            st, dst, wr, on_chain, tail = emu.stream_decompress_jobs(comp, len(plain), found, phase=5 * k)
+            assert (st, wr) == (ost, owr) and dst == odst
+            if k == 0:
+                assert on_chain == len(starts) >= 2
