@@ -15,7 +15,9 @@
 #pragma once
 
 #include <cstdint>
+#ifndef SFB_CPU_EMU
 #include <cuda_runtime.h>
+#endif
 
 namespace sfb {
 
@@ -155,7 +157,11 @@ __global__ void __launch_bounds__(CHECK_THREADS) container_check_kernel(const Co
   // CRC-32, four bytes per step: T(k, b) = CRC of byte b followed by k zero bytes.  The four tables
   // are kept once PER LANE (entry (k, b) of lane l at word (k * 256 + b) * 32 + l: bank = lane), so
   // the 32 lanes' look-ups at 32 unrelated indices never meet in a bank: 128 KiB, one block per SM.
+#ifdef SFB_CPU_EMU
+  uint32_t* const crc_tab = SFB_EMU_CRC_SMEM;  // tests/cpu_emu: the block's shared memory
+#else
   extern __shared__ uint32_t crc_tab[];
+#endif
   for (uint32_t e = threadIdx.x; e < 1024u; e += blockDim.x) {
     uint32_t c = crc_byte_table_entry(e & 255u);
     for (uint32_t k = 0; k < (e >> 8); ++k) c = crc_byte_table_entry(c & 0xffu) ^ (c >> 8);

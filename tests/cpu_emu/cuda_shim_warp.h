@@ -22,6 +22,7 @@
 #define __align__(n) __attribute__((aligned(n)))
 
 struct emu_dim3 { unsigned x = 0, y = 0, z = 0; };
+struct uint4 { unsigned x, y, z, w; };
 static thread_local emu_dim3 threadIdx, blockIdx;
 static thread_local emu_dim3 blockDim, gridDim;
 

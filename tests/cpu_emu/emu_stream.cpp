@@ -10,6 +10,9 @@
 static uint16_t* emu_stream_smem = nullptr;  // one warp's shared memory, seen by all its lanes
 #define SFB_EMU_SMEM emu_stream_smem
 #include "../../starflate_b200/csrc/huff_stream.cuh"
+static uint32_t* emu_crc_smem = nullptr;
+#define SFB_EMU_CRC_SMEM emu_crc_smem
+#include "../../starflate_b200/csrc/container.cuh"
 
 using StreamCfg = sfb::Cfg<8, 6, 96, 1>;
 
@@ -236,5 +239,58 @@ static int stream_decompress_impl(const uint8_t* src, uint64_t src_len, uint8_t*
   for (uint8_t* q = dp + dst_cap; q < dbuf.data() + dbuf.size(); ++q)
     if (*q != 0xC3) return 1;
   if (dst_cap) std::memcpy(dst, dp, dst_cap);
+  return 0;
+}
+
+// One zlib / gzip container (container.cuh): the parse kernel on one host thread, the payload
+// through the single-stream pass 1 + real pass 2 above, the check kernel on the 32 threads of
+// one emulated warp.  dst must be dst_cap bytes; returns 0, or != 0 if something outside dst changed.
+extern "C" int emu_container(const uint8_t* src, uint64_t src_len, uint32_t container, uint8_t* dst, uint64_t dst_cap,
+                             uint8_t* status, uint64_t* written)
+{
+  std::vector<uint8_t> sbuf(src_len + 64, 0xEE);
+  if (src_len) std::memcpy(sbuf.data() + 19, src, src_len);
+  const uint64_t zero = 0;
+  uint64_t pay_off = 0, pay_len = 0;
+  uint32_t kind = 0, expect = 0, isize = 0;
+  sfb::ContainerArgs c{};
+  c.src_base = sbuf.data() + 19;
+  c.src_off = &zero;
+  c.src_len = &src_len;
+  c.container = container;
+  c.n = 1;
+  c.pay_off = &pay_off;
+  c.pay_len = &pay_len;
+  c.kind = &kind;
+  c.expect = &expect;
+  c.isize = &isize;
+  c.dst_base = dst;
+  c.dst_off = &zero;
+  c.status = status;
+  c.written = written;
+  threadIdx.x = 0;
+  blockIdx.x = 0;
+  blockDim.x = 1;
+  gridDim.x = 1;
+  sfb::container_parse_kernel(c);
+  const int rc = stream_decompress_impl(sbuf.data() + 19 + pay_off, pay_len, dst, dst_cap, 37, status, written,
+                                        nullptr, 0, nullptr);
+  if (rc) return rc;
+  EmuWarp warp;
+  emu_warp = &warp;
+  std::vector<uint32_t> tab(4 * 256 * 32);
+  emu_crc_smem = tab.data();
+  std::vector<std::thread> lanes;
+  for (unsigned l = 0; l < 32; ++l)
+    lanes.emplace_back([&c, l] {
+      threadIdx.x = l;
+      blockIdx.x = 0;
+      blockDim.x = 32;
+      gridDim.x = 1;
+      sfb::container_check_kernel(c);
+    });
+  for (auto& t : lanes) t.join();
+  emu_warp = nullptr;
+  emu_crc_smem = nullptr;
   return 0;
 }

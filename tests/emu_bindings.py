@@ -23,7 +23,7 @@ def build(root_lit=8, root_dist=6, pool=96) -> str:
             os.path.join(emu, "cuda_shim.h"), os.path.join(emu, "cuda_shim_warp.h"),
             os.path.join(csrc, "deflate_lane.cuh"), os.path.join(csrc, "huff_lanes.cuh"),
             os.path.join(csrc, "lz_warp.cuh"), os.path.join(csrc, "huff_stream.cuh"),
-            os.path.join(csrc, "block_finder.cuh")]
+            os.path.join(csrc, "block_finder.cuh"), os.path.join(csrc, "container.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         subprocess.check_call(["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-pthread",
                                f"-DSFB_EMU_ROOT_LIT={root_lit}", f"-DSFB_EMU_ROOT_DIST={root_dist}",
@@ -73,6 +73,19 @@ class Emu:
         rc = self.lib.emu_stream_decompress(p(s, _u8p), len(src), p(d, _u8p), cap, phase, p(st, _u8p),
                                             p(wr, _u64p))
         assert rc == 0, f"emulated stream kernel wrote outside its dst region (code {rc})"
+        return int(st[0]), d[:cap].tobytes(), int(wr[0])
+
+    def container(self, kind: int, src: bytes, cap: int, fill: int = 0xA5):
+        """One zlib (1) / gzip (2) / auto (3) container through the emulated container kernels
+        -> (status, dst bytes, written)"""
+        self.lib.emu_container.argtypes = [_u8p, C.c_uint64, C.c_uint32, _u8p, C.c_uint64, _u8p, _u64p]
+        s = np.frombuffer(src, dtype=np.uint8) if len(src) else np.zeros(1, np.uint8)
+        d = np.full(max(cap, 1), fill, dtype=np.uint8)
+        st = np.zeros(1, np.uint8)
+        wr = np.zeros(1, np.uint64)
+        p = lambda a, t: a.ctypes.data_as(t)
+        rc = self.lib.emu_container(p(s, _u8p), len(src), kind, p(d, _u8p), cap, p(st, _u8p), p(wr, _u64p))
+        assert rc == 0
         return int(st[0]), d[:cap].tobytes(), int(wr[0])
 
     def find_blocks(self, src: bytes, max_out: int = 1 << 16):

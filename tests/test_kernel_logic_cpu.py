@@ -252,3 +252,35 @@ def test_block_finder_accepts_what_zlib_writes(emu, oracle):
             assert (st, wr) == (ost, owr) and dst == odst
             if k == 0:
                 assert on_chain == len(starts) >= 2
+
+
+def test_container_kernels_in_emulation(emu):
+    """container.cuh on the host: header parse (zlib, gzip with every optional field), Adler-32 and
+    CRC-32 by the 32 lanes of one warp (all piece lengths and alignments of short outputs), and the
+    ways a container can be wrong.  Checker: Python's zlib / gzip."""
+    import gzip
+    import struct
+    rng = np.random.default_rng(4)
+    texts = [b"", b"a", b"hello, hello, hello", T.text_like(3000, 1), T.repetitive(9000, 2),
+             bytes(rng.integers(0, 256, 777, dtype=np.uint8))] + [T.text_like(n, 7) for n in (63, 64, 65, 127, 129, 1025)]
+    for k, p in enumerate(texts):
+        for kind, blob in ((1, zlib.compress(p, 6)), (2, gzip.compress(p, mtime=0)), (3, zlib.compress(p, 1)),
+                           (3, gzip.compress(p, mtime=5))):
+            st, dst, wr = emu.container(kind, blob, len(p) + 3)
+            assert (st, wr) == (0, len(p)) and dst[: len(p)] == p and dst[len(p):] == b"\xa5" * 3, (k, kind)
+    p = texts[3]
+    hdr = bytearray(b"\x1f\x8b\x08\x1e" + struct.pack("<I", 7) + b"\x00\x03" + struct.pack("<H", 4) + b"abcd" + b"name\0" +
+                    b"comment\0")
+    hdr += struct.pack("<H", zlib.crc32(bytes(hdr)) & 0xffff)
+    full = bytes(hdr) + T.raw_deflate(p, 9) + struct.pack("<II", zlib.crc32(p), len(p))
+    assert gzip.decompress(full) == p
+    assert emu.container(2, full, len(p))[0::2] == (0, len(p))
+    z, g = zlib.compress(p, 6), gzip.compress(p, mtime=0)
+    flip = lambda s, i, m=1: s[:i] + bytes([s[i] ^ m]) + s[i + 1:]
+    for kind, blob, want in ((1, flip(z, len(z) - 1), 9), (1, flip(z, 1), 8), (1, bytes([0x78, 0xbb]) + z[2:], 8), (1, z[:5], 8),
+                             (2, flip(g, len(g) - 6), 9), (2, flip(g, len(g) - 2), 10), (2, flip(g, 3, 0x20), 8),
+                             (2, full[:len(hdr) - 2] + b"\0\0" + full[len(hdr):], 8), (2, g[:15], 8), (2, z, 8)):
+        st, dst, wr = emu.container(kind, blob, len(p))
+        assert st == want, (kind, want, st)
+    st, dst, wr = emu.container(1, z, len(p) - 1)
+    assert st == 4  # dst too small: the raw decoder's status stands
