@@ -14,7 +14,7 @@ static uint32_t* emu_crc_smem = nullptr;
 #define SFB_EMU_CRC_SMEM emu_crc_smem
 #include "../../starflate_b200/csrc/container.cuh"
 
-using StreamCfg = sfb::Cfg<8, 6, 96, 1>;
+using StreamCfg = sfb::Cfg<7, 5, 96, 1>;  // as capi.cu
 
 // one stream; dst_base must be 128-byte aligned, the stream's region starts at dst_base + dst_off
 static uint32_t emu_rec_cap = 1u << 16;

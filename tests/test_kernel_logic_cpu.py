@@ -136,9 +136,8 @@ def test_single_stream_speculative_pass1(emu, oracle, golden):
     pass 2: golden families (truncations, short destinations, crafted headers, bit flips) and
     multi-window streams, at several dst phases."""
     k = 0
-    for name, stride in (("known_answers", 1), ("crafted_dynamic_headers", 3), ("cut7_starfleet_dynamic", 2339),
-                         ("cut1_multiblock_12000", 5999), ("cap_dynamic_4096", 1999), ("cap_stored_4096", 1999),
-                         ("flip_dynamic_4096", 2999), ("cut7_starfleet_fixed", 2339)):
+    for name, stride in (("known_answers", 1), ("crafted_dynamic_headers", 4), ("cut7_starfleet_dynamic", 4001),
+                         ("cap_dynamic_4096", 1999), ("cap_stored_4096", 1999), ("flip_dynamic_4096", 2999)):
         if name not in golden.families:
             continue
         for i, src, cap in golden.cases(name, stride):
@@ -147,7 +146,7 @@ def test_single_stream_speculative_pass1(emu, oracle, golden):
             k += 1
             assert (st, wr) == (want_st, want_wr), (name, i, cls)
             assert "%016x" % oracle.fnv1a64(dst) == want_hash, (name, i, cls)
-    for kind, size, seed in (("multiblock", 16000, 2),):
+    for kind, size, seed in (("multiblock", 6000, 2),):
         plain, comp = T.make_stream(kind, size, 7000 + seed)
         for cap in (len(plain) - 1000,) if seed != 1 else (len(plain), len(plain) - 1000):
             st, dst, wr = emu.stream_decompress(comp, cap, phase=seed * 31)
