@@ -143,15 +143,16 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.samples = []
+        self.samples = []   # (host time the line arrived, line)
         self.proc = None
         self.index = index
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                 "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -159,16 +160,27 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        """nvidia-smi is started well before (it takes ~0.1 s to come up): only the samples between
+        mark_begin() and mark_end() — the timed region — are reported."""
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        lines = [l for t, l in self.samples if self.t0 is None or (self.t0 <= t <= (self.t1 or t) + 0.03)]
+        if not lines:  # a region shorter than one sampling period: the samples nearest to it
+            lines = [l for t, l in self.samples][-3:]
+        for s in lines:
             f = [x.strip() for x in s.split(",")]
             if len(f) < 7:
                 continue
@@ -320,6 +332,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 0)):
         step()
     barrier()
@@ -334,12 +348,11 @@ def main():
         o, c = int(w["dst_off"][i]), int(w["dst_cap"][i])
         assert zlib.crc32(d_dst[o:o + c].cpu().numpy().tobytes()) == int(w["crc"][i]), f"stream {i}"
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     launches0 = ctx.launch_info()["kernel_launches"]
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
            for _ in range(args.steps)]
     barrier()
+    sampler.mark_begin()
     t_wall0 = time.perf_counter()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
@@ -357,6 +370,7 @@ def main():
     e1.record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
+    sampler.mark_end()
     kern_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = sum(kern_ms) if small else e0.elapsed_time(e1)
     launches = ctx.launch_info()["kernel_launches"] - launches0
