@@ -9,9 +9,9 @@
 //     the reference's copy_from_before (src/decompress.cpp:388-398) would have read, because
 //     its forward-overlapping copy is periodic with period d.
 // Pointers always point backwards, so following them ends at a root after finitely many hops.
-// A round replaces every pointer by its target's pointer (ptr[i] <- ptr[ptr[i]]), halving the
-// number of hops: after r rounds every chain of at most 2^r hops is resolved, whatever the data
-// (a 1 GiB run of one byte is a chain of 2^30 hops: 30 rounds).  Concurrent updates are benign:
+// A round replaces every pointer by the pointer two hops on (ptr[i] <- ptr[ptr[ptr[i]]]), which
+// cuts the number of hops to a third: after r rounds every chain of at most 3^r hops is resolved,
+// whatever the data (the longest chain a 1 GiB output can hold, 2^30 hops: 19 rounds).  Concurrent updates are benign:
 // whatever a thread reads through ptr[p], old or new, is an ancestor of i.
 //
 // The output can be done in STRIPES, one after the other, each to the end: every target in an
