@@ -1,6 +1,8 @@
-// Pass 1 for LARGE SINGLE streams on sm_100a: speculative, self-synchronising Huffman decode,
-// ONE WARP PER STREAM (the first half of the single-stream mode of BASELINE.json's north_star;
-// the second half — the LZ77 resolve — is pass 2, lz_warp.cuh, unchanged).
+// Pass 1 for FEW, LARGE streams on sm_100a: speculative, self-synchronising Huffman decode, ONE
+// WARP PER STREAM — or, for a single large stream, per BLOCK of it (block_finder.cuh finds and
+// chains the blocks; modes 1 and 2 below).  This is the first half of the single-stream mode of
+// BASELINE.json's north_star; the second half, the LZ77 resolve, is lz_jump.cuh for one stream
+// and lz_warp.cuh for a batch of them.
 //
 // A lane per stream (huff_lanes.cuh) leaves a batch of a few big streams on a few lanes.  Here
 // the 32 lanes of a warp decode 32 consecutive bit ranges ("spans", SPAN_BITS each) of the SAME
