@@ -316,14 +316,14 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
   }
   // Few streams: a lane per stream would leave the GPU empty, so each stream gets a warp that
   // decodes 32 spans of it speculatively (huff_stream.cuh).  Same results, by construction.
-  // Measured on B200 with 64 KiB streams: 1 184 streams 2.3 ms against 4.7 ms lane per stream, 2 368
-  // 4.1 against 4.7 ms, 3 552 5.5 against 4.8 ms: up to two streams per resident warp of the lane
+  // Measured on B200 with 64 KiB streams: 1 184 streams 1.8 ms against 4.7 ms lane per stream, 3 552
+  // 4.5 against 4.8 ms, 4 736 5.8 against 5.0 ms: up to three streams per resident warp of the lane
   // kernel.  Small streams do not pay for a warp each (4 KiB pages are 7x slower that way): stream
   // sizes are only known on the device, so the room the caller gave them stands in (at least
   // 32 KiB of dst per stream on average).
   bool stream_mode = ctx->stream_ctas_per_sm > 0 &&
-                     n * 16 <= static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->ctas_per_sm) *
-                                   LaneCfg::WARPS * 32 &&
+                     n * 32 <= 3 * static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->ctas_per_sm) *
+                                       LaneCfg::WARPS * 32 &&
                      dst_bytes / n >= 32768;
   if (const char* e = std::getenv("SFB200_STREAM_MODE")) stream_mode = e[0] == '1' && ctx->stream_ctas_per_sm > 0;
   // One stream: pass 2 works on the whole output at once (lz_jump.cuh) instead of one warp walking it

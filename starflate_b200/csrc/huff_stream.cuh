@@ -35,7 +35,10 @@
 
 namespace sfb {
 
-constexpr uint32_t SPAN_BITS = 2048;
+#ifndef SFB_SPAN_BITS
+#define SFB_SPAN_BITS 1024
+#endif
+constexpr uint32_t SPAN_BITS = SFB_SPAN_BITS;
 
 struct StreamArgs {
   const uint8_t* src_base;
