@@ -213,57 +213,88 @@ __device__ __forceinline__ uint32_t find_bits(const uint8_t* src, uint64_t slen,
 
 __global__ void __launch_bounds__(FIND_THREADS) verify_candidates_kernel(const FindArgs a)
 {
+  // per thread a 128-entry table for the code-length code: 7 input bits -> symbol << 3 | length;
+  // entry k of thread t at byte k * FIND_THREADS + t (threads of a warp never meet in a bank)
+  __shared__ uint8_t s_cl[128 * FIND_THREADS];
+  uint8_t* const lut = s_cl + (threadIdx.x % FIND_THREADS);
   const uint8_t* const src = a.src_base + a.src_off[a.idx];
   const uint64_t slen = a.src_len[a.idx];
   const uint64_t total_bits = 8ull * slen;
+  const uint32_t sh = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(src) & 3u);
   uint32_t n_cand = *a.cand_count;
   if (n_cand > a.cand_cap) n_cand = a.cand_cap;
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x; ci < n_cand; ci += stride) {
     const uint64_t p0 = a.cand[ci];
+    // bit buffer over the 4-byte aligned view of the stream (zero past its end): `have` valid bits
+    // in `buf`, the next word to append is `wi`; `p` counts the bits taken
     uint64_t p = p0 + 3u;
-    const uint32_t n_lit = find_bits(src, slen, p, 5) + 257u;
-    const uint32_t n_dist = find_bits(src, slen, p + 5u, 5) + 1u;
-    const uint32_t ncl = find_bits(src, slen, p + 10u, 4) + 4u;
-    p += 14u;
-    // the code-length code, canonical (RFC 1951 §3.2.2): per length the count and the symbols in order
-    const uint32_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    uint64_t wi = (p + 8u * sh) >> 5;
+    uint64_t buf = static_cast<uint64_t>(find_word(src, slen, sh, wi)) >> ((p + 8u * sh) & 31u);
+    uint32_t have = 32u - static_cast<uint32_t>((p + 8u * sh) & 31u);
+    ++wi;
+    auto take = [&](uint32_t n) -> uint32_t {  // n <= 16
+      if (have < n + 16u) {                     // (keeps >= 16 bits for the peek below: have + 32 <= 64)
+        buf |= static_cast<uint64_t>(find_word(src, slen, sh, wi)) << have;
+        have += 32u;
+        ++wi;
+      }
+      const uint32_t v = static_cast<uint32_t>(buf) & ((1u << n) - 1u);
+      buf >>= n;
+      have -= n;
+      p += n;
+      return v;
+    };
+    const uint32_t n_lit = take(5) + 257u;
+    const uint32_t n_dist = take(5) + 1u;
+    const uint32_t ncl = take(4) + 4u;
+    // the code-length code: lengths in the order of RFC 1951 §3.2.7, canonical codes (§3.2.2),
+    // the table filled with every 7-bit input whose low bits are a (bit-reversed) code
     uint32_t cl[19];
 #pragma unroll
     for (uint32_t c = 0; c < 19; ++c) cl[c] = 0;
-    for (uint32_t c = 0; c < ncl; ++c) cl[order[c]] = find_bits(src, slen, p + 3u * c, 3);
-    p += 3u * ncl;
-    uint32_t count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (uint32_t c = 0; c < 19; ++c) ++count[cl[c]];
-    uint32_t offs[8];
-    offs[1] = 0;
-    for (uint32_t l = 1; l < 7; ++l) offs[l + 1] = offs[l] + count[l];
-    uint32_t sorted[19];
-    for (uint32_t c = 0; c < 19; ++c)
-      if (cl[c]) sorted[offs[cl[c]]++] = c;
+    uint64_t bl_count = 0;  // byte l: number of codes of length l
+#pragma unroll
+    for (uint32_t c = 0; c < 19; ++c) {
+      constexpr uint32_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+      if (c < ncl) {
+        const uint32_t l = take(3);
+        cl[order[c]] = l;
+        if (l) bl_count += 1ull << (8u * l);
+      }
+    }
+    uint64_t next_code = 0;  // byte l: the next code of length l
+    {
+      uint32_t code = 0;
+      for (uint32_t l = 1; l <= 7; ++l) {
+        code = (code + static_cast<uint32_t>((bl_count >> (8u * (l - 1u))) & 255u) * (l > 1u)) << 1;
+        next_code |= static_cast<uint64_t>(code & 255u) << (8u * l);
+      }
+    }
+#pragma unroll
+    for (uint32_t c = 0; c < 19; ++c) {
+      const uint32_t l = cl[c];
+      if (l) {
+        const uint32_t code = static_cast<uint32_t>(next_code >> (8u * l)) & 255u;
+        next_code += 1ull << (8u * l);
+        const uint32_t rev = __brev(code) >> (32u - l);
+        for (uint32_t k = rev; k < 128u; k += 1u << l) lut[k * FIND_THREADS] = static_cast<uint8_t>((c << 3) | l);
+      }
+    }
     // the HLIT + HDIST lengths
     const uint32_t total = n_lit + n_dist;
     uint32_t i = 0, prev = 0, kraft_lit = 0, kraft_dist = 0, dist_codes = 0, eob_len = 0;
     bool ok = true;
     while (ok && i < total) {
-      // one code-length symbol, bit by bit
-      uint32_t code = 0, first = 0, index = 0, sym = 99, len = 1;
-      const uint32_t bits = find_bits(src, slen, p, 7);
-      for (; len <= 7; ++len) {
-        code |= (bits >> (len - 1u)) & 1u;
-        const uint32_t cnt = count[len];
-        if (code < first + cnt) {
-          sym = sorted[index + (code - first)];
-          break;
-        }
-        index += cnt;
-        first = (first + cnt) << 1;
-        code <<= 1;
+      if (have < 16u) {
+        buf |= static_cast<uint64_t>(find_word(src, slen, sh, wi)) << have;
+        have += 32u;
+        ++wi;
       }
-      if (sym > 18u) {
-        ok = false;
-        break;
-      }
+      const uint32_t e = lut[(static_cast<uint32_t>(buf) & 127u) * FIND_THREADS];
+      const uint32_t len = e & 7u, sym = e >> 3;
+      buf >>= len;
+      have -= len;
       p += len;
       uint32_t rep = 1, val = sym;
       if (sym == 16u) {
@@ -271,16 +302,13 @@ __global__ void __launch_bounds__(FIND_THREADS) verify_candidates_kernel(const F
           ok = false;
           break;
         }
-        rep = 3u + find_bits(src, slen, p, 2);
-        p += 2u;
+        rep = 3u + take(2);
         val = prev;
       } else if (sym == 17u) {
-        rep = 3u + find_bits(src, slen, p, 3);
-        p += 3u;
+        rep = 3u + take(3);
         val = 0;
       } else if (sym == 18u) {
-        rep = 11u + find_bits(src, slen, p, 7);
-        p += 7u;
+        rep = 11u + take(7);
         val = 0;
       }
       if (i + rep > total) {
@@ -288,16 +316,12 @@ __global__ void __launch_bounds__(FIND_THREADS) verify_candidates_kernel(const F
         break;
       }
       if (val) {
-        for (uint32_t r = 0; r < rep; ++r) {
-          const uint32_t at = i + r;
-          if (at < n_lit) {
-            kraft_lit += 32768u >> val;
-            if (at == 256u) eob_len = val;
-          } else {
-            kraft_dist += 32768u >> val;
-            ++dist_codes;
-          }
-        }
+        const uint32_t lit_end = i + rep < n_lit ? i + rep : n_lit;
+        const uint32_t in_lit = lit_end > i ? lit_end - i : 0u;
+        kraft_lit += in_lit * (32768u >> val);
+        kraft_dist += (rep - in_lit) * (32768u >> val);
+        dist_codes += rep - in_lit;
+        if (i <= 256u && 256u < i + rep) eob_len = val;
       }
       prev = val;
       i += rep;
