@@ -365,7 +365,8 @@ def crafted_lz_streams():
     out = []
     rng = np.random.default_rng(99)
     for lead in (0, 1, 2, 3, 5, 31, 61, 126, 127, 128, 129, 200, 257):
-        for dist, reps in ((1, 5), (2, 3), (3, 3), (7, 3), (127, 2), (128, 3), (129, 3), (200, 3), (258, 2), (1000, 2)):
+        for dist, reps in ((1, 5), (2, 3), (3, 3), (4, 3), (5, 4), (6, 3), (7, 3), (9, 3), (13, 2), (24, 2), (127, 2),
+                           (128, 3), (129, 3), (200, 3), (258, 2), (1000, 2)):
             w = BitWriter()
             blk = fixed_block(w, True)
             n = max(lead, dist)
@@ -396,4 +397,20 @@ def crafted_lz_streams():
             total += 1
     blk.eob()
     out.append(("dense_short", w.tobytes(), total))
+    # back-to-back 3-byte matches (two heads in one 4-byte word) at every word phase, sources near
+    # the very start of the stream (the word below the first byte must not be read)
+    for lead in (1, 2, 3, 4, 5, 6, 7):
+        w = BitWriter()
+        blk = fixed_block(w, True)
+        for b in rng.integers(32, 127, lead):
+            blk.literal(int(b))
+        total = lead
+        for i in range(120):
+            d = min(total, int(rng.choice([1, 2, 3, 4, 5, 6, 7, 8, 30, 131])))
+            if i % 5 == 4:
+                d = total  # the source is the first bytes of the stream
+            blk.match(3 if i % 3 else 4, d)
+            total += 3 if i % 3 else 4
+        blk.eob()
+        out.append((f"threes_lead{lead}", w.tobytes(), total))
     return out
