@@ -4,7 +4,7 @@
 #include "../../include/starflate_b200.h"
 #include "huff_lanes.cuh"
 #include "huff_stream.cuh"
-#include "lz_seg.cuh"
+#include "lz_warp.cuh"
 #include "lz_jump.cuh"
 #include "container.cuh"
 
@@ -60,7 +60,6 @@ struct sfb200_ctx {
   int regs_per_thread = 0;
   int lz_ctas_per_sm = 0;
   int lz_regs_per_thread = 0;
-  bool lz_v1 = false;  // SFB200_LZ_V1=1: the first-generation resolve kernel (A/B measurements)
   int small_ctas_per_sm = 0;   // SmallCfg pass 1 (0: not usable)
   int small_regs_per_thread = 0;
   int stream_ctas_per_sm = 0;  // huff_stream_kernel (0: not usable)
@@ -179,7 +178,6 @@ int sfb200_create(int device, sfb200_ctx** out)
     int cap = SFB_LZ_CTAS_PER_SM;
     if (const char* e = std::getenv("SFB200_LZ_CTAS_PER_SM")) cap = std::atoi(e);
     ctx->lz_ctas_per_sm = (cap > 0 && cap < lz_per_sm) ? cap : lz_per_sm;
-    if (const char* e = std::getenv("SFB200_LZ_V1")) ctx->lz_v1 = e[0] == '1';
     cudaFuncAttributes lfa;
     if (cudaFuncGetAttributes(&lfa, sfb::lz_resolve_kernel) == cudaSuccess)
       ctx->lz_regs_per_thread = lfa.numRegs;
@@ -670,8 +668,7 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
       const uint64_t resident =
           static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->lz_ctas_per_sm);
       const unsigned grid = static_cast<unsigned>(want < resident ? want : resident);
-      if (ctx->lz_v1) sfb::lz_resolve_v1_kernel<<<grid, sfb::LZ_THREADS, 0, s2>>>(r);
-      else sfb::lz_resolve_kernel<<<grid, sfb::LZ_THREADS, 0, s2>>>(r);
+      sfb::lz_resolve_kernel<<<grid, sfb::LZ_THREADS, 0, s2>>>(r);
       SFB_TRY(ctx, cudaGetLastError());
     }
     ctx->launches += 1;

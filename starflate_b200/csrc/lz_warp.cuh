@@ -147,7 +147,7 @@ __device__ __forceinline__ uint32_t lz_mod_small(uint32_t k, uint32_t d)
 
 // (launched with 6 CTAs = 48 warps per SM: measured best on C2 — with 64 the streams in flight push
 //  each other out of the L2, and squeezing the code under 40 registers costs more than it gains)
-__global__ void __launch_bounds__(LZ_THREADS, 5) lz_resolve_v1_kernel(const ResolveArgs a)
+__global__ void __launch_bounds__(LZ_THREADS, 5) lz_resolve_kernel(const ResolveArgs a)
 {
   constexpr unsigned FULL = 0xffffffffu;
   const uint32_t lane = threadIdx.x & 31u;

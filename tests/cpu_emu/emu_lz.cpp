@@ -6,7 +6,7 @@
 #include <thread>
 #include <vector>
 
-#include "../../starflate_b200/csrc/lz_seg.cuh"
+#include "../../starflate_b200/csrc/lz_warp.cuh"
 
 extern "C" void emu_lz_resolve(uint8_t* dst_base, const uint64_t* dst_off, const uint64_t* written,
                                const uint32_t* match_bits, uint64_t n)
