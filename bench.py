@@ -51,6 +51,18 @@ def _html_plain(size: int, seed: int) -> bytes:
 
 
 _CONTAINER = "raw"
+_GOLD = np.uint64(0x9E3779B97F4A7C15)
+
+
+def _weighted_sum(plain: bytes) -> int:
+    """sfb200_checksum_batch_device's position-weighted sum (include/starflate_b200.h), on the host."""
+    total = np.uint64(0)
+    with np.errstate(over="ignore"):
+        for o in range(0, len(plain), 1 << 22):  # (pieces: a 1 GiB stream would need 30 GB of temporaries)
+            b = np.frombuffer(plain, dtype=np.uint8, count=min(1 << 22, len(plain) - o), offset=o).astype(np.uint64)
+            j = np.arange(o + 1, o + len(b) + 1, dtype=np.uint64)
+            total += ((b + np.uint64(1)) * ((_GOLD * j) | np.uint64(1))).sum(dtype=np.uint64)
+    return int(total)
 
 
 def _wrap(comp: bytes, plain: bytes) -> bytes:
@@ -69,18 +81,22 @@ def _gen_one(args):
         plain = _html_plain(size, seed)
         co = zlib.compressobj(6, zlib.DEFLATED, -15, 8, zlib.Z_DEFAULT_STRATEGY)
         comp = co.compress(plain) + co.flush()
-        return _wrap(comp, plain), zlib.crc32(plain), len(plain)
+        return _wrap(comp, plain), zlib.crc32(plain), len(plain), _weighted_sum(plain)
     if kind == "single":
         plain = T.big_text(size, seed)
         comp = T.raw_deflate(plain, 6)
-        return _wrap(comp, plain), zlib.crc32(plain), len(plain)
+        return _wrap(comp, plain), zlib.crc32(plain), len(plain), 0  # (one large stream: its whole CRC-32 is checked)
     plain, comp = T.make_stream(kind, size, seed)
     assert T.first_block_type(comp) == {"dynamic": 2, "fixed": 1, "stored": 0}.get(kind, 2) or kind in ("repetitive", "multiblock")
-    return _wrap(comp, plain), zlib.crc32(plain), len(plain)
+    return _wrap(comp, plain), zlib.crc32(plain), len(plain), _weighted_sum(plain)
 
 
-def make_workload(name: str, n_streams: int, unique: int, rank: int, container: str = "raw"):
-    """-> dict(src u8, src_off, src_len, dst_off, dst_cap (u64 numpy), total_out, desc)."""
+def make_workload(name: str, n_streams: int, unique: int, rank: int, container: str = "raw", first: int = 0,
+                  shared_seeds: bool = False):
+    """-> dict(src u8, src_off, src_len, dst_off, dst_cap (u64 numpy), total_out, desc).
+    `first`, `shared_seeds`: streams [first, first + n_streams) of ONE global batch (stream g has
+    seed number g mod unique whatever the rank: the shards of a strong-scaling run add up to the
+    same batch at every GPU count)."""
     if name == "c2":
         kind, size = "dynamic", 65536
     elif name == "c3":
@@ -95,22 +111,30 @@ def make_workload(name: str, n_streams: int, unique: int, rank: int, container: 
         kind, size = "html", 65536
     else:
         raise ValueError(name)
-    unique = min(unique, n_streams)
+    if shared_seeds:
+        ids = np.unique((first + np.arange(n_streams)) % unique)   # the seeds this shard needs
+    else:
+        unique = min(unique, n_streams)
+        ids = np.arange(unique)
     jobs = []
-    for i in range(unique):
-        k = kind if kind != "mixed" else ["stored", "fixed", "dynamic"][i % 3]
-        jobs.append((k, size, 1_000_003 * (rank + 1) + i, container))
+    for i in ids:
+        k = kind if kind != "mixed" else ["stored", "fixed", "dynamic"][int(i) % 3]
+        jobs.append((k, size, 1_000_003 * ((0 if shared_seeds else rank) + 1) + int(i), container))
+    unique_here = len(jobs)
     workers = max(1, min(os.cpu_count() or 1, 64))
     t0 = time.time()
     with ProcessPoolExecutor(workers) as ex:
-        res = list(ex.map(_gen_one, jobs, chunksize=max(1, unique // (workers * 4))))
+        res = list(ex.map(_gen_one, jobs, chunksize=max(1, unique_here // (workers * 4))))
     gen_s = time.time() - t0
     comp = [r[0] for r in res]
     lens = np.array([len(c) for c in comp], dtype=np.uint64)
-    offs = np.zeros(unique, dtype=np.uint64)
+    offs = np.zeros(unique_here, dtype=np.uint64)
     offs[1:] = np.cumsum(lens)[:-1]
     src = np.frombuffer(b"".join(comp), dtype=np.uint8)
-    sel = np.arange(n_streams) % unique
+    if shared_seeds:
+        sel = np.searchsorted(ids, (first + np.arange(n_streams)) % unique)
+    else:
+        sel = np.arange(n_streams) % unique
     caps = np.array([r[2] for r in res], dtype=np.uint64)[sel]
     dst_off = np.zeros(n_streams, dtype=np.uint64)
     dst_off[1:] = np.cumsum(caps)[:-1]
@@ -118,19 +142,19 @@ def make_workload(name: str, n_streams: int, unique: int, rank: int, container: 
     src_len = lens[sel]
     src_off = np.zeros(n_streams, dtype=np.uint64)
     src_off[1:] = np.cumsum(src_len)[:-1]
-    if unique == n_streams:
+    if unique_here == n_streams and not shared_seeds:
         src_full = src
     else:
-        src_full = np.empty(int(src_len.sum()), dtype=np.uint8)
-        for i in range(n_streams):
-            u = int(sel[i])
-            src_full[int(src_off[i]):int(src_off[i]) + int(lens[u])] = src[int(offs[u]):int(offs[u]) + int(lens[u])]
+        # (gather with one index array: stream i's bytes are src[offs[u] ...], u = sel[i])
+        rep = np.repeat(offs[sel].astype(np.int64) - src_off.astype(np.int64), src_len.astype(np.int64))
+        src_full = src[np.arange(int(src_len.sum()), dtype=np.int64) + rep]
     return {
         "src": src_full, "src_off": src_off, "src_len": src_len, "dst_off": dst_off, "dst_cap": caps,
         "total_out": int(caps.sum()), "total_in": int(src_len.sum()), "n": n_streams,
         "crc": np.array([r[1] for r in res], dtype=np.uint64)[sel], "gen_s": gen_s,
+        "sum": np.array([r[3] for r in res], dtype=np.uint64)[sel],
         "desc": f"{name}: {n_streams} x {size} B {kind} level-{'9' if name == 'c4' else '6'} streams"
-                f" ({unique} unique seeds, zlib {zlib.ZLIB_RUNTIME_VERSION})"
+                f" ({unique_here} unique seeds, zlib {zlib.ZLIB_RUNTIME_VERSION})"
                 + ("" if container == "raw" else f", each in a {container} container (checksum verified on the device)"),
     }
 
@@ -253,6 +277,9 @@ def main():
                     help="wrap every stream in a zlib / gzip container and verify its checksum on the device "
                          "(extension; the BASELINE metric is raw)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-shapes", action="store_true", help="only the headline workload (skip the sharded C3 batch "
+                    "and the C1 / C4 / C5 lines)")
+    ap.add_argument("--shard-streams", type=int, default=1048576, help="streams of the sharded (strong-scaling) batch")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
@@ -305,26 +332,7 @@ def main():
     if world > 1:
         dist.barrier()
     ctx = S.Context(local_rank)
-
-    w = make_workload(args.workload, n_streams, unique, rank, args.container)
-    n = w["n"]
-    to_i64 = lambda a: torch.from_numpy(a.view(np.int64))
-    h_src = torch.from_numpy(w["src"]).pin_memory()
-    d_src = h_src.to(dev, non_blocking=True)
-    d_src_off, d_src_len = to_i64(w["src_off"]).to(dev), to_i64(w["src_len"]).to(dev)
-    d_dst_off, d_dst_cap = to_i64(w["dst_off"]).to(dev), to_i64(w["dst_cap"]).to(dev)
-    d_dst = torch.zeros(w["total_out"] + 64, dtype=torch.uint8, device=dev)
-    d_status = torch.zeros(n, dtype=torch.uint8, device=dev)
-    d_written = torch.zeros(n, dtype=torch.int64, device=dev)
-
-    def step():
-        if args.container != "raw":
-            ctx.decompress_container_batch_device({"zlib": ctx.ZLIB, "gzip": ctx.GZIP}[args.container], d_src,
-                                                  d_src_off, d_src_len, d_dst, d_dst_off, d_dst_cap, d_status,
-                                                  d_written)
-            return
-        ctx.decompress_batch_device(d_src, d_src_off, d_src_len, d_dst, d_dst_off, d_dst_cap,
-                                    d_status, d_written)
+    peak, peak_src = measured_peak_gbs()
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -332,122 +340,213 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    for _ in range(max(args.warmup, 0)):
-        step()
-    barrier()
-    # correctness gate before timing anything: status, sizes and a checksum of every stream
-    assert int(d_status.max()) == 0, "decode failed"
-    assert torch.equal(d_written, d_dst_cap)
-    sums = torch.zeros(n, dtype=torch.int64, device=dev)
-    ctx.checksum_batch_device(d_dst, d_dst_off, d_written, sums)
-    sample = np.unique(np.linspace(0, n - 1, 64).astype(np.int64))
-    torch.cuda.synchronize(dev)
-    for i in sample:
-        o, c = int(w["dst_off"][i]), int(w["dst_cap"][i])
-        assert zlib.crc32(d_dst[o:o + c].cpu().numpy().tobytes()) == int(w["crc"][i]), f"stream {i}"
-
-    launches0 = ctx.launch_info()["kernel_launches"]
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-           for _ in range(args.steps)]
-    barrier()
-    sampler.mark_begin()
-    t_wall0 = time.perf_counter()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
-    # small workloads (C1) would sit in the 126 MB L2 from one step to the next: flush it in between
-    # (outside the per-step events, which are then what is summed)
-    small = w["total_in"] + w["total_out"] < (512 << 20)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if small else None
-    e0.record()
-    for a, b in evs:
-        if small:
-            flush.fill_(1)
-        a.record()
-        step()
-        b.record()
-    e1.record()
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    sampler.mark_end()
-    kern_ms = [a.elapsed_time(b) for a, b in evs]
-    total_ms = sum(kern_ms) if small else e0.elapsed_time(e1)
-    launches = ctx.launch_info()["kernel_launches"] - launches0
-    clocks = sampler.stop()
-    total_ms = sharding.max_over_ranks(total_ms, dev)  # a sharded job is as slow as its slowest rank
-    ms_per_step = total_ms / args.steps
-    value = world * w["total_out"] / (ms_per_step * 1e-3) / 1e9
-
-    # ---- end to end through the public host-buffer API (H2D + kernel + D2H every step) --------
-    e2e = None
-    if not args.no_e2e and args.container == "raw":
-        h_dst = torch.empty(w["total_out"], dtype=torch.uint8).pin_memory()
-        h_np_dst = h_dst.numpy()
-        e_steps = max(1, min(args.steps, 3))
-        ctx.decompress_batch_host(w["src"], w["src_off"], w["src_len"], h_np_dst, w["dst_off"], w["dst_cap"])
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
-            st, wr = ctx.decompress_batch_host(h_src.numpy(), w["src_off"], w["src_len"], h_np_dst,
-                                               w["dst_off"], w["dst_cap"])
-        barrier()
-        dt = (time.perf_counter() - t0) / e_steps
-        assert not st.any()
-        dt = sharding.max_over_ranks(dt, dev)
-        e2e = {"value": world * w["total_out"] / dt / 1e9, "unit": UNIT,
-               "h2d_bytes_per_step": int(w["total_in"] + 32 * n),
-               "d2h_bytes_per_step": int(w["total_out"] + 9 * n),
-               "steps": e_steps, "timer": "host wall clock around sfb200_decompress_batch_host (pinned buffers)"}
-
-    # per-pass device time (CUDA events recorded inside the C-ABI call on its stream), taken
-    # on a few extra steps after the timed region so that the synchronising query stays out of it
-    pass_ms = []
-    for _ in range(3):
-        step()
-        pass_ms.append(ctx.last_pass_ms())
-    clear_ms, p1_ms, p2_ms = [float(x) for x in np.mean(np.array(pass_ms), axis=0)]
-
-    peak, peak_src = measured_peak_gbs()
-    k_ms = float(np.mean(kern_ms))
-    algo_bytes = w["total_in"] + w["total_out"]
-    achieved = algo_bytes / (k_ms * 1e-3) / 1e9
-    single = n == 1
-    k1 = "find/verify candidates + huff_stream_kernel x2 + chain (pass 1)" if single else "huff_lanes_kernel (pass 1)"
-    k2 = "lz_jump_* (pass 2)" if single else "lz_resolve_kernel (pass 2)"
-    dominant = k1 if p1_ms >= p2_ms else k2
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
+    def traffic_of(name):
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
         try:
-            traffic = json.load(open(tpath)).get(args.workload)
+            return json.load(open(tpath)).get(name)
         except Exception:
-            traffic = None
+            return None
+
+    def measure(name, w, steps, warmup, want_e2e, streams_total=None):
+        """One workload on this rank's GPU: device-timed steps (CUDA events, max over ranks), the
+        correctness gate, per-pass times, optionally the end-to-end number through host buffers."""
+        n = w["n"]
+        to_i64 = lambda a: torch.from_numpy(a.view(np.int64))
+        h_src = torch.from_numpy(w["src"]).pin_memory() if want_e2e else torch.from_numpy(w["src"])
+        d_src = h_src.to(dev, non_blocking=True)
+        d_src_off, d_src_len = to_i64(w["src_off"]).to(dev), to_i64(w["src_len"]).to(dev)
+        d_dst_off, d_dst_cap = to_i64(w["dst_off"]).to(dev), to_i64(w["dst_cap"]).to(dev)
+        d_dst = torch.zeros(w["total_out"] + 64, dtype=torch.uint8, device=dev)
+        d_status = torch.zeros(n, dtype=torch.uint8, device=dev)
+        d_written = torch.zeros(n, dtype=torch.int64, device=dev)
+
+        def step():
+            if args.container != "raw":
+                ctx.decompress_container_batch_device({"zlib": ctx.ZLIB, "gzip": ctx.GZIP}[args.container], d_src,
+                                                      d_src_off, d_src_len, d_dst, d_dst_off, d_dst_cap, d_status,
+                                                      d_written)
+                return
+            ctx.decompress_batch_device(d_src, d_src_off, d_src_len, d_dst, d_dst_off, d_dst_cap,
+                                        d_status, d_written)
+
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        for _ in range(max(warmup, 0)):
+            step()
+        barrier()
+        # correctness gate before timing anything: status, sizes, and the position-weighted checksum
+        # of EVERY stream (computed on the device) against the generator's, plus the CRC-32 of a sample
+        assert int(d_status.max()) == 0, "decode failed"
+        assert torch.equal(d_written, d_dst_cap)
+        sums = torch.zeros(n, dtype=torch.int64, device=dev)
+        ctx.checksum_batch_device(d_dst, d_dst_off, d_written, sums)
+        torch.cuda.synchronize(dev)
+        if n > 1:
+            bad = np.nonzero(sums.cpu().numpy().view(np.uint64) != w["sum"])[0]
+            assert len(bad) == 0, f"{name}: {len(bad)} of {n} streams decoded to the wrong bytes (first: stream {int(bad[0])})"
+        for i in np.unique(np.linspace(0, n - 1, 16).astype(np.int64)):
+            o, c = int(w["dst_off"][i]), int(w["dst_cap"][i])
+            assert zlib.crc32(d_dst[o:o + c].cpu().numpy().tobytes()) == int(w["crc"][i]), f"stream {i}"
+
+        launches0 = ctx.launch_info()["kernel_launches"]
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        sampler.mark_begin()
+        t_wall0 = time.perf_counter()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        # small workloads (C1) would sit in the 126 MB L2 from one step to the next: flush it in between
+        # (outside the per-step events, which are then what is summed)
+        small = w["total_in"] + w["total_out"] < (512 << 20)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if small else None
+        e0.record()
+        for a, b in evs:
+            if small:
+                flush.fill_(1)
+            a.record()
+            step()
+            b.record()
+        e1.record()
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+        sampler.mark_end()
+        kern_ms = [a.elapsed_time(b) for a, b in evs]
+        total_ms = sum(kern_ms) if small else e0.elapsed_time(e1)
+        launches = ctx.launch_info()["kernel_launches"] - launches0
+        clocks = sampler.stop()
+        total_ms = sharding.max_over_ranks(total_ms, dev)  # a sharded job is as slow as its slowest rank
+        ms_per_step = total_ms / steps
+        out_all = streams_total["total_out"] if streams_total else world * w["total_out"]
+        value = out_all / (ms_per_step * 1e-3) / 1e9
+
+        e2e = None
+        if want_e2e:
+            h_dst = torch.empty(w["total_out"], dtype=torch.uint8).pin_memory()
+            h_np_dst = h_dst.numpy()
+            e_steps = max(1, min(steps, 3))
+            ctx.decompress_batch_host(w["src"], w["src_off"], w["src_len"], h_np_dst, w["dst_off"], w["dst_cap"])
+            # what the host link gives this rank while all ranks copy at once (the ceiling of e2e:
+            # every decompressed byte crosses it once)
+            d_probe = d_dst[: min(w["total_out"], 1 << 30)]
+            h_probe = h_dst[: d_probe.numel()]
+            barrier()
+            t0 = time.perf_counter()
+            h_probe.copy_(d_probe, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            d2h_gbs = d_probe.numel() / (time.perf_counter() - t0) / 1e9
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                st, wr = ctx.decompress_batch_host(h_src.numpy(), w["src_off"], w["src_len"], h_np_dst,
+                                                   w["dst_off"], w["dst_cap"])
+            barrier()
+            dt = (time.perf_counter() - t0) / e_steps
+            assert not st.any()
+            o, c = int(w["dst_off"][n - 1]), int(w["dst_cap"][n - 1])
+            assert zlib.crc32(h_np_dst[o:o + c].tobytes()) == int(w["crc"][n - 1])
+            dt = sharding.max_over_ranks(dt, dev)
+            d2h_min = -sharding.max_over_ranks(-d2h_gbs, dev)
+            e2e = {"value": world * w["total_out"] / dt / 1e9, "unit": UNIT,
+                   "h2d_bytes_per_step": int(w["total_in"] + 32 * n),
+                   "d2h_bytes_per_step": int(w["total_out"] + 9 * n),
+                   "steps": e_steps, "timer": "host wall clock around sfb200_decompress_batch_host (pinned buffers)",
+                   "device_staging_bytes": ctx.staging_bytes(),
+                   "host_link": {"d2h_gbs_per_rank_all_ranks_copying": d2h_min,
+                                 "frac_of_link": (w["total_out"] / dt / 1e9) / d2h_min if d2h_min else None,
+                                 "note": "every decompressed byte crosses PCIe device-to-host once: the measured "
+                                         "pinned D2H rate (slowest rank, all ranks copying at the same time) is "
+                                         "the ceiling of this number"}}
+            del h_dst
+
+        # per-pass device time (CUDA events recorded inside the C-ABI call on its stream), taken
+        # on a few extra steps after the timed region so that the synchronising query stays out of it
+        pass_ms = []
+        for _ in range(3):
+            step()
+            pass_ms.append(ctx.last_pass_ms())
+        clear_ms, p1_ms, p2_ms = [float(x) for x in np.mean(np.array(pass_ms), axis=0)]
+        k_ms = float(np.mean(kern_ms))
+        algo_bytes = w["total_in"] + w["total_out"]
+        achieved = algo_bytes / (k_ms * 1e-3) / 1e9
+        single = n == 1
+        k1 = "find/verify candidates + huff_stream_kernel x2 + chain (pass 1)" if single else "huff_lanes_kernel (pass 1)"
+        k2 = "lz_jump_* (pass 2)" if single else "lz_resolve_kernel (pass 2)"
+        res = {
+            "value": value, "ms_per_step": ms_per_step, "steps": steps,
+            "workload": w["desc"], "streams_per_gpu": n, "compressed_bytes_per_gpu": w["total_in"],
+            "decompressed_bytes_per_gpu": w["total_out"],
+            "l2": ("L2 flushed (256 MB written) before every timed step; value = sum of the per-step events"
+                   if small else "inputs+outputs far exceed the 126 MB L2; no flush needed"),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic_of(name), "peak_source": peak_src,
+                         "kernel": "whole step: scratch clear + " + k1 + " + " + k2,
+                         "dominant_kernel": k1 if p1_ms >= p2_ms else k2, "step_ms": k_ms,
+                         "algorithmic_bytes": algo_bytes,
+                         "note": "achieved = (compressed read + decompressed written) / device time of the "
+                                 "WHOLE step, not of the dominant kernel alone; with more than two waves of "
+                                 "streams the passes overlap on two internal streams: passes_ms then gives "
+                                 "clear | start of pass 1 .. end of its last wave | the part of pass 2 after that",
+                         "passes_ms": {"clear": clear_ms, k1.split(" (")[0]: p1_ms, k2.split(" (")[0]: p2_ms},
+                         "frac_of_nominal_8TBs": achieved / 8000.0},
+            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "wall_s_timed_region": t_wall,
+            "gate": f"status, written and the device checksum of all {n} streams against the generator's; CRC-32 of 16",
+        }
+        del d_src, d_dst, d_status, d_written, sums
+        torch.cuda.empty_cache()
+        return res
+
+    # ---- the headline workload (BASELINE.json's metric is quoted on C2) ---------------------------
+    w = make_workload(args.workload, n_streams, unique, rank, args.container)
+    head = measure(args.workload, w, args.steps, args.warmup, not args.no_e2e and args.container == "raw")
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": w["desc"], "streams_per_gpu": n, "compressed_bytes_per_gpu": w["total_in"],
-                   "decompressed_bytes_per_gpu": w["total_out"], "parallelism": f"shard{world} (no collective)",
-                   "l2": ("L2 flushed (256 MB written) before every timed step; value = sum of the per-step events"
-                          if small else "inputs+outputs far exceed the 126 MB L2; no flush needed"),
+        "config": {"workload": head["workload"], "streams_per_gpu": head["streams_per_gpu"],
+                   "compressed_bytes_per_gpu": head["compressed_bytes_per_gpu"],
+                   "decompressed_bytes_per_gpu": head["decompressed_bytes_per_gpu"],
+                   "parallelism": f"shard{world} (no collective)", "l2": head["l2"], "gate": head["gate"],
                    "launch": ctx.launch_info()},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "kernel": dominant, "kernel_ms": k_ms,
-                     "algorithmic_bytes": algo_bytes,
-                     "note": "achieved = (compressed read + decompressed written) / device time of the "
-                             "WHOLE step (scratch clear + pass 1 + pass 2), not of the dominant kernel alone; "
-                             "with more than one wave of streams the passes overlap on two internal streams: "
-                             "passes_ms then gives clear | start of pass 1 .. end of its last wave | the part "
-                             "of pass 2 that runs after that",
-                     "passes_ms": {"clear": clear_ms, k1.split(" (")[0]: p1_ms, k2.split(" (")[0]: p2_ms},
-                     "frac_of_nominal_8TBs": achieved / 8000.0},
-        "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
-        "wall_s_timed_region": t_wall,
+        "roofline": head["roofline"], "clocks": head["clocks"], "gpu_launches": head["gpu_launches"],
+        "e2e": head["e2e"], "wall_s_timed_region": head["wall_s_timed_region"],
     }
     if rank == 0 and world == 1 and not args.no_cpu and args.container == "raw":
         line["cpu_baseline"], _ = cpu_baseline(w, args.cpu_seconds)
+    del w
+
+    # ---- one batch sharded across the ranks (BASELINE configs[2]: 1M 4 KiB pages, mixed blocks):
+    #      the same 1 048 576 streams at every GPU count, cut with the library's partition ----------
+    if not args.no_shapes and args.workload == "c2" and args.container == "raw":
+        total = args.shard_streams
+        # (all pages hold 4096 bytes and the three kinds cycle, so equal counts are the balanced cut;
+        #  ragged batches go through sfb200_partition_streams — tests/test_sharding_gloo.py)
+        first = total * rank // world
+        count = total * (rank + 1) // world - first
+        ws = make_workload("c3", count, 65536, rank, first=first, shared_seeds=True)
+        tot = {"total_out": total * 4096}
+        r = measure("c3", ws, max(3, min(args.steps, 5)), 3, False, streams_total=tot)
+        line["sharded"] = {"workload": f"c3: {total} x 4096 B pages (stored / fixed / dynamic by turns), ONE batch cut "
+                                       f"into {world} contiguous shard(s), one per GPU, no collective",
+                           "scaling": "strong", "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"],
+                           "streams_total": total, "streams_this_rank": count, "roofline_frac": r["roofline"]["frac"],
+                           "passes_ms": r["roofline"]["passes_ms"], "clocks": r["clocks"]}
+        del ws
+    # ---- the other named shapes, 1 GPU (north_star: "each named shape is reported") ---------------
+    if not args.no_shapes and world == 1 and args.workload == "c2" and args.container == "raw":
+        shapes = {}
+        for nm, ns, uq, st in (("c1", 1, 1, 5), ("c4", 16384, 128, 3), ("c5", 1, 1, 3)):
+            wsh = make_workload(nm, ns, uq, rank)
+            r = measure(nm, wsh, st, 3, False)
+            shapes[nm] = {k: r[k] for k in ("workload", "value", "ms_per_step", "steps", "clocks", "gpu_launches", "l2")}
+            shapes[nm]["unit"] = UNIT
+            shapes[nm]["roofline"] = {k: r["roofline"][k] for k in ("achieved", "peak", "frac", "passes_ms", "algorithmic_bytes")}
+            del wsh
+        if "sharded" in line:
+            shapes["c3"] = {"see": "sharded (the same workload; at 1 GPU the shard is the whole batch)",
+                            "value": line["sharded"]["value"], "ms_per_step": line["sharded"]["ms_per_step"],
+                            "unit": UNIT, "roofline": {"frac": line["sharded"]["roofline_frac"]},
+                            "clocks": line["sharded"]["clocks"]}
+        line["shapes"] = shapes
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SFB200_ABI_VERSION 3
+#define SFB200_ABI_VERSION 4
 
 /* starflate::DecompressStatus, numeric values preserved (src/decompress.hpp:13-23). */
 enum sfb200_status {
@@ -78,7 +78,8 @@ int sfb200_abi_version(void);
  * aligned words, only words that hold at least one byte of a stream's region, and only the
  * region's own bytes are ever modified.
  * Threading: a context serves one call at a time (it owns scratch buffers and streams); use one
- * context per thread or serialise calls, as the C++ layer does.
+ * context per thread (the C++ layer does) or serialise calls.  Every entry point leaves the calling
+ * thread's current CUDA device as it found it.
  * `cuda_stream` is a cudaStream_t (NULL = default stream); the call is asynchronous. */
 int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
                                    const uint64_t* src_off, const uint64_t* src_len,
@@ -86,15 +87,38 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
                                    const uint64_t* dst_cap, uint8_t* status,
                                    uint64_t* written, uint64_t n, void* cuda_stream);
 
-/* Same batch, HOST buffers: stages src to the device, runs the kernel, copies dst/status/
- * written back, synchronises.  `src_bytes` / `dst_bytes` are the sizes of the two flat
- * buffers.  dst is copied to the device first so that bytes the decoder leaves untouched
- * keep their caller-provided value (reference contract). */
+/* Same batch, HOST buffers, in bounded device memory.  The batch is cut into sub-batches of
+ * consecutive streams that flow through a ring of three staging slots on the device
+ * (SFB200_HOST_STAGING_MB, default 3456 MiB in all; a single stream larger than a slot makes the
+ * slots grow to hold it): the upload of one sub-batch, the kernels of the one before and the
+ * download of the one before that overlap, so a batch of any size — larger than the GPU's memory
+ * included — decodes at the speed of the slower PCIe direction.  `src_bytes` / `dst_bytes` are the
+ * sizes of the two flat buffers.  dst is NOT uploaded and only bytes the decoder produced are
+ * copied back, so everything else in the caller's buffer keeps its value (reference contract:
+ * dst beyond what was written is never touched).  Synchronous.  Pinned host buffers
+ * (cudaHostAlloc / cudaHostRegister) make the copies asynchronous; pageable ones work, slower. */
 int sfb200_decompress_batch_host(sfb200_ctx* ctx, const uint8_t* src, uint64_t src_bytes,
                                  const uint64_t* src_off, const uint64_t* src_len,
                                  uint8_t* dst, uint64_t dst_bytes, const uint64_t* dst_off,
                                  const uint64_t* dst_cap, uint8_t* status, uint64_t* written,
                                  uint64_t n);
+
+/* One batch, several GPUs of one box (BASELINE.json configs[2]: "sharded across 2/4/8 B200";
+ * SURVEY.md §8e).  `ctxs` are n_ctx contexts, normally one per device: the streams are cut into
+ * n_ctx contiguous shards balanced by sum(src_len + dst_cap) (sfb200_partition_streams) and every
+ * context decodes its shard with sfb200_decompress_batch_host on a host thread of its own.  The
+ * streams are independent: there is no communication between the devices.  Results land in the
+ * same arrays as the single-device call would have put them. */
+int sfb200_decompress_batch_host_multi(sfb200_ctx* const* ctxs, int n_ctx, const uint8_t* src, uint64_t src_bytes,
+                                       const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst,
+                                       uint64_t dst_bytes, const uint64_t* dst_off, const uint64_t* dst_cap,
+                                       uint8_t* status, uint64_t* written, uint64_t n);
+/* cut[0] = 0 <= cut[1] <= ... <= cut[parts] = n: shard k is streams [cut[k], cut[k+1]). */
+void sfb200_partition_streams(const uint64_t* src_len, const uint64_t* dst_cap, uint64_t n, int parts,
+                              uint64_t* cut);
+
+/* Device memory the host-buffer entry points hold for staging right now (the three slots). */
+uint64_t sfb200_staging_bytes(const sfb200_ctx* ctx);
 
 /* Single stream, host buffers: the exact shape of the reference entry point
  * decompress(span src, span dst) (src/decompress.hpp:63-64).  *status receives the
@@ -178,9 +202,13 @@ typedef struct sfb200_launch_info {
 int sfb200_get_launch_info(sfb200_ctx* ctx, sfb200_launch_info* out);
 
 /* Device time of the most recent sfb200_decompress_batch_device call on this context, from CUDA
- * events recorded on its stream inside that call (waits for the call to finish):
- *   out3[0] scratch clearing (memsets), out3[1] pass 1 (huff_lanes_kernel),
- *   out3[2] pass 2 (lz_resolve_kernel), milliseconds. */
+ * events recorded on its stream inside that call (waits for the call to finish), milliseconds:
+ *   out3[0] scratch clearing and batch preparation,
+ *   out3[1] pass 1, the Huffman layer (huff_lanes_kernel; one stream or a few large ones:
+ *           find / verify candidates, huff_stream_kernel counting and writing, the chain),
+ *   out3[2] pass 2, the LZ77 back-references (lz_resolve_kernel; single-stream route: lz_jump_*).
+ * With more than two waves of streams the passes overlap: out3[1] then runs to the end of the last
+ * wave of pass 1 and out3[2] is what remains of pass 2 after that. */
 int sfb200_last_pass_ms(sfb200_ctx* ctx, float* out3);
 
 #ifdef __cplusplus

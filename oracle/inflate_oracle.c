@@ -22,7 +22,10 @@
  * code-length repeat before the first length or past the last) are reported
  * with ref_undefined = 1 and this repository's documented status choice:
  *   - running out of input inside a fixed-width field  -> SrcTooSmall
- *   - malformed code-length repeat                      -> InvalidLitOrLen
+ *   - code-length repeat with nothing to repeat, or past
+ *     the HLIT + HDIST lengths the header announced     -> InvalidLitOrLen
+ *   - a repeat that runs from the lit/len lengths into
+ *     the distance lengths (valid per RFC 1951)         -> decoded as the RFC says
  * =========================================================================== */
 #include "inflate_oracle.h"
 
@@ -183,12 +186,18 @@ void sfo_read_header(const uint8_t* src, size_t bit_size, uint8_t bit_offset,
   out[4] = (int)(b.pos - bit_offset);
 }
 
-/* decode_dynamic_huffman_table (src/decompress.cpp:253-312): one run of
- * n_codes code lengths; the lit/len and distance runs are decoded
- * independently (:353-360), so repeats cannot span them. */
-static int read_code_lengths(bits_t* b, const ctable_t* cl, unsigned n_codes,
-                             uint8_t* lens, int* ub)
+/* decode_dynamic_huffman_table (src/decompress.cpp:253-312).  The reference decodes the
+ * lit/len and the distance code lengths as two independent runs (:353-360); RFC 1951 §3.2.7
+ * makes them ONE sequence of n_lit + n_dist lengths (a repeat may cross from the first into the
+ * second, and real encoders — libdeflate, zopfli, 7-zip — write such headers).  The two readings
+ * differ only where the reference has undefined behaviour: a repeat that crosses the boundary
+ * writes past its first array, a 16 as the first distance length reads before its second.
+ * Those inputs are decoded as the RFC says and flagged ref_undefined; everything the reference
+ * defines comes out identically. */
+static int read_code_lengths(bits_t* b, const ctable_t* cl, unsigned n_lit, unsigned n_dist,
+                             uint8_t* lens, int* ub, int* ub_rfc_valid)
 {
+  const unsigned n_codes = n_lit + n_dist;
   memset(lens, 0, n_codes);
   for (unsigned i = 0; i < n_codes; i++) {
     uint16_t sym = 0;
@@ -203,10 +212,11 @@ static int read_code_lengths(bits_t* b, const ctable_t* cl, unsigned n_codes,
     if (sym == 16) { /* :273-280 */
       repeat = 3 + pop_bits(b, 2, ub);
       if (*ub) return SFO_SRC_TOO_SMALL;
-      if (i == 0) { /* reads code_bitsizes[-1] in the reference */
+      if (i == 0) { /* nothing to repeat; reads code_bitsizes[-1] in the reference */
         *ub = 1;
         return SFO_INVALID_LIT_OR_LEN;
       }
+      if (i == n_lit) *ub_rfc_valid = 1; /* the reference reads before its distance array here */
       value = lens[i - 1];
     } else if (sym == 17) { /* :281-288 */
       repeat = 3 + pop_bits(b, 3, ub);
@@ -217,10 +227,11 @@ static int read_code_lengths(bits_t* b, const ctable_t* cl, unsigned n_codes,
       if (*ub) return SFO_SRC_TOO_SMALL;
       value = 0;
     }
-    if (i + repeat > n_codes) { /* writes past code_bitsizes in the reference */
+    if (i + repeat > n_codes) { /* more lengths than the header announced */
       *ub = 1;
       return SFO_INVALID_LIT_OR_LEN;
     }
+    if (i < n_lit && i + repeat > n_lit) *ub_rfc_valid = 1; /* crosses: the reference writes past its lit/len array */
     for (unsigned j = 0; j < repeat; j++) lens[i + j] = (uint8_t)value;
     i += repeat - 1;
   }
@@ -228,7 +239,7 @@ static int read_code_lengths(bits_t* b, const ctable_t* cl, unsigned n_codes,
 }
 
 /* decode_dynamic_huffman_tables (src/decompress.cpp:314-367) */
-static int read_dynamic_tables(bits_t* b, ctable_t* lit, ctable_t* dist, int* ub)
+static int read_dynamic_tables(bits_t* b, ctable_t* lit, ctable_t* dist, int* ub, int* ub_rfc_valid)
 {
   const unsigned n_lit = 257 + pop_bits(b, 5, ub);
   if (*ub) return SFO_SRC_TOO_SMALL;
@@ -243,13 +254,11 @@ static int read_dynamic_tables(bits_t* b, ctable_t* lit, ctable_t* dist, int* ub
   }
   ctable_t cl;
   ctable_build(&cl, cl_lens, 19);
-  uint8_t lens[MAX_SYMS];
-  int st = read_code_lengths(b, &cl, n_lit, lens, ub);
+  uint8_t lens[MAX_SYMS + 32];
+  const int st = read_code_lengths(b, &cl, n_lit, n_dist, lens, ub, ub_rfc_valid);
   if (st != SFO_SUCCESS) return st;
   ctable_build(lit, lens, n_lit);
-  st = read_code_lengths(b, &cl, n_dist, lens, ub);
-  if (st != SFO_SUCCESS) return st;
-  ctable_build(dist, lens, n_dist);
+  ctable_build(dist, lens + n_lit, n_dist);
   return SFO_SUCCESS;
 }
 
@@ -307,7 +316,8 @@ static void decompress_impl(const uint8_t* src, size_t src_len, uint8_t* dst,
 {
   bits_t b = {src, 0, (uint64_t)src_len * 8};
   uint64_t written = 0;
-  int ub = 0;
+  int ub = 0;           /* the reference reads / writes out of bounds: decoding stops with the documented status */
+  int ub_rfc_valid = 0; /* the reference is undefined, RFC 1951 is not: decoding goes on as the RFC says */
   int status = SFO_SUCCESS;
   ctable_t lit, dist;
   for (int was_final = 0; !was_final;) {
@@ -345,7 +355,7 @@ static void decompress_impl(const uint8_t* src, size_t src_len, uint8_t* dst,
       if (type == 1) {
         fixed_tables(&lit, &dist);
       } else {
-        status = read_dynamic_tables(&b, &lit, &dist, &ub);
+        status = read_dynamic_tables(&b, &lit, &dist, &ub, &ub_rfc_valid);
         if (status != SFO_SUCCESS) break;
       }
       status = inflate_block(&b, dst, dst_cap, &written, &lit, &dist, &ub);
@@ -353,7 +363,7 @@ static void decompress_impl(const uint8_t* src, size_t src_len, uint8_t* dst,
     }
   }
   res->status = (uint8_t)status;
-  res->ref_undefined = (uint8_t)ub;
+  res->ref_undefined = (uint8_t)(ub | ub_rfc_valid);
   res->written = written;
   res->bits_consumed = b.pos;
 }

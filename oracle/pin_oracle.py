@@ -159,6 +159,18 @@ def build_families(bases):
         fuzz.append(bytes(b))
     fams.append({"name": "random_bytes", "kind": "hex", "params": [f.hex() for f in fuzz],
                  "caps": [int(rng.choice([0, 16, 300])) for _ in fuzz]})
+    # the C2 unit itself (one 64 KiB level-6 text stream): truncations, bit flips, capacities
+    comp, plain = bases["dynamic_65536"]
+    fams.append({"name": "cut_dynamic_65536", "kind": "cut", "base": "dynamic_65536",
+                 "params": list(range(0, 200)) + list(range(200, len(comp) + 1, 89)) + [len(comp) - 1, len(comp)],
+                 "caps": len(plain)})
+    nbits = len(comp) * 8
+    fams.append({"name": "flip_dynamic_65536", "kind": "flip", "base": "dynamic_65536",
+                 "params": sorted(set(int(x) for x in rng.integers(0, nbits, 500)) | set(range(0, 700))),
+                 "caps": len(plain) + 64})
+    fams.append({"name": "cap_dynamic_65536", "kind": "cap", "base": "dynamic_65536",
+                 "params": sorted(set([int(x) for x in rng.integers(0, len(plain), 120)] +
+                                      [0, 1, 2, 3, len(plain) - 1, len(plain), len(plain) + 1]))})
     return fams
 
 

@@ -210,6 +210,30 @@ class Context:
         self._check(rc, "sfb200_decompress_batch_host")
         return status, written
 
+    @staticmethod
+    def decompress_batch_host_multi(contexts, src: np.ndarray, src_off, src_len, dst: np.ndarray, dst_off, dst_cap):
+        """One batch cut across several contexts (one per GPU), each decoding its contiguous shard
+        on a host thread of its own (sfb200_decompress_batch_host_multi). -> (status, written)"""
+        lib = load_library()
+        n = len(src_off)
+        src_off = np.ascontiguousarray(src_off, dtype=np.uint64)
+        src_len = np.ascontiguousarray(src_len, dtype=np.uint64)
+        dst_off = np.ascontiguousarray(dst_off, dtype=np.uint64)
+        dst_cap = np.ascontiguousarray(dst_cap, dtype=np.uint64)
+        status = np.zeros(n, np.uint8)
+        written = np.zeros(n, np.uint64)
+        arr = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+        f = lib.sfb200_decompress_batch_host_multi
+        f.argtypes = [C.POINTER(C.c_void_p), C.c_int, _u8p, C.c_uint64, _u64p, _u64p, _u8p, C.c_uint64, _u64p,
+                      _u64p, _u8p, _u64p, C.c_uint64]
+        f.restype = C.c_int
+        rc = f(arr, len(contexts), _p(src, _u8p), src.size, _p(src_off, _u64p), _p(src_len, _u64p), _p(dst, _u8p),
+               dst.size, _p(dst_off, _u64p), _p(dst_cap, _u64p), _p(status, _u8p), _p(written, _u64p), n)
+        if rc != 0:
+            msgs = "; ".join((lib.sfb200_last_error(c.h) or b"").decode() for c in contexts)
+            raise StarflateError(f"sfb200_decompress_batch_host_multi: {_RC_NAMES.get(rc, rc)} {msgs}")
+        return status, written
+
     def decompress(self, src: bytes, dst_cap: int, fill: int = 0):
         """Single stream (the reference entry point's shape). -> (status, dst bytes, written)"""
         s = np.frombuffer(src, dtype=np.uint8) if len(src) else np.zeros(1, np.uint8)
@@ -220,6 +244,12 @@ class Context:
                                         C.byref(st), C.byref(wr))
         self._check(rc, "sfb200_decompress")
         return st.value, d[:dst_cap].tobytes(), wr.value
+
+    def staging_bytes(self) -> int:
+        """Device memory held for the host-buffer entry points' staging slots."""
+        self.lib.sfb200_staging_bytes.argtypes = [C.c_void_p]
+        self.lib.sfb200_staging_bytes.restype = C.c_uint64
+        return int(self.lib.sfb200_staging_bytes(self.h))
 
     def last_pass_ms(self):
         """(clear_ms, pass1_ms, pass2_ms) of the most recent device-batch call (CUDA events)."""

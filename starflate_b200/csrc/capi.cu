@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -85,18 +86,24 @@ struct sfb200_ctx {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // call start | pass 1 start | pass 1 end | pass 2 end
   bool ev_valid = false;
   std::string err;
-  // staging for the host-buffer entry points (grown on demand)
-  uint8_t* d_src = nullptr;
+  // staging for the host-buffer entry points: a ring of kStageSlots sub-batch slots in device memory
+  // (bounded whatever the batch: SFB200_HOST_STAGING_MB), plus the single-stream helpers' buffers
+  uint8_t* d_src = nullptr;   // (single-stream helpers: size discovery, containers)
   uint64_t d_src_cap = 0;
   uint8_t* d_dst = nullptr;
   uint64_t d_dst_cap = 0;
-  uint64_t* d_meta = nullptr;  // src_off, src_len, dst_off, dst_cap, written : 5*n u64, then status n u8
-  uint64_t d_meta_n = 0;
+  uint8_t* st_src[3] = {nullptr, nullptr, nullptr};
+  uint8_t* st_dst[3] = {nullptr, nullptr, nullptr};
+  uint64_t st_src_cap = 0, st_dst_cap = 0;      // per slot
+  int st_slots = 0;                             // slots allocated so far (a small call needs one)
+  uint64_t* st_meta[3] = {nullptr, nullptr, nullptr};  // per slot: src_off, src_len, dst_off, dst_cap, written (u64 x n), status (u8 x n)
+  uint64_t* st_hmeta[3] = {nullptr, nullptr, nullptr};  // pinned mirror: the four input arrays (rebased) + written + status
+  uint64_t st_meta_n = 0;
+  cudaStream_t s_meta = nullptr;                // status / written read-back
+  cudaEvent_t st_ev[3][4] = {};                 // per slot: in_done | run_done | meta_done | out_done
   cudaStream_t hs[3] = {nullptr, nullptr, nullptr};  // H2D | kernels | D2H
   cudaStream_t ps[2] = {nullptr, nullptr};           // pass-1 chain | pass-2 chain (wave overlap)
   std::vector<cudaEvent_t> wave_ev;
-  uint64_t* h_meta = nullptr;  // pinned: written n u64, then status n u8 (so the D2H of the results never blocks the host)
-  uint64_t h_meta_n = 0;
 };
 
 namespace {
@@ -106,6 +113,28 @@ int fail(sfb200_ctx* ctx, cudaError_t e, const char* what)
   if (ctx) ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
   return e == cudaErrorMemoryAllocation ? SFB200_RC_OUT_OF_MEMORY : SFB200_RC_CUDA_ERROR;
 }
+
+// Every entry point works on its context's device and leaves the calling thread's current
+// device as it found it (a process with one context per GPU — or PyTorch beside us — must not
+// see its current device change under it).
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int device)
+  {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = prev == device || cudaSetDevice(device) == cudaSuccess;
+    if (prev == device) prev = -1;  // nothing to restore
+  }
+  ~DeviceGuard()
+  {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+#define SFB_ENTER(ctx)                                                   \
+  DeviceGuard guard_((ctx)->device);                                     \
+  if (!guard_.ok) return fail((ctx), cudaGetLastError(), "cudaSetDevice"); \
+  (ctx)->err.clear()
 
 #define SFB_TRY(ctx, call)                                   \
   do {                                                       \
@@ -150,7 +179,8 @@ int sfb200_create(int device, sfb200_ctx** out)
     delete ctx;
     return rc;
   };
-  if (cudaSetDevice(device) != cudaSuccess) return bail(SFB200_RC_NO_DEVICE);
+  DeviceGuard guard_(device);
+  if (!guard_.ok) return bail(SFB200_RC_NO_DEVICE);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(SFB200_RC_CUDA_ERROR);
   ctx->sm_count = prop.multiProcessorCount;
@@ -233,7 +263,7 @@ int sfb200_create(int device, sfb200_ctx** out)
 void sfb200_destroy(sfb200_ctx* ctx)
 {
   if (!ctx) return;
-  cudaSetDevice(ctx->device);
+  DeviceGuard guard_(ctx->device);
   cudaFree(ctx->d_counter);
   cudaFree(ctx->d_lens);
   cudaFree(ctx->d_bits);
@@ -245,7 +275,15 @@ void sfb200_destroy(sfb200_ctx* ctx)
   cudaFree(ctx->d_order);
   cudaFree(ctx->d_src);
   cudaFree(ctx->d_dst);
-  cudaFree(ctx->d_meta);
+  for (int k = 0; k < 3; ++k) {
+    cudaFree(ctx->st_src[k]);
+    cudaFree(ctx->st_dst[k]);
+    cudaFree(ctx->st_meta[k]);
+    if (ctx->st_hmeta[k]) cudaFreeHost(ctx->st_hmeta[k]);
+    for (auto& e : ctx->st_ev[k])
+      if (e) cudaEventDestroy(e);
+  }
+  if (ctx->s_meta) cudaStreamDestroy(ctx->s_meta);
   for (auto& e : ctx->ev)
     if (e) cudaEventDestroy(e);
   for (auto& st : ctx->hs)
@@ -253,7 +291,6 @@ void sfb200_destroy(sfb200_ctx* ctx)
   for (auto& st : ctx->ps)
     if (st) cudaStreamDestroy(st);
   for (auto& e : ctx->wave_ev) cudaEventDestroy(e);
-  if (ctx->h_meta) cudaFreeHost(ctx->h_meta);
   delete ctx;
 }
 
@@ -288,7 +325,7 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
   if (!ctx) return SFB200_RC_BAD_ARGUMENT;
   if (n == 0) return SFB200_RC_OK;
   if (!src_off || !src_len || !dst_off || !dst_cap || !status) return SFB200_RC_BAD_ARGUMENT;
-  SFB_TRY(ctx, cudaSetDevice(ctx->device));
+  SFB_ENTER(ctx);
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   // the kernels index dst (and the bitmap) from a 128-byte aligned base
   const uint64_t delta = reinterpret_cast<uintptr_t>(dst_base) & 127u;
@@ -342,7 +379,15 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
     const uint64_t need = jump_tiles * sfb::JUMP_TILE * 4 + jump_tiles * 4 * (1 + sfb::JUMP_TILE / 128) +
                           stripes * (sfb::JUMP_MAX_ROUNDS + 1) * 4;
     const int rc = grow(ctx, &ctx->d_jump, &ctx->d_jump_cap, need);
-    if (rc != SFB200_RC_OK) return rc;
+    if (rc == SFB200_RC_OUT_OF_MEMORY) {
+      // no room for the pointer array (4 bytes per dst byte): a warp walks the stream instead —
+      // slower, same results
+      cudaGetLastError();
+      ctx->err.clear();
+      jump = false;
+    } else if (rc != SFB200_RC_OK) {
+      return rc;
+    }
   }
   // ... and pass 1 decodes its blocks side by side (block_finder.cuh).  The input's size is only known
   // on the device; the scratch is sized for an input a little larger than the output, and block
@@ -361,7 +406,14 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
                           8ull * cand_cap + sizeof(sfb::WinRec) * static_cast<uint64_t>(rec_cap) +
                           28ull * job_cap + 64;
     const int rc = grow(ctx, &ctx->d_find, &ctx->d_find_cap, need);
-    if (rc != SFB200_RC_OK) return rc;
+    if (rc == SFB200_RC_OUT_OF_MEMORY) {  // blocks one after the other instead of side by side
+      cudaGetLastError();
+      ctx->err.clear();
+      blocks = false;
+      jump = false;
+    } else if (rc != SFB200_RC_OK) {
+      return rc;
+    }
   }
   // Geometry.  Measured on C2 (profiles/r01_small_geometry_c2.md): with 16 warps per SM the small
   // geometry makes pass 1 issue-bound (63 % of issue slots, 11.1 ms against 12.1 ms for the
@@ -692,7 +744,7 @@ int sfb200_decompressed_size_batch_device(sfb200_ctx* ctx, const uint8_t* src_ba
   if (!ctx) return SFB200_RC_BAD_ARGUMENT;
   if (n == 0) return SFB200_RC_OK;
   if (!src_off || !src_len || !status || !size) return SFB200_RC_BAD_ARGUMENT;
-  SFB_TRY(ctx, cudaSetDevice(ctx->device));
+  SFB_ENTER(ctx);
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   ctx->ev_valid = false;
   SFB_TRY(ctx, cudaMemsetAsync(ctx->d_counter, 0, kCountersPerWave * sizeof(unsigned long long), st));
@@ -734,7 +786,7 @@ int sfb200_decompressed_size_batch_device(sfb200_ctx* ctx, const uint8_t* src_ba
 int sfb200_last_pass_ms(sfb200_ctx* ctx, float* out3)
 {
   if (!ctx || !out3 || !ctx->ev_valid) return SFB200_RC_BAD_ARGUMENT;
-  SFB_TRY(ctx, cudaSetDevice(ctx->device));
+  SFB_ENTER(ctx);
   SFB_TRY(ctx, cudaEventSynchronize(ctx->ev[3]));
   for (int i = 0; i < 3; ++i) SFB_TRY(ctx, cudaEventElapsedTime(&out3[i], ctx->ev[i], ctx->ev[i + 1]));
   return SFB200_RC_OK;
@@ -746,7 +798,7 @@ int sfb200_checksum_batch_device(sfb200_ctx* ctx, const uint8_t* base, const uin
 {
   if (!ctx) return SFB200_RC_BAD_ARGUMENT;
   if (n == 0) return SFB200_RC_OK;
-  SFB_TRY(ctx, cudaSetDevice(ctx->device));
+  SFB_ENTER(ctx);
   const unsigned threads = 128;
   const uint64_t blocks = (n * 32 + threads - 1) / threads;
   sfb::checksum_kernel<<<static_cast<unsigned>(blocks), threads, 0,
@@ -756,13 +808,20 @@ int sfb200_checksum_batch_device(sfb200_ctx* ctx, const uint8_t* base, const uin
   return SFB200_RC_OK;
 }
 
-// Host buffers.  The batch is cut into sub-batches of about SFB200_HOST_CHUNK_MB of output
-// (default 1536) that flow through three CUDA streams — H2D of sub-batch k+1, the two kernels of
-// sub-batch k and D2H of sub-batch k-1 overlap — so the call is bounded by the slower PCIe
-// direction, not by the sum of the stages.  dst is NOT uploaded: only bytes the decoder produced
-// are copied back (whole runs of adjacent, completely filled regions in one copy; for a stream
-// that stopped early just its `written` prefix), so everything else in the caller's buffer
-// keeps its value, as the reference guarantees.
+// Host buffers, in BOUNDED device memory.  The batch is cut into sub-batches of consecutive
+// streams that flow through a ring of three staging slots (SFB200_HOST_STAGING_MB, default 3456:
+// per slot 768 MiB of dst and 384 MiB of src) on four CUDA streams:
+//   s_in   H2D of the sub-batch's compressed bytes and (rebased) offsets
+//   s_run  the kernels (sfb200_decompress_batch_device on the slot's buffers)
+//   s_meta status / written of the sub-batch -> pinned host memory
+//   s_out  D2H of the bytes the decoder produced
+// H2D of sub-batch k+2, the kernels of k+1 and the D2H of k overlap, so the call is bounded by the
+// slower PCIe direction rather than by the sum of the stages, and a batch far larger than the GPU's
+// memory decodes in the same ~3.4 GiB.  dst is NOT uploaded: only bytes the decoder produced are
+// copied back (whole runs of adjacent, completely filled regions in one copy; for a stream that
+// stopped early just its `written` prefix), so everything else in the caller's buffer keeps its
+// value, as the reference guarantees.  A single stream larger than a slot makes the slots grow to
+// hold it (one stream is one unit of work: SURVEY.md §8 f3 has the chunked single stream as next).
 int sfb200_decompress_batch_host(sfb200_ctx* ctx, const uint8_t* src, uint64_t src_bytes,
                                  const uint64_t* src_off, const uint64_t* src_len,
                                  uint8_t* dst, uint64_t dst_bytes, const uint64_t* dst_off,
@@ -773,161 +832,289 @@ int sfb200_decompress_batch_host(sfb200_ctx* ctx, const uint8_t* src, uint64_t s
   if (n == 0) return SFB200_RC_OK;
   if (!src_off || !src_len || !dst_off || !dst_cap || !status) return SFB200_RC_BAD_ARGUMENT;
   if ((src_bytes && !src) || (dst_bytes && !dst)) return SFB200_RC_BAD_ARGUMENT;
+  uint64_t max_src = 0, max_dst = 0;
   for (uint64_t i = 0; i < n; ++i) {
     if (src_off[i] > src_bytes || src_len[i] > src_bytes - src_off[i]) return SFB200_RC_BAD_ARGUMENT;
     if (dst_off[i] > dst_bytes || dst_cap[i] > dst_bytes - dst_off[i]) return SFB200_RC_BAD_ARGUMENT;
+    max_src = std::max(max_src, src_len[i]);
+    max_dst = std::max(max_dst, dst_cap[i]);
   }
-  SFB_TRY(ctx, cudaSetDevice(ctx->device));
-  int rc = grow(ctx, &ctx->d_src, &ctx->d_src_cap, src_bytes + 16);
-  if (rc) return rc;
-  rc = grow(ctx, &ctx->d_dst, &ctx->d_dst_cap, dst_bytes + 64);
-  if (rc) return rc;
-  if (n > ctx->d_meta_n) {
-    if (ctx->d_meta) SFB_TRY(ctx, cudaFree(ctx->d_meta));
-    ctx->d_meta = nullptr;
-    ctx->d_meta_n = 0;
-    const uint64_t want = n + n / 8 + 64;
-    SFB_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_meta), want * (5 * 8 + 1)));
-    ctx->d_meta_n = want;
+  SFB_ENTER(ctx);
+  constexpr int S = 3;
+  // ---- slot sizes ------------------------------------------------------------------------------
+  uint64_t budget = 3456ull << 20;
+  if (const char* e = std::getenv("SFB200_HOST_STAGING_MB")) {
+    const long v = std::atol(e);
+    if (v > 0) budget = static_cast<uint64_t>(v) << 20;
   }
-  if (n > ctx->h_meta_n) {
-    if (ctx->h_meta) SFB_TRY(ctx, cudaFreeHost(ctx->h_meta));
-    ctx->h_meta = nullptr;
-    ctx->h_meta_n = 0;
-    const uint64_t want = n + n / 8 + 64;
-    SFB_TRY(ctx, cudaMallocHost(reinterpret_cast<void**>(&ctx->h_meta), want * 9));
-    ctx->h_meta_n = want;
+  if (const char* e = std::getenv("SFB200_HOST_STAGING_KB")) {  // (tests: force many sub-batches)
+    const long v = std::atol(e);
+    if (v > 0) budget = static_cast<uint64_t>(v) << 10;
   }
-  uint64_t* const wr_host = ctx->h_meta;
-  uint8_t* const st_host = reinterpret_cast<uint8_t*>(ctx->h_meta + ctx->h_meta_n);
-  for (auto& st : ctx->hs)
-    if (!st) SFB_TRY(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  cudaStream_t s_in = ctx->hs[0], s_run = ctx->hs[1], s_out = ctx->hs[2];
-  const uint64_t cap_n = ctx->d_meta_n;
-  uint64_t* m_src_off = ctx->d_meta;
-  uint64_t* m_src_len = m_src_off + cap_n;
-  uint64_t* m_dst_off = m_src_len + cap_n;
-  uint64_t* m_dst_cap = m_dst_off + cap_n;
-  uint64_t* m_written = m_dst_cap + cap_n;
-  uint8_t* m_status = reinterpret_cast<uint8_t*>(m_written + cap_n);
+  uint64_t want_dst = std::max<uint64_t>(budget / S * 2 / 3, 4096), want_src = std::max<uint64_t>(budget / S / 3, 4096);
+  // (a stream is staged whole; 256 bytes of slack for the 128-byte rebasing of the windows)
+  want_dst = std::max(want_dst, max_dst + 256);
+  want_src = std::max(want_src, max_src + 256);
+  // no more than the batch needs
+  want_dst = std::min(want_dst, dst_bytes + 256);
+  want_src = std::min(want_src, src_bytes + 256);
+  const uint64_t want_n = std::min<uint64_t>(n, 1ull << 22);  // streams per sub-batch
+  auto sync_all = [&]() {
+    for (auto& st : ctx->hs)
+      if (st) cudaStreamSynchronize(st);
+    if (ctx->s_meta) cudaStreamSynchronize(ctx->s_meta);
+  };
+  const uint64_t slot_src = want_src, slot_dst = want_dst;  // (what a sub-batch may span; the slots may be larger already)
 
-  // sub-batches of consecutive streams
-  uint64_t chunk_bytes = 1536ull << 20;
-  if (const char* e = std::getenv("SFB200_HOST_CHUNK_MB")) {
-    const long v = std::atol(e);
-    if (v > 0) chunk_bytes = static_cast<uint64_t>(v) << 20;
-  }
-  if (const char* e = std::getenv("SFB200_HOST_CHUNK_KB")) {  // (tests: force many sub-batches)
-    const long v = std::atol(e);
-    if (v > 0) chunk_bytes = static_cast<uint64_t>(v) << 10;
-  }
+  // ---- sub-batches of consecutive streams whose src and dst windows fit a slot -------------------
   struct Sub {
     uint64_t first, count, src_lo, src_hi, dst_lo, dst_hi;
-    cudaEvent_t in_done, run_done, meta_done;
   };
   std::vector<Sub> subs;
   for (uint64_t i = 0; i < n;) {
-    Sub sb{i, 0, ~0ull, 0, ~0ull, 0, nullptr, nullptr, nullptr};
-    uint64_t acc = 0;
-    // (the first sub-batch is a quarter of the others so that the D2H direction, which bounds
-    //  the call, starts early)
-    const uint64_t target = subs.empty() ? chunk_bytes / 4 : chunk_bytes;
-    while (i < n && (sb.count == 0 || acc < target)) {
-      sb.src_lo = std::min(sb.src_lo, src_off[i]);
-      sb.src_hi = std::max(sb.src_hi, src_off[i] + src_len[i]);
-      sb.dst_lo = std::min(sb.dst_lo, dst_off[i]);
-      sb.dst_hi = std::max(sb.dst_hi, dst_off[i] + dst_cap[i]);
-      acc += dst_cap[i] + src_len[i];
+    Sub sb{i, 0, ~0ull, 0, ~0ull, 0};
+    while (i < n && sb.count < want_n) {
+      const uint64_t slo = std::min(sb.src_lo, src_off[i]), shi = std::max(sb.src_hi, src_off[i] + src_len[i]);
+      const uint64_t dlo = std::min(sb.dst_lo, dst_off[i]) & ~127ull, dhi = std::max(sb.dst_hi, dst_off[i] + dst_cap[i]);
+      if (sb.count && (shi - slo > slot_src || dhi - dlo > slot_dst)) break;
+      sb.src_lo = slo;
+      sb.src_hi = shi;
+      sb.dst_lo = dlo;  // (128-byte aligned: keeps the windows' alignment and the bitmap phase of the caller's layout)
+      sb.dst_hi = dhi;
       ++sb.count;
       ++i;
     }
-    sb.dst_lo &= ~31ull;  // keep the bitmap phase of the caller's layout
     subs.push_back(sb);
   }
-  std::vector<uint64_t> rel_off(n);  // dst offsets relative to each sub-batch's window
-  for (const Sub& sb : subs)
-    for (uint64_t j = 0; j < sb.count; ++j) rel_off[sb.first + j] = dst_off[sb.first + j] - sb.dst_lo;
+  // ---- the slots this call needs (grown, never shrunk; a call with one sub-batch takes one) -----
+  const int need_slots = static_cast<int>(std::min<size_t>(S, subs.size()));
+  if (slot_dst > ctx->st_dst_cap || slot_src > ctx->st_src_cap) {
+    sync_all();
+    for (int k = 0; k < S; ++k) {
+      if (ctx->st_src[k]) SFB_TRY(ctx, cudaFree(ctx->st_src[k]));
+      if (ctx->st_dst[k]) SFB_TRY(ctx, cudaFree(ctx->st_dst[k]));
+      ctx->st_src[k] = ctx->st_dst[k] = nullptr;
+    }
+    ctx->st_slots = 0;
+    ctx->st_src_cap = std::max(slot_src, ctx->st_src_cap);
+    ctx->st_dst_cap = std::max(slot_dst, ctx->st_dst_cap);
+  }
+  for (; ctx->st_slots < need_slots; ++ctx->st_slots) {
+    const int k = ctx->st_slots;
+    SFB_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->st_src[k]), ctx->st_src_cap + 64));
+    SFB_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->st_dst[k]), ctx->st_dst_cap + 64));
+  }
+  if (want_n > ctx->st_meta_n) {
+    sync_all();
+    for (int k = 0; k < S; ++k) {
+      if (ctx->st_meta[k]) SFB_TRY(ctx, cudaFree(ctx->st_meta[k]));
+      if (ctx->st_hmeta[k]) SFB_TRY(ctx, cudaFreeHost(ctx->st_hmeta[k]));
+      ctx->st_meta[k] = ctx->st_hmeta[k] = nullptr;
+    }
+    ctx->st_meta_n = 0;
+    const uint64_t cap = want_n + want_n / 8 + 64;
+    for (int k = 0; k < S; ++k) {
+      SFB_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->st_meta[k]), cap * (5 * 8 + 1) + 64));
+      SFB_TRY(ctx, cudaMallocHost(reinterpret_cast<void**>(&ctx->st_hmeta[k]), cap * (5 * 8 + 1) + 64));
+    }
+    ctx->st_meta_n = cap;
+  }
+  for (auto& st : ctx->hs)
+    if (!st) SFB_TRY(ctx, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  if (!ctx->s_meta) SFB_TRY(ctx, cudaStreamCreateWithFlags(&ctx->s_meta, cudaStreamNonBlocking));
+  for (int k = 0; k < S; ++k)
+    for (auto& e : ctx->st_ev[k])
+      if (!e) SFB_TRY(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  cudaStream_t s_in = ctx->hs[0], s_run = ctx->hs[1], s_out = ctx->hs[2], s_meta = ctx->s_meta;
+  const uint64_t cap_n = ctx->st_meta_n;
+  // the scratch of the device call is sized once, for the largest sub-batch (no reallocation —
+  // cudaFree synchronises the device — while the pipeline runs)
+  {
+    uint64_t big = 0, big_n = 0;
+    for (const Sub& sb : subs) {
+      big = std::max(big, sb.dst_hi - sb.dst_lo);
+      big_n = std::max(big_n, sb.count);
+    }
+    const uint64_t bits_words = (big + 128) / 32 + 8;
+    if (bits_words > ctx->d_bits_words) {
+      sync_all();
+      if (ctx->d_bits) SFB_TRY(ctx, cudaFree(ctx->d_bits));
+      ctx->d_bits = nullptr;
+      ctx->d_bits_words = 0;
+      const uint64_t want = bits_words + bits_words / 8 + 64;
+      SFB_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_bits), want * sizeof(uint32_t)));
+      ctx->d_bits_words = want;
+    }
+    if (big_n > ctx->d_order_n) {
+      sync_all();
+      if (ctx->d_order) SFB_TRY(ctx, cudaFree(ctx->d_order));
+      ctx->d_order = nullptr;
+      ctx->d_order_n = 0;
+      const uint64_t want = big_n + big_n / 8 + 64;
+      SFB_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_order), want * sizeof(uint32_t)));
+      ctx->d_order_n = want;
+    }
+  }
   auto cleanup = [&](int code) {
-    for (auto& st : ctx->hs) cudaStreamSynchronize(st);
-    for (Sub& sb : subs)
-      for (cudaEvent_t ev : {sb.in_done, sb.run_done, sb.meta_done})
-        if (ev) cudaEventDestroy(ev);
+    sync_all();
     return code;
   };
-#define SFB_TRYC(call)                                        \
-  do {                                                        \
-    const cudaError_t e_ = (call);                            \
+#define SFB_TRYC(call)                                           \
+  do {                                                           \
+    const cudaError_t e_ = (call);                               \
     if (e_ != cudaSuccess) return cleanup(fail(ctx, e_, #call)); \
   } while (0)
-  for (Sub& sb : subs) {
-    SFB_TRYC(cudaEventCreateWithFlags(&sb.in_done, cudaEventDisableTiming));
-    SFB_TRYC(cudaEventCreateWithFlags(&sb.run_done, cudaEventDisableTiming));
-    SFB_TRYC(cudaEventCreateWithFlags(&sb.meta_done, cudaEventDisableTiming));
-  }
-  auto enqueue = [&](Sub& sb) -> int {
+  // slot k % S: device arrays and their pinned mirror
+  auto d_arr = [&](int slot, int which) { return ctx->st_meta[slot] + static_cast<uint64_t>(which) * cap_n; };
+  auto h_arr = [&](int slot, int which) { return ctx->st_hmeta[slot] + static_cast<uint64_t>(which) * cap_n; };
+  auto enqueue = [&](size_t k) -> int {
+    const Sub& sb = subs[k];
+    const int slot = static_cast<int>(k % S);
     const uint64_t f = sb.first, c = sb.count;
+    // the slot is free once the bytes of its previous occupant have left for the host
+    // (and the host has read that sub-batch's status / written from the pinned mirror: it has —
+    //  sub-batch k - S was finished before this one is enqueued)
+    if (k >= static_cast<size_t>(S)) SFB_TRYC(cudaStreamWaitEvent(s_in, ctx->st_ev[slot][3], 0));
+    uint64_t* h_so = h_arr(slot, 0), * h_sl = h_arr(slot, 1), * h_do = h_arr(slot, 2), * h_dc = h_arr(slot, 3);
+    for (uint64_t j = 0; j < c; ++j) {
+      h_so[j] = src_off[f + j] - sb.src_lo;
+      h_sl[j] = src_len[f + j];
+      h_do[j] = dst_off[f + j] - sb.dst_lo;
+      h_dc[j] = dst_cap[f + j];
+    }
     if (sb.src_hi > sb.src_lo)
-      SFB_TRYC(cudaMemcpyAsync(ctx->d_src + sb.src_lo, src + sb.src_lo, sb.src_hi - sb.src_lo,
-                               cudaMemcpyHostToDevice, s_in));
-    SFB_TRYC(cudaMemcpyAsync(m_src_off + f, src_off + f, c * 8, cudaMemcpyHostToDevice, s_in));
-    SFB_TRYC(cudaMemcpyAsync(m_src_len + f, src_len + f, c * 8, cudaMemcpyHostToDevice, s_in));
-    SFB_TRYC(cudaMemcpyAsync(m_dst_off + f, rel_off.data() + f, c * 8, cudaMemcpyHostToDevice, s_in));
-    SFB_TRYC(cudaMemcpyAsync(m_dst_cap + f, dst_cap + f, c * 8, cudaMemcpyHostToDevice, s_in));
-    SFB_TRYC(cudaEventRecord(sb.in_done, s_in));
-    SFB_TRYC(cudaStreamWaitEvent(s_run, sb.in_done, 0));
-    const int r = sfb200_decompress_batch_device(ctx, ctx->d_src, m_src_off + f, m_src_len + f,
-                                                 ctx->d_dst + sb.dst_lo, sb.dst_hi - sb.dst_lo,
-                                                 m_dst_off + f, m_dst_cap + f, m_status + f,
-                                                 m_written + f, c, s_run);
+      SFB_TRYC(cudaMemcpyAsync(ctx->st_src[slot], src + sb.src_lo, sb.src_hi - sb.src_lo, cudaMemcpyHostToDevice, s_in));
+    // (the four arrays are contiguous in both mirrors when c == cap_n; copy them one by one)
+    for (int w = 0; w < 4; ++w)
+      SFB_TRYC(cudaMemcpyAsync(d_arr(slot, w), h_arr(slot, w), c * 8, cudaMemcpyHostToDevice, s_in));
+    SFB_TRYC(cudaEventRecord(ctx->st_ev[slot][0], s_in));
+    SFB_TRYC(cudaStreamWaitEvent(s_run, ctx->st_ev[slot][0], 0));
+    uint8_t* const d_status = reinterpret_cast<uint8_t*>(d_arr(slot, 5));
+    const int r = sfb200_decompress_batch_device(ctx, ctx->st_src[slot], d_arr(slot, 0), d_arr(slot, 1), ctx->st_dst[slot],
+                                                 sb.dst_hi - sb.dst_lo, d_arr(slot, 2), d_arr(slot, 3), d_status,
+                                                 d_arr(slot, 4), c, s_run);
     if (r) return cleanup(r);
-    SFB_TRYC(cudaEventRecord(sb.run_done, s_run));
-    SFB_TRYC(cudaStreamWaitEvent(s_out, sb.run_done, 0));
-    SFB_TRYC(cudaMemcpyAsync(st_host + f, m_status + f, c, cudaMemcpyDeviceToHost, s_out));
-    SFB_TRYC(cudaMemcpyAsync(wr_host + f, m_written + f, c * 8, cudaMemcpyDeviceToHost, s_out));
-    SFB_TRYC(cudaEventRecord(sb.meta_done, s_out));
+    SFB_TRYC(cudaEventRecord(ctx->st_ev[slot][1], s_run));
+    SFB_TRYC(cudaStreamWaitEvent(s_meta, ctx->st_ev[slot][1], 0));
+    SFB_TRYC(cudaMemcpyAsync(h_arr(slot, 4), d_arr(slot, 4), c * 8, cudaMemcpyDeviceToHost, s_meta));
+    SFB_TRYC(cudaMemcpyAsync(h_arr(slot, 5), d_status, c, cudaMemcpyDeviceToHost, s_meta));
+    SFB_TRYC(cudaEventRecord(ctx->st_ev[slot][2], s_meta));
     return SFB200_RC_OK;
   };
-  rc = enqueue(subs[0]);
-  if (rc) return rc;
+  int rc = SFB200_RC_OK;
+  size_t enq = 0;
+  for (; enq < subs.size() && enq < static_cast<size_t>(S) - 1; ++enq) {
+    rc = enqueue(enq);
+    if (rc) return rc;
+  }
   for (size_t k = 0; k < subs.size(); ++k) {
-    if (k + 1 < subs.size()) {
-      rc = enqueue(subs[k + 1]);
+    // keep S - 1 sub-batches in flight behind this one (slot (k + S - 1) % S is the one sub-batch
+    // k - 1 has just left)
+    if (enq < subs.size()) {
+      rc = enqueue(enq++);
       if (rc) return rc;
     }
-    Sub& sb = subs[k];
-    SFB_TRYC(cudaEventSynchronize(sb.meta_done));
+    const Sub& sb = subs[k];
+    const int slot = static_cast<int>(k % S);
+    SFB_TRYC(cudaEventSynchronize(ctx->st_ev[slot][2]));
+    const uint64_t* const wr_host = h_arr(slot, 4);
+    const uint8_t* const st_host = reinterpret_cast<const uint8_t*>(h_arr(slot, 5));
     // bytes produced -> the caller's buffer, in as few copies as the layout allows
-    uint64_t run_lo = 0, run_hi = 0;  // pending run [run_lo, run_hi) of produced bytes
+    SFB_TRYC(cudaStreamWaitEvent(s_out, ctx->st_ev[slot][1], 0));
+    uint64_t run_lo = 0, run_hi = 0;  // pending run [run_lo, run_hi) of produced bytes (caller's offsets)
     auto flush_run = [&]() -> int {
       if (run_hi > run_lo)
-        SFB_TRYC(cudaMemcpyAsync(dst + run_lo, ctx->d_dst + run_lo, run_hi - run_lo,
+        SFB_TRYC(cudaMemcpyAsync(dst + run_lo, ctx->st_dst[slot] + (run_lo - sb.dst_lo), run_hi - run_lo,
                                  cudaMemcpyDeviceToHost, s_out));
       run_lo = run_hi = 0;
       return SFB200_RC_OK;
     };
-    for (uint64_t j = sb.first; j < sb.first + sb.count; ++j) {
+    for (uint64_t j = 0; j < sb.count; ++j) {
+      const uint64_t i = sb.first + j;
       const uint64_t w = wr_host[j];
-      status[j] = st_host[j];
-      if (written) written[j] = w;
+      status[i] = st_host[j];
+      if (written) written[i] = w;
       if (w == 0) continue;
-      if (run_hi > run_lo && dst_off[j] == run_hi) {
+      if (run_hi > run_lo && dst_off[i] == run_hi) {
         run_hi += w;
       } else {
         rc = flush_run();
         if (rc) return rc;
-        run_lo = dst_off[j];
+        run_lo = dst_off[i];
         run_hi = run_lo + w;
       }
-      if (w != dst_cap[j]) {  // the rest of this region is not ours: the run ends here
+      if (w != dst_cap[i]) {  // the rest of this region is not ours: the run ends here
         rc = flush_run();
         if (rc) return rc;
       }
     }
     rc = flush_run();
     if (rc) return rc;
+    SFB_TRYC(cudaEventRecord(ctx->st_ev[slot][3], s_out));
   }
 #undef SFB_TRYC
   return cleanup(SFB200_RC_OK);
+}
+
+uint64_t sfb200_staging_bytes(const sfb200_ctx* ctx)
+{
+  return ctx ? static_cast<uint64_t>(ctx->st_slots) * (ctx->st_src_cap + ctx->st_dst_cap + 128) : 0;
+}
+
+// One batch, several GPUs: the streams are cut into contiguous shards balanced by the bytes they
+// move (sum of src_len + dst_cap) and every context decodes its shard through
+// sfb200_decompress_batch_host on a thread of its own.  No communication between the devices:
+// streams are independent.  Returns the first non-zero infrastructure code, if any.
+int sfb200_decompress_batch_host_multi(sfb200_ctx* const* ctxs, int n_ctx, const uint8_t* src, uint64_t src_bytes,
+                                       const uint64_t* src_off, const uint64_t* src_len, uint8_t* dst,
+                                       uint64_t dst_bytes, const uint64_t* dst_off, const uint64_t* dst_cap,
+                                       uint8_t* status, uint64_t* written, uint64_t n)
+{
+  if (!ctxs || n_ctx <= 0) return SFB200_RC_BAD_ARGUMENT;
+  for (int k = 0; k < n_ctx; ++k)
+    if (!ctxs[k]) return SFB200_RC_BAD_ARGUMENT;
+  if (n == 0) return SFB200_RC_OK;
+  if (!src_off || !src_len || !dst_off || !dst_cap || !status) return SFB200_RC_BAD_ARGUMENT;
+  if (n_ctx == 1)
+    return sfb200_decompress_batch_host(ctxs[0], src, src_bytes, src_off, src_len, dst, dst_bytes, dst_off, dst_cap,
+                                        status, written, n);
+  std::vector<uint64_t> cut(static_cast<size_t>(n_ctx) + 1, n);
+  sfb200_partition_streams(src_len, dst_cap, n, n_ctx, cut.data());
+  std::vector<int> rcs(static_cast<size_t>(n_ctx), SFB200_RC_OK);
+  std::vector<std::thread> th;
+  for (int k = 0; k < n_ctx; ++k) {
+    const uint64_t lo = cut[k], cnt = cut[k + 1] - cut[k];
+    if (cnt == 0) continue;
+    th.emplace_back([=, &rcs] {
+      rcs[k] = sfb200_decompress_batch_host(ctxs[k], src, src_bytes, src_off + lo, src_len + lo, dst, dst_bytes,
+                                            dst_off + lo, dst_cap + lo, status + lo, written ? written + lo : nullptr,
+                                            cnt);
+    });
+  }
+  for (auto& t : th) t.join();
+  for (int r : rcs)
+    if (r) return r;
+  return SFB200_RC_OK;
+}
+
+// cut[0] = 0 <= cut[1] <= ... <= cut[parts] = n: contiguous shards with (nearly) equal sums of
+// src_len + dst_cap.
+void sfb200_partition_streams(const uint64_t* src_len, const uint64_t* dst_cap, uint64_t n, int parts, uint64_t* cut)
+{
+  long double total = 0;
+  for (uint64_t i = 0; i < n; ++i) total += static_cast<long double>(src_len[i]) + static_cast<long double>(dst_cap[i]);
+  cut[0] = 0;
+  long double acc = 0;
+  uint64_t i = 0;
+  for (int k = 1; k < parts; ++k) {
+    const long double goal = total * k / parts;
+    while (i < n && acc + (static_cast<long double>(src_len[i]) + static_cast<long double>(dst_cap[i])) / 2 <= goal) {
+      acc += static_cast<long double>(src_len[i]) + static_cast<long double>(dst_cap[i]);
+      ++i;
+    }
+    cut[k] = i;
+  }
+  cut[parts] = n;
 }
 
 int sfb200_decompress(sfb200_ctx* ctx, const uint8_t* src, size_t src_len, uint8_t* dst,
@@ -952,7 +1139,7 @@ int sfb200_decompress_container_batch_device(sfb200_ctx* ctx, int container, con
   if (container == SFB200_CONTAINER_RAW)
     return sfb200_decompress_batch_device(ctx, src_base, src_off, src_len, dst_base, dst_bytes, dst_off, dst_cap,
                                           status, written, n, cuda_stream);
-  SFB_TRY(ctx, cudaSetDevice(ctx->device));
+  SFB_ENTER(ctx);
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   int rc = grow(ctx, &ctx->d_cont, &ctx->d_cont_cap, n * 36 + 64);
   if (rc != SFB200_RC_OK) return rc;
@@ -996,7 +1183,7 @@ int sfb200_decompress_container(sfb200_ctx* ctx, int container, const uint8_t* s
                                 uint8_t* dst, size_t dst_cap, uint8_t* status, uint64_t* written)
 {
   if (!ctx || !status || (!src && src_len) || (!dst && dst_cap)) return SFB200_RC_BAD_ARGUMENT;
-  SFB_TRY(ctx, cudaSetDevice(ctx->device));
+  SFB_ENTER(ctx);
   const uint64_t meta_at = (static_cast<uint64_t>(src_len) + 15) & ~15ull;
   int rc = grow(ctx, &ctx->d_src, &ctx->d_src_cap, meta_at + 64);
   if (rc != SFB200_RC_OK) return rc;
@@ -1025,7 +1212,7 @@ int sfb200_decompressed_size(sfb200_ctx* ctx, const uint8_t* src, size_t src_len
                              uint64_t* size)
 {
   if (!ctx || !status || !size || (!src && src_len)) return SFB200_RC_BAD_ARGUMENT;
-  SFB_TRY(ctx, cudaSetDevice(ctx->device));
+  SFB_ENTER(ctx);
   int rc = grow(ctx, &ctx->d_src, &ctx->d_src_cap, static_cast<uint64_t>(src_len) + 64);
   if (rc != SFB200_RC_OK) return rc;
   // metadata lives behind the stream in the same staging buffer: off, len, size (u64), status (u8)

@@ -911,17 +911,18 @@ __device__ __forceinline__ int parse_block_header(BitReader& br, const LaneMem& 
             }
           }
         }
-        // the two independent runs of code lengths (src/decompress.cpp:353-360)
+        // The HLIT + HDIST code lengths are ONE sequence (RFC 1951 §3.2.7: a repeat may run from
+        // the literal/length lengths into the distance lengths, and libdeflate, zopfli and 7-zip
+        // write such headers).  The reference decodes two independent runs
+        // (src/decompress.cpp:353-360) and has undefined behaviour exactly where the two readings
+        // differ — a repeat that crosses the boundary writes past its array, a 16 as the first
+        // distance length reads before it — so every input on which it is defined decodes the
+        // same here.
         const int total = n_lit + n_dist;
         LensWriter lw(m.lens);
-        int run_begin = 0, run_end = n_lit;
         uint32_t prev = 0;
 #pragma unroll 1
         for (int i = 0; i < total && err < 0;) {
-          if (i == run_end) {
-            run_begin = n_lit;
-            run_end = total;
-          }
           br.norm();
           const uint32_t bits = br.peek();
           const uint32_t j = bits & 127u;
@@ -941,10 +942,10 @@ __device__ __forceinline__ int parse_block_header(BitReader& br, const LaneMem& 
             err = ST_INVALID_LIT_OR_LEN;  // src/decompress.cpp:265-267
           } else if (left - static_cast<int64_t>(L) < static_cast<int64_t>(xbits)) {
             err = ST_SRC_TOO_SMALL;       // reference: unchecked pop_bits (class U)
-          } else if (sym == 16 && i == run_begin) {
-            err = ST_INVALID_LIT_OR_LEN;  // reference reads code_bitsizes[-1] (class U)
-          } else if (i + repeat > run_end) {
-            err = ST_INVALID_LIT_OR_LEN;  // reference writes past code_bitsizes (class U)
+          } else if (sym == 16 && i == 0) {
+            err = ST_INVALID_LIT_OR_LEN;  // no previous length to repeat (reference: reads code_bitsizes[-1], class U)
+          } else if (i + repeat > total) {
+            err = ST_INVALID_LIT_OR_LEN;  // more lengths than HLIT + HDIST (reference: writes past code_bitsizes, class U)
           } else {
             br.skip(L + xbits);
 #pragma unroll 1

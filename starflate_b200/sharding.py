@@ -9,24 +9,24 @@ import numpy as np
 
 def partition_streams(src_len, dst_cap, world: int):
     """-> list of `world` (first, count) ranges, contiguous and covering all streams, with
-    sum(src_len + dst_cap) per range as even as a contiguous cut allows."""
-    src_len = np.asarray(src_len, dtype=np.uint64)
-    dst_cap = np.asarray(dst_cap, dtype=np.uint64)
+    sum(src_len + dst_cap) per range as even as a contiguous cut allows.  The arithmetic is the
+    library's own (sfb200_partition_streams, which sfb200_decompress_batch_host_multi uses to cut a
+    batch across the GPUs of a box): host code, no device needed."""
+    import ctypes as C
+
+    from . import load_library
+    src_len = np.ascontiguousarray(src_len, dtype=np.uint64)
+    dst_cap = np.ascontiguousarray(dst_cap, dtype=np.uint64)
     n = len(src_len)
     assert len(dst_cap) == n and world >= 1
-    cost = np.cumsum((src_len + dst_cap).astype(np.float64))
-    total = float(cost[-1]) if n else 0.0
-    bounds = [0]
-    for r in range(1, world):
-        target = total * r / world
-        cut = int(np.searchsorted(cost, target, side="left")) if n else 0
-        if cut < n and n:  # put the boundary on the nearer side of the stream that straddles it
-            before = float(cost[cut - 1]) if cut else 0.0
-            if abs(float(cost[cut]) - target) <= abs(before - target):
-                cut += 1
-        bounds.append(max(bounds[-1], min(cut, n)))
-    bounds.append(n)
-    return [(bounds[r], bounds[r + 1] - bounds[r]) for r in range(world)]
+    lib = load_library()
+    u64p = C.POINTER(C.c_uint64)
+    lib.sfb200_partition_streams.argtypes = [u64p, u64p, C.c_uint64, C.c_int, u64p]
+    lib.sfb200_partition_streams.restype = None
+    cut = np.zeros(world + 1, dtype=np.uint64)
+    lib.sfb200_partition_streams(src_len.ctypes.data_as(u64p), dst_cap.ctypes.data_as(u64p), n, world,
+                                 cut.ctypes.data_as(u64p))
+    return [(int(cut[r]), int(cut[r + 1] - cut[r])) for r in range(world)]
 
 
 def max_over_ranks(value: float, device=None) -> float:

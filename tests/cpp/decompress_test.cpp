@@ -16,6 +16,8 @@
 #include <fstream>
 #include <iterator>
 #include <string>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -222,6 +224,23 @@ void test_decompress_gpu(const std::string& bases)
     bad[16] = std::byte{0x5c};
     EXPECT(decompress_container(bad, out, Container::Zlib, &wr) == ContainerStatus::ChecksumMismatch);
     EXPECT(decompress_container(z, out, Container::Gzip, &wr) == ContainerStatus::BadContainer);
+  }
+  {  // the reference's decompress() is re-entrant ("one stream per core"): eight threads at once,
+     // more than the mirror's pool holds contexts, each decoding the test page several times
+    const std::vector<std::byte> star = read_file(bases + "/starfleet_dynamic.deflate");
+    std::atomic<int> bad{0};
+    std::vector<std::thread> threads;
+    for (int t = 0; t < 8; ++t)
+      threads.emplace_back([&star, &bad, t] {
+        for (int k = 0; k < 3; ++k) {
+          std::vector<std::byte> out(149618 - (t == 7 ? 5 : 0));
+          const auto st = decompress(star, out);
+          if (t == 7 ? st != DecompressStatus::DstTooSmall : (st != DecompressStatus::Success || fnv1a64(out) != 0xe83588b6d41150e9ull))
+            ++bad;
+        }
+      });
+    for (auto& th : threads) th.join();
+    EXPECT(bad.load() == 0);
   }
 }
 }  // namespace

@@ -56,6 +56,12 @@ KNOWN = [
     ("dyn_rep16_first_dist", "05e0dbb66ddbb66ddb261b4cff948201", 4, INVALID_LIT_OR_LEN, None, "U"),
     ("dyn_rep18_overflow", "05e0dbb66ddbb66ddb261b4cff344a7f00", 4, INVALID_LIT_OR_LEN, None, "U"),
     ("dyn_eof_in_hclen", "05e0db", 4, SRC_TOO_SMALL, None, "U"),
+    # RFC 1951 §3.2.7: the HLIT + HDIST code lengths are one sequence.  A repeat that runs from the
+    # lit/len lengths into the distance lengths, or a 16 as the first distance length, is valid
+    # (zlib decodes both to "aaaaa"; libdeflate, zopfli and 7-zip write such headers); the reference
+    # decodes two independent runs and is undefined here (class U): decoded as the RFC says.
+    ("dyn_rep16_crosses_into_dist", "05e307090000008030649dfd43f8c0", 8, SUCCESS, "6161616161", "U"),
+    ("dyn_rep16_first_dist_valid", "05e307090000008030649dfd43780403", 8, SUCCESS, "6161616161", "U"),
 ]
 
 # read_header vectors (decompress_test.cpp:62-89): (bytes, bit_size, has_value, final, type, error)

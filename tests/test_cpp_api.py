@@ -20,7 +20,7 @@ def test_binary():
     os.makedirs(os.path.dirname(BIN), exist_ok=True)
     deps = [src, build.CXX_SO] + [os.path.join(d, f) for d, _, fs in os.walk(os.path.join(ROOT, "starflate_b200", "cpp")) for f in fs]
     if not os.path.exists(BIN) or any(os.path.getmtime(d) > os.path.getmtime(BIN) for d in deps):
-        subprocess.check_call(["g++", "-std=c++23", "-O1", "-fno-exceptions", "-w",
+        subprocess.check_call(["g++", "-std=c++23", "-O1", "-fno-exceptions", "-w", "-pthread",
                                "-I", os.path.join(ROOT, "starflate_b200", "cpp"), "-I", os.path.join(ROOT, "include"),
                                "-o", BIN, src, "-L", build.OUT, "-lstarflate", "-lstarflate_b200",
                                f"-Wl,-rpath,{build.OUT}"])

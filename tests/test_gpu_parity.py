@@ -114,7 +114,7 @@ def test_host_batch_api_pipelined_sub_batches(ctx, oracle, monkeypatch):
     """The host entry point cut into many sub-batches (H2D / kernels / D2H overlapped): ragged
     regions, gaps, failures and short capacities must come back exactly as from one batch, and
     every byte the decoder did not produce must keep the caller's value."""
-    monkeypatch.setenv("SFB200_HOST_CHUNK_KB", "48")
+    monkeypatch.setenv("SFB200_HOST_STAGING_KB", "48")
     rng = np.random.default_rng(3)
     streams, caps = [], []
     for i in range(300):
@@ -131,6 +131,65 @@ def test_host_batch_api_pipelined_sub_batches(ctx, oracle, monkeypatch):
         dst_o = b.new_dst()
         ost, owr, _ = oracle.decompress_batch(b.src, b.src_off, b.src_len, dst_o, b.dst_off, b.dst_cap)
         assert (st == ost).all() and (wr == owr).all() and (dst == dst_o).all()
+
+
+def test_host_batch_larger_than_the_staging_budget(oracle, monkeypatch):
+    """SURVEY.md §8 f3 (bounded device memory): a batch several times the configured staging budget
+    decodes through the ring of three sub-batch slots, bit-exact, failures and short capacities
+    included, and the context's staging never grows beyond the budget."""
+    import starflate_b200 as S
+    monkeypatch.setenv("SFB200_HOST_STAGING_MB", "6")
+    c = S.Context(0)
+    try:
+        rng = np.random.default_rng(5)
+        streams, caps = [], []
+        for i in range(700):
+            kind = ["dynamic", "fixed", "stored", "multiblock", "repetitive"][i % 5]
+            plain, comp = T.make_stream(kind, int(rng.integers(20000, 70000)), 12000 + i)
+            if i % 13 == 0:
+                comp = comp[: int(rng.integers(0, len(comp)))]
+            streams.append(comp)
+            caps.append(len(plain) - (5 if i % 11 == 0 else 0))
+        b = T.Batch(streams, caps, dst_align=1)
+        assert b.dst_total > 5 * (6 << 20)
+        dst = b.new_dst()
+        st, wr = c.decompress_batch_host(b.src, b.src_off, b.src_len, dst, b.dst_off, b.dst_cap)
+        dst_o = b.new_dst()
+        ost, owr, _ = oracle.decompress_batch(b.src, b.src_off, b.src_len, dst_o, b.dst_off, b.dst_cap)
+        assert (st == ost).all() and (wr == owr).all() and (dst == dst_o).all()
+        assert c.staging_bytes() <= (6 << 20) + 3 * 1024
+    finally:
+        c.close()
+
+
+def test_one_batch_across_several_contexts(oracle):
+    """sfb200_decompress_batch_host_multi: one batch cut into contiguous shards, one per context
+    (normally one per GPU; two contexts on the devices that are there), each on its own host
+    thread — results as from one call, and the caller's current device is left alone."""
+    import torch
+
+    import starflate_b200 as S
+    ndev = torch.cuda.device_count()
+    ctxs = [S.Context(k % ndev) for k in range(max(2, min(ndev, 4)))]
+    try:
+        rng = np.random.default_rng(6)
+        streams, caps = [], []
+        for i in range(400):
+            kind = ["dynamic", "fixed", "stored", "multiblock", "repetitive"][i % 5]
+            plain, comp = T.make_stream(kind, int(rng.integers(1, 40000)), 15000 + i)
+            streams.append(comp if i % 10 else comp[: len(comp) // 3])
+            caps.append(len(plain) - (3 if i % 6 == 0 else 0))
+        b = T.Batch(streams, caps, dst_align=1)
+        before = torch.cuda.current_device()
+        dst = b.new_dst()
+        st, wr = S.Context.decompress_batch_host_multi(ctxs, b.src, b.src_off, b.src_len, dst, b.dst_off, b.dst_cap)
+        assert torch.cuda.current_device() == before
+        dst_o = b.new_dst()
+        ost, owr, _ = oracle.decompress_batch(b.src, b.src_off, b.src_len, dst_o, b.dst_off, b.dst_cap)
+        assert (st == ost).all() and (wr == owr).all() and (dst == dst_o).all()
+    finally:
+        for c in ctxs:
+            c.close()
 
 
 def test_small_table_geometry_with_hand_over(oracle, golden, monkeypatch):
