@@ -5,6 +5,7 @@
 #include "huff_lanes.cuh"
 #include "huff_stream.cuh"
 #include "lz_warp.cuh"
+#include "lz_window.cuh"
 #include "lz_jump.cuh"
 #include "container.cuh"
 
@@ -61,6 +62,7 @@ struct sfb200_ctx {
   int regs_per_thread = 0;
   int lz_ctas_per_sm = 0;
   int lz_regs_per_thread = 0;
+  bool lz_v1 = false;          // SFB200_LZ_V1=1: the first-generation pass 2 (lz_warp.cuh), kept for A/B runs
   int small_ctas_per_sm = 0;   // SmallCfg pass 1 (0: not usable)
   int small_regs_per_thread = 0;
   int stream_ctas_per_sm = 0;  // huff_stream_kernel (0: not usable)
@@ -199,9 +201,12 @@ int sfb200_create(int device, sfb200_ctx** out)
   cudaFuncAttributes fa;
   if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess) ctx->regs_per_thread = fa.numRegs;
   {
+    if (const char* e = std::getenv("SFB200_LZ_V1")) ctx->lz_v1 = e[0] == '1';
+    static_assert(sfb::LZ_THREADS == sfb::LZW_THREADS, "one launch geometry for both pass-2 kernels");
     int lz_per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lz_per_sm, sfb::lz_resolve_kernel,
-                                                      sfb::LZ_THREADS, 0) != cudaSuccess ||
+    if ((ctx->lz_v1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lz_per_sm, sfb::lz_resolve_kernel, sfb::LZ_THREADS, 0)
+                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lz_per_sm, sfb::lz_window_kernel, sfb::LZW_THREADS, 0)) !=
+            cudaSuccess ||
         lz_per_sm < 1)
       return bail(SFB200_RC_CUDA_ERROR);
     // fewer resident warps keep the streams' 32 KiB windows inside the L2
@@ -209,7 +214,8 @@ int sfb200_create(int device, sfb200_ctx** out)
     if (const char* e = std::getenv("SFB200_LZ_CTAS_PER_SM")) cap = std::atoi(e);
     ctx->lz_ctas_per_sm = (cap > 0 && cap < lz_per_sm) ? cap : lz_per_sm;
     cudaFuncAttributes lfa;
-    if (cudaFuncGetAttributes(&lfa, sfb::lz_resolve_kernel) == cudaSuccess)
+    if ((ctx->lz_v1 ? cudaFuncGetAttributes(&lfa, sfb::lz_resolve_kernel)
+                    : cudaFuncGetAttributes(&lfa, sfb::lz_window_kernel)) == cudaSuccess)
       ctx->lz_regs_per_thread = lfa.numRegs;
   }
   if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_counter), (kCountersPerWave * kMaxWaves + 8) * sizeof(unsigned long long)) !=
@@ -720,7 +726,8 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
       const uint64_t resident =
           static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->lz_ctas_per_sm);
       const unsigned grid = static_cast<unsigned>(want < resident ? want : resident);
-      sfb::lz_resolve_kernel<<<grid, sfb::LZ_THREADS, 0, s2>>>(r);
+      if (ctx->lz_v1) sfb::lz_resolve_kernel<<<grid, sfb::LZ_THREADS, 0, s2>>>(r);
+      else sfb::lz_window_kernel<<<grid, sfb::LZW_THREADS, 0, s2>>>(r);
       SFB_TRY(ctx, cudaGetLastError());
     }
     ctx->launches += 1;

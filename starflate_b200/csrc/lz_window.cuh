@@ -1,0 +1,472 @@
+// Pass 2 of the batched raw-DEFLATE decoder for sm_100a, second generation: LZ77 back-references,
+// ONE WARP PER STREAM, driven by 1 KiB WINDOWS of the match-head bitmap.
+//
+// Replaces the copy half of the reference's decompress_length_distance and copy_from_before
+// (src/decompress.cpp:157-187,388-398) exactly like lz_warp.cuh (same input: literals and 3-byte
+// match descriptors in place, one bitmap bit per match head; all range / room checks were made by
+// pass 1) — what changes is how the work is cut:
+//
+//   * A lane loads ONE bitmap word per window (32 lanes x 32 bits = 1024 output bytes); the head
+//     count of the window (popc + warp reduction) picks the mode.
+//   * SPARSE windows (<= LZW_SPARSE_MAX heads; none at all for stored data): matches are taken one
+//     at a time, in order.  A maximum-length match is checked, 32 candidates at once, for being the
+//     first of a RUN of back-to-back matches with the same distance (what a compressor makes of a
+//     long repeat: byte p = byte p - D over the whole run), and the run is FILLED in one go:
+//       - D in {1,2,4,8,16}: the 16-byte pattern is built once and stored with 16-byte vector
+//         stores, 512 bytes per warp iteration, no loads at all (memset-like);
+//       - D >= 512: 16 bytes per lane copied from p - D, iterations separated by __syncwarp;
+//       - anything else: 4 bytes per lane from the period [p0 - D, p0), phase kept incrementally.
+//   * DENSE windows (text): 128-byte chunks, one aligned word per lane.  DEFLATE's minimum match
+//     length of 3 means a word holds at most two heads and its bytes fall into at most TWO
+//     segments: bytes [0, nA) continue match A (the incoming one, or a head at byte 0), bytes
+//     [s, 4) belong to the word's last head B.  Non-overlapping segments (distance >= length, 99.9 %
+//     of text matches) are gathered as ONE unaligned word each; a chunk none of whose sources lies
+//     inside the chunk itself (two thirds of text chunks) is done in a single shot without the
+//     frontier machinery.  Overlapping matches and the ragged first / last chunk of a stream take
+//     the per-byte walk of lz_warp.cuh.
+#pragma once
+
+#include "lz_warp.cuh"
+
+namespace sfb {
+
+constexpr int LZW_THREADS = 256;
+constexpr uint32_t LZW_SPARSE_MAX = 6;
+constexpr uint32_t LZW_NONE = 0xffffffffu;
+
+struct LzwView {
+  uint8_t* base;          // view byte v lives at base[v]; base is 128-byte aligned, windows start at v % 1024 == 0
+  const uint32_t* bits;   // bitmap word of view bytes [32 w, 32 w + 32) at bits[w]
+  uint32_t q, end;        // the stream occupies view bytes [q, end)
+  uint32_t lane;
+};
+
+__device__ __forceinline__ uint32_t lzw_popc(uint32_t v)
+{
+#ifdef SFB_CPU_EMU
+  return static_cast<uint32_t>(__builtin_popcount(v));
+#else
+  return static_cast<uint32_t>(__popc(v));
+#endif
+}
+__device__ __forceinline__ uint32_t lzw_ldw(const uint8_t* base, uint32_t v)  // v % 4 == 0
+{
+  return *reinterpret_cast<const uint32_t*>(base + v);
+}
+__device__ __forceinline__ void lzw_st16(uint8_t* p, uint32_t x, uint32_t y, uint32_t z, uint32_t w)  // p % 16 == 0
+{
+  uint4 v;
+  v.x = x;
+  v.y = y;
+  v.z = z;
+  v.w = w;
+  *reinterpret_cast<uint4*>(p) = v;
+}
+__device__ __forceinline__ void lzw_prefetch(const void* p)
+{
+#ifndef SFB_CPU_EMU
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+// the 3-byte descriptor at view position h (any alignment; h + 2 is inside the stream)
+__device__ __forceinline__ uint32_t lzw_desc(const uint8_t* base, uint32_t h)
+{
+  const uint32_t a = h & ~3u, r = h & 3u;
+  const uint32_t lo = lzw_ldw(base, a);
+  const uint32_t hi = r >= 2u ? lzw_ldw(base, a + 4u) : 0u;
+  return lz_funnel(lo, hi, 8u * r) & 0xffffffu;
+}
+// n source bytes (1 <= n <= 4) starting at view position f, as the low bytes of a word; only aligned
+// words that hold at least one of them are read
+__device__ __forceinline__ uint32_t lzw_gather(const uint8_t* base, uint32_t f, uint32_t n)
+{
+  const uint32_t a = f & ~3u, r = f & 3u;
+  const uint32_t lo = lzw_ldw(base, a);
+  const uint32_t hi = r + n > 4u ? lzw_ldw(base, a + 4u) : 0u;
+  return lz_funnel(lo, hi, 8u * r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// FILL: bytes [p0, p1) := the periodic continuation of the d bytes before p0 (byte p = byte p - d,
+// front to back — what copy_from_before() produces for one match, or for a run of back-to-back
+// matches with the same distance).  All bytes below p0 are final.  Warp-uniform arguments.
+
+// 4 bytes per lane; reads only from the period [p0 - d, p0)
+__device__ __noinline__ void lzw_fill_periodic(const LzwView v, uint32_t p0, uint32_t p1, uint32_t d)
+{
+  uint8_t* const base = v.base;
+  uint32_t a = (p0 & ~3u) + 4u * v.lane;
+  if (a >= p1) return;
+  // phase of byte a inside the period (a may lie up to 3 bytes before p0: add whole periods first)
+  uint32_t m = (a + 4u * d - p0) % d;
+  const uint32_t step = 128u % d;
+  const uint32_t s0 = p0 - d;
+  for (; a < p1; a += 128u) {
+    const bool full = a >= p0 && a + 4u <= p1;
+    uint32_t val;
+    if (full && d >= 4u && m + 3u < d) {  // four consecutive sources
+      val = lzw_gather(base, s0 + m, 4u);
+      *reinterpret_cast<uint32_t*>(base + a) = val;
+    } else {
+      uint32_t mb = m;
+#pragma unroll
+      for (uint32_t b = 0; b < 4; ++b) {
+        while (mb >= d) mb -= d;
+        const uint32_t p = a + b;
+        if (p >= p0 && p < p1) base[p] = base[s0 + mb];
+        ++mb;
+      }
+    }
+    m += step;
+    if (m >= d) m -= d;
+  }
+}
+
+// d in {1, 2, 4, 8, 16}: the 16 bytes of every aligned 16-byte slot are the same — build them once
+__device__ __noinline__ void lzw_fill_pattern16(const LzwView v, uint32_t p0, uint32_t p1, uint32_t d)
+{
+  constexpr unsigned FULL = 0xffffffffu;
+  uint8_t* const base = v.base;
+  const uint32_t r = p0 & 15u;
+  // slot byte t (position (p0 & ~15) + t) = period byte ((t - r) mod d); lane k < 4 assembles word k
+  uint32_t w = 0;
+  {
+    const uint32_t k = v.lane & 3u;
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j) {
+      const uint32_t t = 4u * k + j;
+      w |= static_cast<uint32_t>(base[p0 - d + ((t - r) & (d - 1u))]) << (8u * j);
+    }
+  }
+  const uint32_t r0 = __shfl_sync(FULL, w, 0), r1 = __shfl_sync(FULL, w, 1), r2 = __shfl_sync(FULL, w, 2),
+                 r3 = __shfl_sync(FULL, w, 3);
+  const uint32_t h16 = (p0 + 15u) & ~15u;   // first full slot
+  const uint32_t t16 = p1 & ~15u;           // end of the last full slot
+  // ragged head [p0, h16) and tail [t16, p1): lane t < 16 owns slot byte t
+  if (v.lane < 16u) {
+    const uint32_t t = v.lane;
+    const uint32_t word = (t & 8u) ? ((t & 4u) ? r3 : r2) : ((t & 4u) ? r1 : r0);
+    const uint8_t byte = static_cast<uint8_t>(word >> (8u * (t & 3u)));
+    const uint32_t ph = (p0 & ~15u) + t;
+    if (ph >= p0 && ph < p1 && ph < h16) base[ph] = byte;
+    const uint32_t pt = t16 + t;
+    if (t16 >= h16 && pt < p1) base[pt] = byte;
+  }
+  for (uint32_t a = h16 + 16u * v.lane; a + 16u <= t16 + 0u && a < t16; a += 512u) lzw_st16(base + a, r0, r1, r2, r3);
+}
+
+// d >= 512: 16 bytes per lane from p - d; a 512-byte iteration only reads what earlier iterations
+// (or earlier matches) wrote
+__device__ __noinline__ void lzw_fill_far(const LzwView v, uint32_t p0, uint32_t p1, uint32_t d)
+{
+  uint8_t* const base = v.base;
+  const uint32_t h16 = (p0 + 15u) & ~15u, t16 = p1 & ~15u;
+  if (h16 >= t16) {
+    lzw_fill_periodic(v, p0, p1, d);
+    return;
+  }
+  if (p0 < h16) lzw_fill_periodic(v, p0, h16, d);  // (reads [p0 - d, p0) only)
+  __syncwarp();
+  for (uint32_t a0 = h16; a0 < t16; a0 += 512u) {
+    const uint32_t a = a0 + 16u * v.lane;
+    if (a < t16) {
+      const uint32_t s = a - d, sa = s & ~3u, sh = 8u * (s & 3u);
+      const uint32_t w0 = lzw_ldw(base, sa), w1 = lzw_ldw(base, sa + 4u), w2 = lzw_ldw(base, sa + 8u),
+                     w3 = lzw_ldw(base, sa + 12u);
+      const uint32_t w4 = sh ? lzw_ldw(base, sa + 16u) : 0u;
+      lzw_st16(base + a, lz_funnel(w0, w1, sh), lz_funnel(w1, w2, sh), lz_funnel(w2, w3, sh), lz_funnel(w3, w4, sh));
+    }
+    __syncwarp();
+  }
+  if (t16 < p1) lzw_fill_periodic(v, t16, p1, d);
+}
+
+__device__ __forceinline__ void lzw_fill(const LzwView& v, uint32_t p0, uint32_t p1, uint32_t d)
+{
+  const uint32_t n = p1 - p0;
+  if (n >= 48u && d <= 16u && (d & (d - 1u)) == 0u) lzw_fill_pattern16(v, p0, p1, d);
+  else if (n >= 48u && d >= 512u) lzw_fill_far(v, p0, p1, d);
+  else lzw_fill_periodic(v, p0, p1, d);
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------
+// One 128-byte chunk of a dense window.  `lo`/`hi`: only bytes in [lo, hi) are this call's to
+// produce (stream edges; bytes a fill has already produced).  EDGE = the chunk is not wholly
+// inside [lo, hi).  c_*: the most recent match seen so far (in/out).
+template <bool EDGE>
+__device__ __forceinline__ void lzw_chunk(const LzwView& v, uint32_t P, uint32_t lo, uint32_t hi, uint32_t cw,
+                                          uint32_t ncw, uint32_t hb4, uint32_t& c_o, uint32_t& c_end,
+                                          uint32_t& c_d)
+{
+  constexpr unsigned FULL = 0xffffffffu;
+  uint8_t* const base = v.base;
+  const uint32_t lane = v.lane;
+  const uint32_t wp = P + 4u * lane;
+  uint32_t vm = 15u;
+  if (EDGE) {
+    const uint32_t l = lo > wp ? (lo - wp < 4u ? lo - wp : 4u) : 0u;
+    const uint32_t h = hi > wp ? (hi - wp < 4u ? hi - wp : 4u) : 0u;
+    vm = h > l ? ((1u << h) - 1u) & ~((1u << l) - 1u) : 0u;
+  }
+  const uint32_t hb = hb4 & vm;
+  // the word after mine (lane 31: first word of the next chunk)
+  const uint32_t nx = __shfl_sync(FULL, lane == 0u ? ncw : cw, static_cast<int>((lane + 1u) & 31u));
+  const uint32_t hl = 31u - static_cast<uint32_t>(__clz(static_cast<int>(hb | 1u)));  // my last head (0: none or byte 0)
+  const uint32_t dl = lz_funnel(cw, nx, 8u * hl) & 0xffffffu;                         // its descriptor
+  const uint32_t own_pack = (4u * lane + hl) | (dl << 7);
+  const uint32_t hm = __ballot_sync(FULL, hb != 0);
+  const uint32_t below = hm & ((1u << lane) - 1u);
+  const uint32_t sl = 31u - static_cast<uint32_t>(__clz(static_cast<int>(below | 1u)));
+  const uint32_t in_pack = __shfl_sync(FULL, own_pack, static_cast<int>(sl));
+  uint32_t in_o = c_o, in_end = c_end, in_d = c_d;
+  if (below) {
+    in_o = P + (in_pack & 127u);
+    in_end = in_o + ((in_pack >> 7) & 255u) + 3u;
+    in_d = (in_pack >> 15) + 1u;
+  }
+  if (hm) {  // (warp-uniform) the last head of this chunk is carried into the next ones
+    const uint32_t top = 31u - static_cast<uint32_t>(__clz(static_cast<int>(hm)));
+    const uint32_t pk = __shfl_sync(FULL, own_pack, static_cast<int>(top));
+    c_o = P + (pk & 127u);
+    c_end = c_o + ((pk >> 7) & 255u) + 3u;
+    c_d = (pk >> 15) + 1u;
+  }
+  // my bytes: [0, nA) continue match A, [s, 4) belong to my last head B (length >= 3 covers them all)
+  const bool has0 = (hb & 1u) != 0;
+  const bool hasB = (hb & 0xeu) != 0;
+  const uint32_t s = hasB ? hl : 4u;
+  const uint32_t A_o = has0 ? wp : in_o;
+  const uint32_t A_e = has0 ? wp + (cw & 255u) + 3u : in_end;
+  const uint32_t A_d = has0 ? ((cw >> 8) & 0xffffu) + 1u : in_d;
+  const uint32_t B_d = (dl >> 8) + 1u;
+  uint32_t nA = A_e > wp ? A_e - wp : 0u;
+  nA = nA < s ? nA : s;
+  bool bytewise = EDGE;
+  if (!EDGE) {
+    const bool ovl = (nA != 0u && wp + nA - 1u - A_o >= A_d) || (hasB && 3u - s >= B_d);
+    bytewise = __any_sync(FULL, ovl) != 0;
+  }
+  if (!bytewise) {
+    // ---- segment mode: one unaligned word per segment ------------------------------------------
+    bool pendA = nA != 0u, pendB = hasB;
+    const uint32_t fA = wp - A_d, lastA = fA + nA - 1u;
+    const uint32_t fB = wp + s - B_d, lastB = wp + 3u - B_d;
+    const uint32_t mA = 0xffffffffu >> ((32u - 8u * nA) & 31u);  // (nA >= 1 where it is used)
+    const uint32_t mB = 0xffffffffu << ((8u * s) & 31u);         // (s < 4 where it is used)
+    uint32_t res = cw;
+    const bool dep = (pendA && lastA >= P) || (pendB && lastB >= P);
+    if (!__any_sync(FULL, dep)) {  // every source lies before the chunk: one shot
+      if (pendA) {
+        const uint32_t g = lzw_gather(base, fA, nA);
+        res = (res & ~mA) | (g & mA);
+      }
+      if (pendB) {
+        const uint32_t g = lzw_gather(base, fB, 4u - s) << ((8u * s) & 31u);
+        res = (res & ~mB) | (g & mB);
+      }
+      if (pendA | pendB) *reinterpret_cast<uint32_t*>(base + wp) = res;
+      __syncwarp();
+      return;
+    }
+    for (;;) {
+      // F = first byte of the chunk that is still unresolved
+      const uint32_t first = pendA ? wp : (pendB ? wp + s : LZW_NONE);
+      const uint32_t bal = __ballot_sync(FULL, first != LZW_NONE);
+      if (bal == 0) break;
+      const uint32_t F = __shfl_sync(FULL, first, __ffs(static_cast<int>(bal)) - 1);
+      const bool doA = pendA && lastA < F, doB = pendB && lastB < F;
+      if (doA) {
+        const uint32_t g = lzw_gather(base, fA, nA);
+        res = (res & ~mA) | (g & mA);
+        pendA = false;
+      }
+      if (doB) {
+        const uint32_t g = lzw_gather(base, fB, 4u - s) << ((8u * s) & 31u);
+        res = (res & ~mB) | (g & mB);
+        pendB = false;
+      }
+      if (doA | doB) *reinterpret_cast<uint32_t*>(base + wp) = res;
+      __syncwarp();
+    }
+    return;
+  }
+  // ---- per-byte mode (overlapping matches, ragged chunks): sources by the period rule ---------
+  uint32_t src[4];
+  uint32_t pend = 0;
+#pragma unroll
+  for (uint32_t b = 0; b < 4; ++b) {
+    const bool useB = b >= s;
+    const uint32_t o = useB ? wp + s : A_o;
+    const uint32_t d = useB ? B_d : A_d;
+    const bool cov = ((vm >> b) & 1u) && (useB || b < nA);
+    uint32_t k = wp + b - o;
+    if (cov && k >= d) k = lz_mod_small(k, d);  // overlapping copy: period d
+    src[b] = o - d + k;
+    if (cov) pend |= 1u << b;
+  }
+  uint32_t res = cw;
+  for (;;) {
+    const uint32_t pm_any = __ballot_sync(FULL, pend != 0);
+    if (pm_any == 0) break;
+    const int fl = __ffs(static_cast<int>(pm_any)) - 1;
+    const uint32_t fp = __shfl_sync(FULL, pend, fl);
+    const uint32_t F = P + 4u * static_cast<uint32_t>(fl) + static_cast<uint32_t>(__ffs(static_cast<int>(fp)) - 1);
+#pragma unroll
+    for (uint32_t b = 0; b < 4; ++b) {
+      if (((pend >> b) & 1u) && src[b] < F) {
+        const uint32_t byte = base[src[b]];
+        res = lz_prmt(res, byte, 0x3210u ^ ((0x4u ^ b) << (4u * b)));  // byte b <- `byte`
+        pend &= ~(1u << b);
+      }
+    }
+    if (vm == 15u) {
+      *reinterpret_cast<uint32_t*>(base + wp) = res;
+    } else {  // a word this call does not own alone: only our bytes
+#pragma unroll
+      for (uint32_t b = 0; b < 4; ++b)
+        if ((vm >> b) & 1u) base[wp + b] = static_cast<uint8_t>(res >> (8u * b));
+    }
+    __syncwarp();
+  }
+}
+
+// this lane's bitmap word of window W, restricted to the stream's own bytes
+__device__ __forceinline__ uint32_t lzw_window_bits(const LzwView& v, uint32_t W)
+{
+  const uint32_t pos0 = W + 32u * v.lane;
+  if (pos0 >= v.end || pos0 + 32u <= v.q) return 0u;
+  uint32_t w = v.bits[pos0 >> 5];
+  if (pos0 < v.q) w &= 0xffffffffu << (v.q - pos0);
+  if (pos0 + 32u > v.end) w &= 0xffffffffu >> (pos0 + 32u - v.end);
+  return w;
+}
+
+__global__ void __launch_bounds__(LZW_THREADS, 5) lz_window_kernel(const ResolveArgs a)
+{
+  constexpr unsigned FULL = 0xffffffffu;
+  const uint32_t lane = threadIdx.x & 31u;
+  for (;;) {
+    unsigned long long si = 0;
+    if (lane == 0) si = atomicAdd(a.stream_counter, 1ull);
+    si = __shfl_sync(FULL, si, 0);
+    if (si >= a.n) break;
+    si = a.todo_list ? a.todo_list[si] : a.idx_base + si;
+    const uint64_t off = a.dst_off[si] + a.dst_delta;
+    const uint64_t wr = a.written[si];
+    if (wr == 0) continue;
+    LzwView v;
+    v.base = a.dst_base + (off & ~1023ull);
+    v.bits = a.match_bits + ((off & ~1023ull) >> 5);
+    v.q = static_cast<uint32_t>(off & 1023u);
+    v.end = v.q + static_cast<uint32_t>(wr);
+    v.lane = lane;
+    const uint32_t end = v.end;
+    uint32_t cur = v.q;                        // every byte below cur is final (dense mode: see c_*)
+    uint32_t c_o = 0, c_end = 0, c_d = 1;      // dense mode: the most recent match, may reach past cur
+    uint32_t pre_P = LZW_NONE, pre_w = 0;      // a chunk word loaded ahead (valid while nothing was written there)
+    uint32_t W = 0;
+    uint32_t wbits = lzw_window_bits(v, 0);
+    while (W < end) {
+      if (cur >= W + 1024u) {  // a run went past this window
+        W = cur & ~1023u;
+        if (W >= end) break;
+        wbits = lzw_window_bits(v, W);
+        continue;
+      }
+      const uint32_t pos0 = W + 32u * lane;
+      uint32_t mine = wbits;  // heads at or after cur
+      if (cur > pos0) mine = cur - pos0 >= 32u ? 0u : mine & (0xffffffffu << (cur - pos0));
+      uint32_t cnt = lzw_popc(mine);
+      cnt = __reduce_add_sync(FULL, cnt);
+      const uint32_t wend = W + 1024u < end ? W + 1024u : end;
+      if (c_end > cur && (cnt <= LZW_SPARSE_MAX || c_end - cur >= 128u)) {
+        // the match carried out of a dense chunk: finish it in one go
+        const uint32_t e = c_end;
+        lzw_fill(v, cur, e, c_d);
+        cur = e;
+        c_end = 0;
+        pre_P = LZW_NONE;
+        continue;
+      }
+      if (cnt <= LZW_SPARSE_MAX && c_end <= cur) {
+        // ---- sparse window: one match (or run of matches) at a time ---------------------------
+        if (cnt) pre_P = LZW_NONE;
+        while (cnt) {
+          uint32_t m2 = wbits;
+          if (cur > pos0) m2 = cur - pos0 >= 32u ? 0u : m2 & (0xffffffffu << (cur - pos0));
+          const uint32_t bal = __ballot_sync(FULL, m2 != 0);
+          if (bal == 0) break;
+          const int fl = __ffs(static_cast<int>(bal)) - 1;
+          const uint32_t fm = __shfl_sync(FULL, m2, fl);
+          const uint32_t h = W + 32u * static_cast<uint32_t>(fl) + static_cast<uint32_t>(__ffs(static_cast<int>(fm)) - 1);
+          const uint32_t desc = lzw_desc(v.base, h);
+          const uint32_t L = (desc & 255u) + 3u, D = (desc >> 8) + 1u;
+          uint32_t run_end = h + L;
+          if (L == 258u) {
+            // is this the first of a run of back-to-back matches with the same distance?  Lane i
+            // looks at h + i L (lane 0 at the head itself).
+            const uint32_t g = h + lane * L;
+            bool okD = false, ok = false;
+            uint32_t Lg = 0;
+            if (g + 3u <= end && ((v.bits[g >> 5] >> (g & 31u)) & 1u)) {
+              const uint32_t dg = lzw_desc(v.base, g);
+              Lg = (dg & 255u) + 3u;
+              okD = (dg >> 8) + 1u == D;
+              ok = okD && Lg == L;
+            }
+            const uint32_t okm = __ballot_sync(FULL, ok), okDm = __ballot_sync(FULL, okD);
+            const uint32_t f = okm == FULL ? 32u : static_cast<uint32_t>(__ffs(static_cast<int>(~okm)) - 1);  // >= 1
+            run_end = h + f * L;
+            const uint32_t Lf = __shfl_sync(FULL, Lg, static_cast<int>(f & 31u));
+            if (f < 32u && ((okDm >> f) & 1u)) run_end += Lf;  // a shorter last one
+          }
+          __syncwarp();  // every lane has read the descriptor(s) before the fill overwrites them
+          lzw_fill(v, h, run_end, D);
+          cur = run_end;
+          if (cur >= wend) break;
+        }
+        if (cur < wend) cur = wend;
+        if (cur >= W + 1024u || cur >= end) {
+          W += 1024u;
+          if (W < end) wbits = lzw_window_bits(v, W);
+        }
+        continue;
+      }
+      // ---- dense window: 128-byte chunks --------------------------------------------------------
+      if (W + 1024u < end) lzw_prefetch(v.base + W + 1024u + 32u * lane);
+      {
+        uint32_t P = cur & ~127u;
+        const uint32_t lo = cur;  // (bytes below are final or not ours)
+        auto load_w = [&](uint32_t PP) -> uint32_t {
+          const uint32_t wp = PP + 4u * lane;
+          return (wp + 4u > v.q && wp < end) ? lzw_ldw(v.base, wp) : 0u;
+        };
+        uint32_t cw = pre_P == P ? pre_w : load_w(P);
+        bool stopped = false;
+        for (; P < wend; P += 128u) {
+          if (c_end >= P + 128u && c_end > cur && P >= lo) {  // the carried match covers the whole chunk: fill it
+            stopped = true;
+            break;
+          }
+          const uint32_t ncw = load_w(P + 128u);
+          const uint32_t mw = __shfl_sync(FULL, wbits, static_cast<int>(((P - W) >> 5) + (lane >> 3)));
+          const uint32_t hb4 = (mw >> (4u * (lane & 7u))) & 15u;
+          if (P >= lo && P + 128u <= end) lzw_chunk<false>(v, P, lo, end, cw, ncw, hb4, c_o, c_end, c_d);
+          else lzw_chunk<true>(v, P, lo, end, cw, ncw, hb4, c_o, c_end, c_d);
+          cw = ncw;
+          cur = P + 128u < end ? P + 128u : end;
+        }
+        pre_P = P;
+        pre_w = cw;
+        if (stopped) continue;  // (the fill branch above takes it from here)
+      }
+      W += 1024u;
+      if (W < end) wbits = lzw_window_bits(v, W);
+    }
+  }
+}
+
+}  // namespace sfb

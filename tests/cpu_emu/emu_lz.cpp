@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE ONLY — the pass-2 kernel (lz_warp.cuh) run on the host, one warp = 32
+// TEST INFRASTRUCTURE ONLY — the pass-2 kernel (lz_window.cuh) run on the host, one warp = 32
 // threads in lock-step through real barriers (see cuda_shim_warp.h).
 #define SFB_CPU_EMU 1
 #include "cuda_shim_warp.h"
@@ -6,7 +6,10 @@
 #include <thread>
 #include <vector>
 
-#include "../../starflate_b200/csrc/lz_warp.cuh"
+#include <cstdlib>
+#include <cstdio>
+
+#include "../../starflate_b200/csrc/lz_window.cuh"
 
 extern "C" void emu_lz_resolve(uint8_t* dst_base, const uint64_t* dst_off, const uint64_t* written,
                                const uint32_t* match_bits, uint64_t n)
@@ -31,7 +34,8 @@ extern "C" void emu_lz_resolve(uint8_t* dst_base, const uint64_t* dst_off, const
       blockIdx.x = 0;
       blockDim.x = 32;
       gridDim.x = 1;
-      sfb::lz_resolve_kernel(a);
+      if (std::getenv("SFB_EMU_LZ_V1")) sfb::lz_resolve_kernel(a);  // (the first-generation kernel, kept for A/B)
+      else sfb::lz_window_kernel(a);
     });
   for (auto& t : lanes) t.join();
   emu_warp = nullptr;

@@ -413,4 +413,28 @@ def crafted_lz_streams():
             total += 3 if i % 3 else 4
         blk.eob()
         out.append((f"threes_lead{lead}", w.tobytes(), total))
+    # RUNS: back-to-back maximum-length matches with one distance (what a compressor makes of a long
+    # repeat), a shorter last one, then another run with another distance right behind — the resolve
+    # pass merges such runs and fills them 16 bytes per lane; every kind of period, every phase
+    for lead in (0, 1, 7, 15, 16, 17, 100, 1000, 1023, 1024, 1025):
+        for dist, nmax, last in ((1, 3, 100), (1, 40, 0), (2, 5, 3), (3, 4, 257), (4, 2, 50), (5, 3, 0), (8, 33, 258),
+                                 (15, 2, 9), (16, 6, 77), (17, 3, 30), (31, 2, 0), (258, 3, 11), (300, 4, 100),
+                                 (511, 2, 3), (512, 5, 200), (513, 35, 17), (4000, 3, 0)):
+            w = BitWriter()
+            blk = fixed_block(w, True)
+            n = max(lead, dist)
+            for b in rng.integers(32, 127, n):
+                blk.literal(int(b))
+            total = n
+            for d2, k, l2 in ((dist, nmax, last), (max(1, dist // 2), 2, 5)):
+                for r in range(k):
+                    blk.match(258, d2)
+                    total += 258
+                if l2 >= 3:
+                    blk.match(l2, d2)
+                    total += l2
+            blk.literal(65)
+            total += 1
+            blk.eob()
+            out.append((f"run_lead{lead}_d{dist}x{nmax}", w.tobytes(), total))
     return out

@@ -22,7 +22,7 @@ def build(root_lit=8, root_dist=6, pool=96) -> str:
     srcs = [os.path.join(emu, "emu.cpp"), os.path.join(emu, "emu_lz.cpp"), os.path.join(emu, "emu_stream.cpp"),
             os.path.join(emu, "cuda_shim.h"), os.path.join(emu, "cuda_shim_warp.h"),
             os.path.join(csrc, "deflate_lane.cuh"), os.path.join(csrc, "huff_lanes.cuh"),
-            os.path.join(csrc, "lz_warp.cuh"), os.path.join(csrc, "huff_stream.cuh"),
+            os.path.join(csrc, "lz_warp.cuh"), os.path.join(csrc, "lz_window.cuh"), os.path.join(csrc, "huff_stream.cuh"),
             os.path.join(csrc, "block_finder.cuh"), os.path.join(csrc, "container.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         subprocess.check_call(["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-pthread",

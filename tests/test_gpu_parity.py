@@ -143,7 +143,7 @@ def test_host_batch_larger_than_the_staging_budget(oracle, monkeypatch):
     try:
         rng = np.random.default_rng(5)
         streams, caps = [], []
-        for i in range(700):
+        for i in range(800):
             kind = ["dynamic", "fixed", "stored", "multiblock", "repetitive"][i % 5]
             plain, comp = T.make_stream(kind, int(rng.integers(20000, 70000)), 12000 + i)
             if i % 13 == 0:
