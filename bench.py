@@ -470,7 +470,7 @@ def main():
         achieved = algo_bytes / (k_ms * 1e-3) / 1e9
         single = n == 1
         k1 = "find/verify candidates + huff_stream_kernel x2 + chain (pass 1)" if single else "huff_lanes_kernel (pass 1)"
-        k2 = "lz_jump_* (pass 2)" if single else "lz_resolve_kernel (pass 2)"
+        k2 = "lz_jump_* (pass 2)" if single else "lz_window_kernel (pass 2)"
         res = {
             "value": value, "ms_per_step": ms_per_step, "steps": steps,
             "workload": w["desc"], "streams_per_gpu": n, "compressed_bytes_per_gpu": w["total_in"],

@@ -193,7 +193,7 @@ typedef struct sfb200_launch_info {
   /* pass 1 in single-stream mode, huff_stream_kernel (one warp per stream; few, large streams) */
   int stream_ctas_per_sm;
   int stream_regs_per_thread;
-  /* pass 2, lz_resolve_kernel (one warp per stream) */
+  /* pass 2, lz_window_kernel (one warp per stream) */
   int lz_threads_per_cta;
   int lz_ctas_per_sm;
   int lz_regs_per_thread;
@@ -206,7 +206,7 @@ int sfb200_get_launch_info(sfb200_ctx* ctx, sfb200_launch_info* out);
  *   out3[0] scratch clearing and batch preparation,
  *   out3[1] pass 1, the Huffman layer (huff_lanes_kernel; one stream or a few large ones:
  *           find / verify candidates, huff_stream_kernel counting and writing, the chain),
- *   out3[2] pass 2, the LZ77 back-references (lz_resolve_kernel; single-stream route: lz_jump_*).
+ *   out3[2] pass 2, the LZ77 back-references (lz_window_kernel; single-stream route: lz_jump_*).
  * With more than two waves of streams the passes overlap: out3[1] then runs to the end of the last
  * wave of pass 1 and out3[2] is what remains of pass 2 after that. */
 int sfb200_last_pass_ms(sfb200_ctx* ctx, float* out3);

@@ -62,6 +62,8 @@ struct sfb200_ctx {
   int regs_per_thread = 0;
   int lz_ctas_per_sm = 0;
   int lz_regs_per_thread = 0;
+  int lzw_minb = 6;            // lz_window_kernel instantiation (register budget for 4 / 5 / 6 CTAs per SM;
+                               // measured: 6 is best on C3, within 2 % of 5 on C2 and C4 — SFB200_LZW_CTAS)
   bool lz_v1 = false;          // SFB200_LZ_V1=1: the first-generation pass 2 (lz_warp.cuh), kept for A/B runs
   int small_ctas_per_sm = 0;   // SmallCfg pass 1 (0: not usable)
   int small_regs_per_thread = 0;
@@ -204,8 +206,15 @@ int sfb200_create(int device, sfb200_ctx** out)
     if (const char* e = std::getenv("SFB200_LZ_V1")) ctx->lz_v1 = e[0] == '1';
     static_assert(sfb::LZ_THREADS == sfb::LZW_THREADS, "one launch geometry for both pass-2 kernels");
     int lz_per_sm = 0;
+    if (const char* e = std::getenv("SFB200_LZW_CTAS")) {
+      const int v = std::atoi(e);
+      if (v == 4 || v == 5 || v == 6) ctx->lzw_minb = v;
+    }
+    const void* lzw = ctx->lzw_minb == 4   ? reinterpret_cast<const void*>(sfb::lz_window_kernel<4>)
+                      : ctx->lzw_minb == 5 ? reinterpret_cast<const void*>(sfb::lz_window_kernel<5>)
+                                           : reinterpret_cast<const void*>(sfb::lz_window_kernel<6>);
     if ((ctx->lz_v1 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lz_per_sm, sfb::lz_resolve_kernel, sfb::LZ_THREADS, 0)
-                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lz_per_sm, sfb::lz_window_kernel, sfb::LZW_THREADS, 0)) !=
+                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lz_per_sm, lzw, sfb::LZW_THREADS, 0)) !=
             cudaSuccess ||
         lz_per_sm < 1)
       return bail(SFB200_RC_CUDA_ERROR);
@@ -214,8 +223,7 @@ int sfb200_create(int device, sfb200_ctx** out)
     if (const char* e = std::getenv("SFB200_LZ_CTAS_PER_SM")) cap = std::atoi(e);
     ctx->lz_ctas_per_sm = (cap > 0 && cap < lz_per_sm) ? cap : lz_per_sm;
     cudaFuncAttributes lfa;
-    if ((ctx->lz_v1 ? cudaFuncGetAttributes(&lfa, sfb::lz_resolve_kernel)
-                    : cudaFuncGetAttributes(&lfa, sfb::lz_window_kernel)) == cudaSuccess)
+    if ((ctx->lz_v1 ? cudaFuncGetAttributes(&lfa, sfb::lz_resolve_kernel) : cudaFuncGetAttributes(&lfa, lzw)) == cudaSuccess)
       ctx->lz_regs_per_thread = lfa.numRegs;
   }
   if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_counter), (kCountersPerWave * kMaxWaves + 8) * sizeof(unsigned long long)) !=
@@ -722,12 +730,14 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
       ctx->launches += (sfb::JUMP_MAX_ROUNDS + 1) * cnt * stripes;
     } else {
       constexpr uint64_t wpc = sfb::LZ_THREADS / 32;
-      const uint64_t want = (cnt + wpc - 1) / wpc;
       const uint64_t resident =
           static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->lz_ctas_per_sm);
+      const uint64_t want = (cnt + wpc - 1) / wpc;
       const unsigned grid = static_cast<unsigned>(want < resident ? want : resident);
       if (ctx->lz_v1) sfb::lz_resolve_kernel<<<grid, sfb::LZ_THREADS, 0, s2>>>(r);
-      else sfb::lz_window_kernel<<<grid, sfb::LZW_THREADS, 0, s2>>>(r);
+      else if (ctx->lzw_minb == 4) sfb::lz_window_kernel<4><<<grid, sfb::LZW_THREADS, 0, s2>>>(r);
+      else if (ctx->lzw_minb == 5) sfb::lz_window_kernel<5><<<grid, sfb::LZW_THREADS, 0, s2>>>(r);
+      else sfb::lz_window_kernel<6><<<grid, sfb::LZW_THREADS, 0, s2>>>(r);
       SFB_TRY(ctx, cudaGetLastError());
     }
     ctx->launches += 1;

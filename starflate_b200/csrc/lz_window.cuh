@@ -251,23 +251,29 @@ __device__ __forceinline__ void lzw_chunk(const LzwView& v, uint32_t P, uint32_t
   }
   if (!bytewise) {
     // ---- segment mode: one unaligned word per segment ------------------------------------------
+    // (all loads of a round are issued before the first one is used: one memory latency per round)
     bool pendA = nA != 0u, pendB = hasB;
     const uint32_t fA = wp - A_d, lastA = fA + nA - 1u;
     const uint32_t fB = wp + s - B_d, lastB = wp + 3u - B_d;
     const uint32_t mA = 0xffffffffu >> ((32u - 8u * nA) & 31u);  // (nA >= 1 where it is used)
-    const uint32_t mB = 0xffffffffu << ((8u * s) & 31u);         // (s < 4 where it is used)
+    const uint32_t shB = (8u * s) & 31u;                         // (s < 4 where it is used)
+    const uint32_t mB = 0xffffffffu << shB;
+    const uint8_t* const pA = base + (fA & ~3u);
+    const uint8_t* const pB = base + (fB & ~3u);
+    const uint32_t rA = fA & 3u, rB = fB & 3u;
+    const bool hiA = rA + nA > 4u, hiB = rB + 4u - s > 4u;       // the segment reaches into a second word
+    uint32_t* const out = reinterpret_cast<uint32_t*>(base + wp);
     uint32_t res = cw;
     const bool dep = (pendA && lastA >= P) || (pendB && lastB >= P);
     if (!__any_sync(FULL, dep)) {  // every source lies before the chunk: one shot
-      if (pendA) {
-        const uint32_t g = lzw_gather(base, fA, nA);
-        res = (res & ~mA) | (g & mA);
-      }
-      if (pendB) {
-        const uint32_t g = lzw_gather(base, fB, 4u - s) << ((8u * s) & 31u);
-        res = (res & ~mB) | (g & mB);
-      }
-      if (pendA | pendB) *reinterpret_cast<uint32_t*>(base + wp) = res;
+      const uint32_t a0 = pendA ? *reinterpret_cast<const uint32_t*>(pA) : 0u;
+      const uint32_t a1 = (pendA && hiA) ? *reinterpret_cast<const uint32_t*>(pA + 4) : 0u;
+      const uint32_t b0 = pendB ? *reinterpret_cast<const uint32_t*>(pB) : 0u;
+      const uint32_t b1 = (pendB && hiB) ? *reinterpret_cast<const uint32_t*>(pB + 4) : 0u;
+      const uint32_t gA = lz_funnel(a0, a1, 8u * rA), gB = lz_funnel(b0, b1, 8u * rB) << shB;
+      if (pendA) res = (res & ~mA) | (gA & mA);
+      if (pendB) res = (res & ~mB) | (gB & mB);
+      if (pendA | pendB) *out = res;
       __syncwarp();
       return;
     }
@@ -278,17 +284,16 @@ __device__ __forceinline__ void lzw_chunk(const LzwView& v, uint32_t P, uint32_t
       if (bal == 0) break;
       const uint32_t F = __shfl_sync(FULL, first, __ffs(static_cast<int>(bal)) - 1);
       const bool doA = pendA && lastA < F, doB = pendB && lastB < F;
-      if (doA) {
-        const uint32_t g = lzw_gather(base, fA, nA);
-        res = (res & ~mA) | (g & mA);
-        pendA = false;
-      }
-      if (doB) {
-        const uint32_t g = lzw_gather(base, fB, 4u - s) << ((8u * s) & 31u);
-        res = (res & ~mB) | (g & mB);
-        pendB = false;
-      }
-      if (doA | doB) *reinterpret_cast<uint32_t*>(base + wp) = res;
+      const uint32_t a0 = doA ? *reinterpret_cast<const uint32_t*>(pA) : 0u;
+      const uint32_t a1 = (doA && hiA) ? *reinterpret_cast<const uint32_t*>(pA + 4) : 0u;
+      const uint32_t b0 = doB ? *reinterpret_cast<const uint32_t*>(pB) : 0u;
+      const uint32_t b1 = (doB && hiB) ? *reinterpret_cast<const uint32_t*>(pB + 4) : 0u;
+      const uint32_t gA = lz_funnel(a0, a1, 8u * rA), gB = lz_funnel(b0, b1, 8u * rB) << shB;
+      if (doA) res = (res & ~mA) | (gA & mA);
+      if (doB) res = (res & ~mB) | (gB & mB);
+      pendA = pendA && !doA;
+      pendB = pendB && !doB;
+      if (doA | doB) *out = res;
       __syncwarp();
     }
     return;
@@ -344,7 +349,9 @@ __device__ __forceinline__ uint32_t lzw_window_bits(const LzwView& v, uint32_t W
   return w;
 }
 
-__global__ void __launch_bounds__(LZW_THREADS, 5) lz_window_kernel(const ResolveArgs a)
+// MINB: resident CTAs per SM the register allocation aims at (capi.cu picks the instantiation)
+template <int MINB>
+__global__ void __launch_bounds__(LZW_THREADS, MINB) lz_window_kernel(const ResolveArgs a)
 {
   constexpr unsigned FULL = 0xffffffffu;
   const uint32_t lane = threadIdx.x & 31u;
@@ -366,7 +373,8 @@ __global__ void __launch_bounds__(LZW_THREADS, 5) lz_window_kernel(const Resolve
     const uint32_t end = v.end;
     uint32_t cur = v.q;                        // every byte below cur is final (dense mode: see c_*)
     uint32_t c_o = 0, c_end = 0, c_d = 1;      // dense mode: the most recent match, may reach past cur
-    uint32_t pre_P = LZW_NONE, pre_w = 0;      // a chunk word loaded ahead (valid while nothing was written there)
+    uint32_t pre_P = LZW_NONE, pre_w = 0, pre_w1 = 0;  // the words of chunks pre_P and pre_P + 128, loaded ahead
+                                                       // (valid while nothing was written there)
     uint32_t W = 0;
     uint32_t wbits = lzw_window_bits(v, 0);
     while (W < end) {
@@ -436,7 +444,10 @@ __global__ void __launch_bounds__(LZW_THREADS, 5) lz_window_kernel(const Resolve
         continue;
       }
       // ---- dense window: 128-byte chunks --------------------------------------------------------
-      if (W + 1024u < end) lzw_prefetch(v.base + W + 1024u + 32u * lane);
+      // (chunk words are loaded TWO chunks ahead and the next window's bitmap word one window ahead:
+      //  a chunk's own loads never wait for memory; chunk P only writes inside [P, P + 128))
+      const uint32_t nwb = lzw_window_bits(v, W + 1024u);
+      if (W + 2048u < end) lzw_prefetch(v.base + W + 2048u + 32u * lane);
       {
         uint32_t P = cur & ~127u;
         const uint32_t lo = cur;  // (bytes below are final or not ours)
@@ -444,27 +455,36 @@ __global__ void __launch_bounds__(LZW_THREADS, 5) lz_window_kernel(const Resolve
           const uint32_t wp = PP + 4u * lane;
           return (wp + 4u > v.q && wp < end) ? lzw_ldw(v.base, wp) : 0u;
         };
-        uint32_t cw = pre_P == P ? pre_w : load_w(P);
+        uint32_t cw, ncw;
+        if (pre_P == P) {
+          cw = pre_w;
+          ncw = pre_w1;
+        } else {
+          cw = load_w(P);
+          ncw = load_w(P + 128u);
+        }
         bool stopped = false;
         for (; P < wend; P += 128u) {
           if (c_end >= P + 128u && c_end > cur && P >= lo) {  // the carried match covers the whole chunk: fill it
             stopped = true;
             break;
           }
-          const uint32_t ncw = load_w(P + 128u);
+          const uint32_t nncw = load_w(P + 256u);
           const uint32_t mw = __shfl_sync(FULL, wbits, static_cast<int>(((P - W) >> 5) + (lane >> 3)));
           const uint32_t hb4 = (mw >> (4u * (lane & 7u))) & 15u;
           if (P >= lo && P + 128u <= end) lzw_chunk<false>(v, P, lo, end, cw, ncw, hb4, c_o, c_end, c_d);
           else lzw_chunk<true>(v, P, lo, end, cw, ncw, hb4, c_o, c_end, c_d);
           cw = ncw;
+          ncw = nncw;
           cur = P + 128u < end ? P + 128u : end;
         }
         pre_P = P;
         pre_w = cw;
+        pre_w1 = ncw;
         if (stopped) continue;  // (the fill branch above takes it from here)
       }
       W += 1024u;
-      if (W < end) wbits = lzw_window_bits(v, W);
+      wbits = nwb;
     }
   }
 }

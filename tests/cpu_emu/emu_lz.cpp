@@ -35,7 +35,7 @@ extern "C" void emu_lz_resolve(uint8_t* dst_base, const uint64_t* dst_off, const
       blockDim.x = 32;
       gridDim.x = 1;
       if (std::getenv("SFB_EMU_LZ_V1")) sfb::lz_resolve_kernel(a);  // (the first-generation kernel, kept for A/B)
-      else sfb::lz_window_kernel(a);
+      else sfb::lz_window_kernel<5>(a);
     });
   for (auto& t : lanes) t.join();
   emu_warp = nullptr;

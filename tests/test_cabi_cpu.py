@@ -67,7 +67,7 @@ def test_kernels_are_sm100a_sass(lib_path):
     assert "sm_100a" in out
     sass = subprocess.run([cuobjdump, "-sass", lib_path], capture_output=True, text=True).stdout
     assert re.search(r"Function : \S*huff_lanes_kernel", sass)
-    assert re.search(r"Function : \S*lz_resolve_kernel", sass)
+    assert re.search(r"Function : \S*lz_window_kernel", sass)
     for name in ("huff_stream_kernel", "find_candidates_kernel", "verify_candidates_kernel", "chain_kernel",
                  "lz_jump_init_kernel", "lz_jump_round_kernel"):  # the single-stream route
         assert re.search(r"Function : \S*" + name, sass), name

@@ -5,8 +5,8 @@ mkdir -p gpurun_out
 TAG=${1:-x}
 VARIANTS=${2:-"v2:;v1:SFB200_LZ_V1=1"}
 WL=${3:-c2,c4,c3}
-python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_$TAG.log 2>&1; echo "pytest rc=$?"
-tail -5 gpurun_out/r02_pytest_$TAG.log
+if [ -z "$SKIP_TESTS" ]; then python -m pytest tests -m gpu -x -q > gpurun_out/r02_pytest_$TAG.log 2>&1; echo "pytest rc=$?"; fi
+[ -z "$SKIP_TESTS" ] && tail -5 gpurun_out/r02_pytest_$TAG.log
 python tools/ab_bench.py --workloads $WL --variants "$VARIANTS" --steps 5 --unique 2048 --out gpurun_out/r02_ab_$TAG.jsonl 2> gpurun_out/r02_ab_$TAG.err | python -c "
 import sys, json
 for l in sys.stdin:
