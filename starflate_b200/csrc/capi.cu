@@ -64,6 +64,7 @@ struct sfb200_ctx {
   int lz_regs_per_thread = 0;
   int lzw_minb = 6;            // lz_window_kernel instantiation (register budget for 4 / 5 / 6 CTAs per SM;
                                // measured: 6 is best on C3, within 2 % of 5 on C2 and C4 — SFB200_LZW_CTAS)
+  uint32_t no_pair = 0;        // SFB200_NO_PAIR=1: pass 1 takes one token per iteration (A/B runs)
   bool lz_v1 = false;          // SFB200_LZ_V1=1: the first-generation pass 2 (lz_warp.cuh), kept for A/B runs
   int small_ctas_per_sm = 0;   // SmallCfg pass 1 (0: not usable)
   int small_regs_per_thread = 0;
@@ -204,6 +205,7 @@ int sfb200_create(int device, sfb200_ctx** out)
   if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess) ctx->regs_per_thread = fa.numRegs;
   {
     if (const char* e = std::getenv("SFB200_LZ_V1")) ctx->lz_v1 = e[0] == '1';
+    if (const char* e = std::getenv("SFB200_NO_PAIR")) ctx->no_pair = e[0] == '1';
     static_assert(sfb::LZ_THREADS == sfb::LZW_THREADS, "one launch geometry for both pass-2 kernels");
     int lz_per_sm = 0;
     if (const char* e = std::getenv("SFB200_LZW_CTAS")) {
@@ -544,6 +546,7 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
     a.defer_count = nullptr;
     a.todo_list = order;
     a.todo_count = nullptr;
+    a.no_pair = ctx->no_pair;
     const uint64_t groups = (cnt + 31) / 32;
     if (stream_mode) {
       sfb::StreamArgs sa;
@@ -784,6 +787,7 @@ int sfb200_decompressed_size_batch_device(sfb200_ctx* ctx, const uint8_t* src_ba
   a.defer_count = nullptr;
   a.todo_list = nullptr;
   a.todo_count = nullptr;
+  a.no_pair = ctx->no_pair;
   auto kern = sfb::huff_lanes_kernel<LaneCfg, true>;
   if (!ctx->count_configured) {  // (function attributes are per device)
     SFB_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LaneCfg::SMEM_BYTES));

@@ -66,6 +66,7 @@ struct BatchArgs {
   unsigned long long* defer_count;          // out: how many
   const uint32_t* todo_list;                // in: the streams to do, in this order (null: idx_base + 0 .. n)
   const unsigned long long* todo_count;     // in: how many of them (null: n)
+  uint32_t no_pair;                         // A/B switch (SFB200_NO_PAIR=1): one token per iteration, as before
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -97,7 +98,8 @@ struct Cfg {
 // LUT entry (u16).  bits 0-3 = code length L (1..15); L == 0 marks a special entry.
 //   L != 0, literal/length table: bits 4-11 = literal byte, or (length base - 3) with
 //           bit 15 set and bits 12-14 = number of extra bits (literals keep bits 12-15 clear)
-//   L != 0, distance table: bits 4-8 = distance symbol (0..29)
+//   L != 0, distance table: bits 4-8 = distance symbol (0..29), bits 9-12 = its number of extra
+//           bits (so that the bit count of a token does not wait for the base/extra table)
 //   L == 0: 0x0000 no code here;
 //           bit 15 set: sub-table pointer, bits 4-11 offset from the pool start,
 //                       bits 12-14 sub-table index bits (1..7);
@@ -588,7 +590,7 @@ __device__ __forceinline__ uint32_t long_decode(const LongTab<ROOT>& t, uint32_t
 template <bool LITLEN>
 __device__ __forceinline__ uint16_t make_entry(uint32_t s, uint32_t L)
 {
-  if (!LITLEN) return static_cast<uint16_t>(s < 30 ? ((s << 4) | L) : E_SLOW);
+  if (!LITLEN) return static_cast<uint16_t>(s < 30 ? (((c_dist_info[s] >> 16) << 9) | (s << 4) | L) : E_SLOW);
   if (s < 256) return static_cast<uint16_t>((s << 4) | L);
   if (s == 256 || s > 285) return static_cast<uint16_t>(E_SLOW);
   const uint32_t info = c_len_info[s - 257];

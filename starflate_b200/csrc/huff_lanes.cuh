@@ -98,12 +98,15 @@ struct TokWin {
     atomicOr(reinterpret_cast<uint32_t*>(p - (sh >> 3)), bits8 << sh);
   }
 
-  // The one output step of a token: append the n (0..3) low bytes of `chunk` at the cursor —
+  // The one output step of a token: append the n (0..4) low bytes of `chunk` at the cursor —
   // the descriptor of a match iff `is_head` — then move the cursor `skipn` bytes further over
   // bytes pass 2 will produce (the body of a match).  A word the cursor leaves is stored whole:
   // its bytes past the appended ones all belong to the match body, so any value will do there;
   // its head bits go to the bitmap byte of that word.  No branches: predicated stores.
-  __device__ __forceinline__ void emit(uint32_t chunk, uint32_t n, uint32_t skipn, bool is_head)
+  // `hoff` (0 or 1): the descriptor starts that many bytes into the chunk — a literal paired with
+  // the match that follows it (n <= 4 then; the caller keeps k + hoff <= 7, so the head bit stays
+  // in this word).
+  __device__ __forceinline__ void emit(uint32_t chunk, uint32_t n, uint32_t skipn, bool is_head, uint32_t hoff = 0u)
   {
 #ifdef SFB_TRACE_EMIT
     SFB_TRACE_EMIT(vpos, chunk, n, skipn, obuf);
@@ -111,7 +114,7 @@ struct TokWin {
     const uint32_t k = vpos & 7u;
     const uint32_t sh = 8u * k;
     const uint64_t merged = obuf | (static_cast<uint64_t>(chunk) << sh);  // chunk < 2^(8n)
-    const uint32_t hb = fb | (is_head ? 1u << k : 0u);
+    const uint32_t hb = fb | (is_head ? 1u << (k + hoff) : 0u);
     const uint32_t np = vpos + n + skipn;
     const uint32_t wv = vpos & ~7u;
     const uint32_t nw = np & ~7u;
@@ -187,7 +190,7 @@ struct CountWin {
   }
   __device__ __forceinline__ uint32_t written() const { return vpos; }
   __device__ __forceinline__ uint32_t room() const { return vend - vpos; }
-  __device__ __forceinline__ void emit(uint32_t, uint32_t n, uint32_t skipn, bool) { vpos += n + skipn; }
+  __device__ __forceinline__ void emit(uint32_t, uint32_t n, uint32_t skipn, bool, uint32_t = 0u) { vpos += n + skipn; }
   __device__ __forceinline__ void spill_pending() const {}
   __device__ __forceinline__ void jump(uint32_t n) { vpos += n; }
   __device__ __forceinline__ void flush_tail() const {}
@@ -250,6 +253,7 @@ huff_lanes_kernel(const BatchArgs a)
   // the streams of this launch: all n, or the ones an earlier launch handed on
   const uint64_t n_todo = a.todo_count ? static_cast<uint64_t>(*a.todo_count) : a.n;
   const uint64_t n_groups = (n_todo + 31) / 32;
+  const bool pair_on = a.no_pair == 0;
   // per-lane table state that outlives a stream (see parse_block_header)
   bool tables_fixed = false;
   LongTab<C::ROOT_LIT> lt_lit;     // canonical first/count of the codes longer than the LUT roots
@@ -358,7 +362,7 @@ huff_lanes_kernel(const BatchArgs a)
       // software pipeline: the output step of a token is deferred to the start of the next
       // iteration, where it is independent of everything around it and fills the latency of
       // the decode chain (window -> LUT -> length -> window)
-      uint32_t p_chunk = 0, p_n = 0, p_skip = 0;
+      uint32_t p_chunk = 0, p_n = 0, p_skip = 0, p_hoff = 0;
       bool p_mt = false;
       while (__any_sync(FULL, state == S_DECODE)) {
         // ---- decode one token.  Straight-line and nearly branch-free (results are only used by
@@ -367,25 +371,39 @@ huff_lanes_kernel(const BatchArgs a)
         bool dec = state == S_DECODE;
         SFB_STAT(tokens);
         const uint32_t bo0 = br.bo;   // < 32
-        // while no window word reaches past the end of the stream every bit the token can see
-        // is real (a token is <= 48 of the >= 65 window bits); otherwise go the exact way
+        // while no window word reaches past the end of the stream every bit the iteration can see
+        // is real (a literal of <= ROOT_LIT bits and a token of <= 48 are at most 56 of the >= 65
+        // window bits); otherwise go the exact way
         const bool tail = br.tail();
         uint32_t n0, n1;
         br.next2(n0, n1);
-        const uint32_t bits = br.peek();
-        const uint32_t bits_hi = funnel_r(br.w1, br.w2, bo0);
+        // ---- a literal in front: when the next symbol is a literal whose code fits the LUT root
+        //      (text: nearly every literal) it is taken together with the token behind it — one
+        //      more root look-up on the chain, ~1.4 tokens per iteration on text.  Everything that
+        //      can go wrong with the token behind it (exact path, distance / room checks) is not
+        //      handled here: that token is then left for the next iteration, where it comes first.
+        const uint32_t bits0 = br.peek();
+        const uint32_t bits_hi = funnel_r(br.w1, br.w2, bo0);   // window bits [32, 64) from the token start
+        const uint32_t e1 = lds16(lutb + (C::LIT_OFF * 64) + ((bits0 << 6) & (((1u << C::ROOT_LIT) - 1u) << 6)));
+        ow.emit(p_chunk, p_n, p_skip, p_mt, p_hoff);   // (the previous iteration's output step)
+        const bool pre1 = dec & !tail & (ow.room() != 0u) & ((ow.vpos & 7u) != 7u) & pair_on;
+        // a literal entry has bits 12-15 clear and its code length (1 .. ROOT_LIT) in bits 0-3
+        const uint32_t t1 = e1 & 0xf00fu;
+        const bool lit1 = pre1 & (t1 - 1u < 15u);
+        const uint32_t off = lit1 ? t1 : 0u;
+        const uint32_t bo1 = bo0 + off;   // < 32 + ROOT_LIT
+        const uint32_t bits = funnel_r(bits0, bits_hi, off);
         const uint32_t e = lut_lookup_s<C::ROOT_LIT, C::LIT_OFF, C::POOL_OFF, C::POOL>(lutb, bits);
-        ow.emit(p_chunk, p_n, p_skip, p_mt);   // (the previous token's output step)
         const uint32_t L = e & 15u;
         const uint32_t xb = (e >> 12) & 7u;               // 0 for literals
         bool is_match = (e & 0x8000u) != 0;               // (pointers were resolved: L != 0 then)
         uint32_t value = ((e >> 4) & 0xffu) + ((bits >> L) & ~(0xffffffffu << xb)) + (is_match ? 3u : 0u);
         const uint32_t used1 = L + xb;
-        const uint32_t dbits = br.peek_at(bo0 + used1);   // bo0 + used1 <= 31 + 20
+        const uint32_t dbits = br.peek_at(bo1 + used1);   // bo1 + used1 <= 31 + 8 + 20
         const uint32_t de = lut_lookup_s<C::ROOT_DIST, C::DIST_OFF, C::POOL_OFF, C::POOL>(lutb, dbits);
         const uint32_t dL = de & 15u;
         const uint32_t dinfo = lds32(sdi + ((de >> 2) & 0x7cu));
-        const uint32_t dxb = dinfo >> 16;
+        const uint32_t dxb = (de >> 9) & 15u;
         uint32_t dist = (dinfo & 0xffffu) + ((dbits >> dL) & ~(0xffffffffu << dxb));
         uint32_t used = used1 + (is_match ? dL + dxb : 0u);
         // anything that is not a plain literal / length+distance — end of block included — is
@@ -393,7 +411,8 @@ huff_lanes_kernel(const BatchArgs a)
         // (near the end of the input the token must also fit into the real bits that are left)
         // (the last few tokens of a stream — `tail` — all go the exact way, whether they fit or not:
         //  cheaper than asking every token of the stream whether it fits)
-        if (dec & ((L == 0) | (is_match & (dL == 0)) | tail)) {
+        const bool odd = (L == 0) | (is_match & (dL == 0));
+        if (dec & !lit1 & (odd | tail)) {
           const int32_t left32 = static_cast<int32_t>(br.ebits - 32u * br.rp - bo0);
           // (a) a valid code longer than the tables hold: canonical decode in registers
           bool done = false;
@@ -466,27 +485,33 @@ huff_lanes_kernel(const BatchArgs a)
             }
           }
         }
-        if (dec) br.skip(used);
-        br.norm2(n0, n1);
-        if (it & 1u) br.stage_step();
-        ++it;
         // ---- act on the token ----------------------------------------------------------------
         // (src/decompress.cpp:178-183 distance then room for a match, :150-152 room for a
         //  literal; nothing of a token that fails is written)
-        const bool bad_dist = is_match & (dist > ow.written());
-        if (dec & (bad_dist | (ow.room() < (is_match ? value : 1u)))) {
+        const uint32_t lit1n = lit1 ? 1u : 0u;
+        const bool drop2 = lit1 & odd;   // the token behind the literal waits for its own iteration
+        if (dec) br.skip(off + (drop2 ? 0u : used));
+        const bool bad_dist = is_match & (dist > ow.written() + lit1n);
+        bool tok = dec & !drop2;
+        if (tok & (bad_dist | (ow.room() - lit1n < (is_match ? value : 1u)))) {
+          // (a literal in front of the failing token is still written: it came first)
           status = bad_dist ? ST_INVALID_DISTANCE : ST_DST_TOO_SMALL;
           state = S_DONE;
-          dec = false;
+          tok = false;
         }
-        const bool mt = dec & is_match;
+        br.norm2(n0, n1);
+        if (it & 1u) br.stage_step();
+        ++it;
+        const bool mt = tok & is_match;
         const uint32_t desc = (value - 3u) | ((dist - 1u) << 8);
+        const uint32_t chunk2 = tok ? (mt ? desc : value) : 0u;
         p_mt = mt;
-        p_chunk = dec ? (mt ? desc : value) : 0u;
-        p_n = dec ? (mt ? 3u : 1u) : 0u;
+        p_hoff = lit1n;
+        p_chunk = lit1 ? (((e1 >> 4) & 0xffu) | (chunk2 << 8)) : chunk2;
+        p_n = (tok ? (mt ? 3u : 1u) : 0u) + lit1n;
         p_skip = mt ? value - 3u : 0u;
       }
-      ow.emit(p_chunk, p_n, p_skip, p_mt);  // drain the pipeline
+      ow.emit(p_chunk, p_n, p_skip, p_mt, p_hoff);  // drain the pipeline
       if (state == S_DONE && live) {
         ow.flush_tail();
         a.status[idx] = static_cast<uint8_t>(status);
