@@ -101,6 +101,8 @@ def make_workload(name: str, n_streams: int, unique: int, rank: int, container: 
         kind, size = "dynamic", 65536
     elif name == "c3":
         kind, size = "mixed", 4096
+    elif name in ("c3s", "c3f", "c3d"):   # diagnostics (tools/ab_bench.py): the three page types of C3, one at a time
+        kind, size = {"s": "stored", "f": "fixed", "d": "dynamic"}[name[2]], 4096
     elif name == "c4":
         kind, size = "repetitive", 1 << 20
     elif name == "c1":     # one ~1 MiB text stream (the reference's own CPU-runnable case)

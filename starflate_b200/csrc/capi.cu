@@ -5,6 +5,7 @@
 #include "huff_lanes.cuh"
 #include "huff_stream.cuh"
 #include "lz_warp.cuh"
+#include "stored_copy.cuh"
 #include "lz_window.cuh"
 #include "lz_jump.cuh"
 #include "container.cuh"
@@ -64,6 +65,7 @@ struct sfb200_ctx {
   int lz_regs_per_thread = 0;
   int lzw_minb = 6;            // lz_window_kernel instantiation (register budget for 4 / 5 / 6 CTAs per SM;
                                // measured: 6 is best on C3, within 2 % of 5 on C2 and C4 — SFB200_LZW_CTAS)
+  bool no_stored = false;      // SFB200_NO_STORED=1: stored streams go through the lane kernel like the others (A/B runs)
   uint32_t no_pair = 0;        // SFB200_NO_PAIR=1: pass 1 takes one token per iteration (A/B runs)
   bool lz_v1 = false;          // SFB200_LZ_V1=1: the first-generation pass 2 (lz_warp.cuh), kept for A/B runs
   int small_ctas_per_sm = 0;   // SmallCfg pass 1 (0: not usable)
@@ -72,7 +74,8 @@ struct sfb200_ctx {
   int stream_regs_per_thread = 0;
   uint32_t* d_defer = nullptr;  // streams handed from the small to the large geometry
   uint64_t d_defer_n = 0;
-  uint32_t* d_order = nullptr;  // processing order (streams sorted by first block type)
+  uint32_t* d_order = nullptr;  // processing order (streams sorted by first block type); behind its d_order_n
+                                // entries: one byte per stream, "stored_streams_kernel finished it"
   uint64_t d_order_n = 0;
   unsigned long long* d_counter = nullptr;  // 2 * kMaxWaves work counters
   uint32_t* d_lens = nullptr;  // per-resident-lane code-length scratch
@@ -206,6 +209,7 @@ int sfb200_create(int device, sfb200_ctx** out)
   {
     if (const char* e = std::getenv("SFB200_LZ_V1")) ctx->lz_v1 = e[0] == '1';
     if (const char* e = std::getenv("SFB200_NO_PAIR")) ctx->no_pair = e[0] == '1';
+    if (const char* e = std::getenv("SFB200_NO_STORED")) ctx->no_stored = e[0] == '1';
     static_assert(sfb::LZ_THREADS == sfb::LZW_THREADS, "one launch geometry for both pass-2 kernels");
     int lz_per_sm = 0;
     if (const char* e = std::getenv("SFB200_LZW_CTAS")) {
@@ -228,7 +232,7 @@ int sfb200_create(int device, sfb200_ctx** out)
     if ((ctx->lz_v1 ? cudaFuncGetAttributes(&lfa, sfb::lz_resolve_kernel) : cudaFuncGetAttributes(&lfa, lzw)) == cudaSuccess)
       ctx->lz_regs_per_thread = lfa.numRegs;
   }
-  if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_counter), (kCountersPerWave * kMaxWaves + 8) * sizeof(unsigned long long)) !=
+  if (cudaMalloc(reinterpret_cast<void**>(&ctx->d_counter), (kCountersPerWave * kMaxWaves + 16) * sizeof(unsigned long long)) !=
       cudaSuccess)
     return bail(SFB200_RC_OUT_OF_MEMORY);
   {
@@ -487,9 +491,10 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
   SFB_TRY(ctx, cudaEventRecord(ctx->ev[0], st));
   SFB_TRY(ctx, cudaMemsetAsync(ctx->d_counter, 0,
                                kCountersPerWave * std::max<uint64_t>(n_waves, 1) * sizeof(unsigned long long), st));
-  SFB_TRY(ctx, cudaMemsetAsync(ctx->d_counter + kCountersPerWave * kMaxWaves, 0, 8 * sizeof(unsigned long long), st));
+  SFB_TRY(ctx, cudaMemsetAsync(ctx->d_counter + kCountersPerWave * kMaxWaves, 0, 16 * sizeof(unsigned long long), st));
   SFB_TRY(ctx, cudaMemsetAsync(ctx->d_bits, 0, bits_words * sizeof(uint32_t), st));
   // Order the streams by the type of their first block (see lz_warp.cuh: PrepArgs)
+  uint8_t* handled = nullptr;
   bool sorted = n >= 64 && n < 0xffffffffull && !stream_mode;
   if (const char* e = std::getenv("SFB200_NO_SORT"))
     if (e[0] == '1') sorted = false;
@@ -499,7 +504,7 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
       ctx->d_order = nullptr;
       ctx->d_order_n = 0;
       const uint64_t want = n + n / 8 + 64;
-      SFB_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_order), want * sizeof(uint32_t)));
+      SFB_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_order), want * (sizeof(uint32_t) + 1)));
       ctx->d_order_n = want;
     }
     sfb::PrepArgs pa;
@@ -515,6 +520,30 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
     sfb::prep_scatter_kernel<<<grid, sfb::PREP_THREADS, 0, st>>>(pa);
     SFB_TRY(ctx, cudaGetLastError());
     ctx->launches += 2;
+    // Streams of stored blocks: a warp each, wide copies (stored_copy.cuh); the lane kernel skips
+    // what this kernel finished.
+    if (!ctx->no_stored) {
+      handled = reinterpret_cast<uint8_t*>(ctx->d_order + ctx->d_order_n);
+      SFB_TRY(ctx, cudaMemsetAsync(handled, 0, n, st));
+      sfb::StoredArgs sa;
+      sa.src_base = src_base;
+      sa.src_off = src_off;
+      sa.src_len = src_len;
+      sa.dst_base = dst_base + delta;
+      sa.dst_off = dst_off;
+      sa.dst_cap = dst_cap;
+      sa.status = status;
+      sa.written = written;
+      sa.handled = handled;
+      sa.order = ctx->d_order;
+      sa.type_count = pa.type_count;
+      sa.counter = pa.type_count + 8;
+      const uint64_t warps = static_cast<uint64_t>(ctx->sm_count) * 8 * (sfb::STORED_THREADS / 32);
+      const uint64_t want = (std::min<uint64_t>(n, warps) + sfb::STORED_THREADS / 32 - 1) / (sfb::STORED_THREADS / 32);
+      sfb::stored_streams_kernel<<<static_cast<unsigned>(want), sfb::STORED_THREADS, 0, st>>>(sa);
+      SFB_TRY(ctx, cudaGetLastError());
+      ctx->launches += 1;
+    }
   }
   SFB_TRY(ctx, cudaEventRecord(ctx->ev[1], st));
   if (overlap) {
@@ -547,6 +576,7 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
     a.todo_list = order;
     a.todo_count = nullptr;
     a.no_pair = ctx->no_pair;
+    a.handled = handled;
     const uint64_t groups = (cnt + 31) / 32;
     if (stream_mode) {
       sfb::StreamArgs sa;
@@ -788,6 +818,7 @@ int sfb200_decompressed_size_batch_device(sfb200_ctx* ctx, const uint8_t* src_ba
   a.todo_list = nullptr;
   a.todo_count = nullptr;
   a.no_pair = ctx->no_pair;
+  a.handled = nullptr;
   auto kern = sfb::huff_lanes_kernel<LaneCfg, true>;
   if (!ctx->count_configured) {  // (function attributes are per device)
     SFB_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LaneCfg::SMEM_BYTES));
@@ -972,7 +1003,7 @@ int sfb200_decompress_batch_host(sfb200_ctx* ctx, const uint8_t* src, uint64_t s
       ctx->d_order = nullptr;
       ctx->d_order_n = 0;
       const uint64_t want = big_n + big_n / 8 + 64;
-      SFB_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_order), want * sizeof(uint32_t)));
+      SFB_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_order), want * (sizeof(uint32_t) + 1)));
       ctx->d_order_n = want;
     }
   }

@@ -67,6 +67,7 @@ struct BatchArgs {
   const uint32_t* todo_list;                // in: the streams to do, in this order (null: idx_base + 0 .. n)
   const unsigned long long* todo_count;     // in: how many of them (null: n)
   uint32_t no_pair;                         // A/B switch (SFB200_NO_PAIR=1): one token per iteration, as before
+  const uint8_t* handled;                   // in (may be null): 1 = stored_streams_kernel finished this stream already
 };
 
 // ---------------------------------------------------------------------------------------------

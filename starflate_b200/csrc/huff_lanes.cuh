@@ -285,6 +285,7 @@ huff_lanes_kernel(const BatchArgs a)
     uint32_t copy_left = 0;
     bool live = slot < n_todo;
     bool first_header = true;  // nothing of this stream has been decided yet
+    if (live && a.handled != nullptr && a.handled[idx] != 0) live = false;  // (a stream of stored blocks: done already)
     if (live) {
       const uint64_t slen = a.src_len[idx];
       const uint64_t cap = COUNT ? 0xfffffef0ull : a.dst_cap[idx];

@@ -98,6 +98,7 @@ extern "C" int emu_decompress_batch(const uint8_t* src, const uint64_t* src_off,
     a.todo_list = nullptr;
     a.todo_count = nullptr;
     a.no_pair = 0;
+    a.handled = nullptr;
     threadIdx.x = 0;
     blockIdx.x = 0;
     uint32_t handed[1] = {0xffffffffu};

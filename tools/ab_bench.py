@@ -42,7 +42,8 @@ def main():
         variants.append((name, dict(e.split("=", 1) for e in envs.split(",") if e)))
     all_keys = sorted({k for _, e in variants for k in e})
     out = open(args.out, "a") if args.out else None
-    defaults = {"c1": 1, "c2": 65536, "c3": 1048576, "c4": 16384, "c5": 1, "html": 65536}
+    defaults = {"c1": 1, "c2": 65536, "c3": 1048576, "c4": 16384, "c5": 1, "html": 65536,
+                "c3s": 349525, "c3f": 349525, "c3d": 349525}
     for wl in args.workloads.split(","):
         n_streams = args.streams or defaults[wl]
         uniq = {"c4": min(args.unique, 256), "c1": 1, "c5": 1}.get(wl, args.unique)
