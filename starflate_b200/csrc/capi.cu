@@ -40,6 +40,12 @@ namespace {
 // block does not fit is handed to a LaneCfg launch.
 using LaneCfg = sfb::Cfg<SFB_ROOT_LIT, SFB_ROOT_DIST, SFB_POOL, SFB_WARPS, SFB_LANE_CTAS>;
 using SmallCfg = sfb::Cfg<6, 5, 96, 8, 2>;
+// WideCfg (9/6-bit roots, a 256-entry sub-table pool, 1 728 B per lane, ONE CTA of 4 warps per SM) is
+// for batches with no more streams than that has lanes (BASELINE config 4: 16 384 x 1 MiB) — such a
+// batch cannot fill the SMs anyway, and its blocks are the ones whose alphabets overflow the tables
+// of LaneCfg (C4: one 1-bit code for length 258 and 256 literals of 9-10 bits, 15 % of the tokens,
+// which took the canonical long-code path through global scratch one lane at a time).
+using WideCfg = sfb::Cfg<9, 6, 256, 4, 1>;
 // single-stream mode (huff_stream.cuh): one warp per CTA, the large geometry
 // (7/5-bit roots: 18.5 KiB of shared memory per warp, 8 warps per SM instead of 7 — this kernel has one
 //  warp per CTA and is latency-bound too; measured 12 % faster on a 256 MiB stream and 24 % on 1 184 x
@@ -63,12 +69,14 @@ struct sfb200_ctx {
   int regs_per_thread = 0;
   int lz_ctas_per_sm = 0;
   int lz_regs_per_thread = 0;
-  int lzw_minb = 6;            // lz_window_kernel instantiation (register budget for 4 / 5 / 6 CTAs per SM;
-                               // measured: 6 is best on C3, within 2 % of 5 on C2 and C4 — SFB200_LZW_CTAS)
+  int lzw_minb = 5;            // lz_window_kernel instantiation (register budget for 4 / 5 / 6 CTAs per SM;
+                               // measured with the long periodic fill in: 5 (48 registers) beats 6 (40, spills
+                               // in the chunk loop) on C2 8.5 / 8.9 ms and C4 5.0 / 5.5 ms — SFB200_LZW_CTAS)
   bool no_stored = false;      // SFB200_NO_STORED=1: stored streams go through the lane kernel like the others (A/B runs)
   uint32_t no_pair = 0;        // SFB200_NO_PAIR=1: pass 1 takes one token per iteration (A/B runs)
   bool lz_v1 = false;          // SFB200_LZ_V1=1: the first-generation pass 2 (lz_warp.cuh), kept for A/B runs
   int small_ctas_per_sm = 0;   // SmallCfg pass 1 (0: not usable)
+  int wide_ctas_per_sm = 0;    // WideCfg pass 1 (0: not usable; SFB200_NO_WIDE=1 turns it off)
   int small_regs_per_thread = 0;
   int stream_ctas_per_sm = 0;  // huff_stream_kernel (0: not usable)
   int stream_regs_per_thread = 0;
@@ -211,6 +219,7 @@ int sfb200_create(int device, sfb200_ctx** out)
     if (const char* e = std::getenv("SFB200_NO_PAIR")) ctx->no_pair = e[0] == '1';
     if (const char* e = std::getenv("SFB200_NO_STORED")) ctx->no_stored = e[0] == '1';
     static_assert(sfb::LZ_THREADS == sfb::LZW_THREADS, "one launch geometry for both pass-2 kernels");
+    static_assert(LaneCfg::WARPS == WideCfg::WARPS, "the wide launch takes the CTA count computed for the large one");
     int lz_per_sm = 0;
     if (const char* e = std::getenv("SFB200_LZW_CTAS")) {
       const int v = std::atoi(e);
@@ -247,6 +256,21 @@ int sfb200_create(int device, sfb200_ctx** out)
       ctx->small_ctas_per_sm = sp;
     cudaFuncAttributes sfa;
     if (cudaFuncGetAttributes(&sfa, sk) == cudaSuccess) ctx->small_regs_per_thread = sfa.numRegs;
+    cudaGetLastError();
+  }
+  {
+    auto sk = sfb::huff_lanes_kernel<WideCfg>;
+    int sp = 0;
+    bool off = false;
+    if (const char* e = std::getenv("SFB200_NO_WIDE")) off = e[0] == '1';
+    if (!off &&
+        cudaFuncSetAttribute(sk, cudaFuncAttributeMaxDynamicSharedMemorySize, WideCfg::SMEM_BYTES) ==
+            cudaSuccess &&
+        cudaFuncSetAttribute(sk, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sp, sk, WideCfg::WARPS * 32,
+                                                      WideCfg::SMEM_BYTES) == cudaSuccess)
+      ctx->wide_ctas_per_sm = sp;
     cudaGetLastError();
   }
   {
@@ -691,7 +715,13 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
       const uint64_t resident =
           static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->ctas_per_sm);
       const unsigned grid = static_cast<unsigned>(want < resident ? want : resident);
-      sfb::huff_lanes_kernel<LaneCfg><<<grid, LaneCfg::WARPS * 32, LaneCfg::SMEM_BYTES, s1>>>(a);
+      // (a batch that fits the lanes of the wide geometry takes it: see WideCfg)
+      const uint64_t wide_resident =
+          static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->wide_ctas_per_sm);
+      if (!use_small && n_waves == 1 && wide_resident != 0 && want <= wide_resident)
+        sfb::huff_lanes_kernel<WideCfg><<<static_cast<unsigned>(want), WideCfg::WARPS * 32, WideCfg::SMEM_BYTES, s1>>>(a);
+      else
+        sfb::huff_lanes_kernel<LaneCfg><<<grid, LaneCfg::WARPS * 32, LaneCfg::SMEM_BYTES, s1>>>(a);
       SFB_TRY(ctx, cudaGetLastError());
       ctx->launches += 1;
     }

@@ -94,7 +94,7 @@ __device__ __forceinline__ uint32_t lzw_gather(const uint8_t* base, uint32_t f, 
 // matches with the same distance).  All bytes below p0 are final.  Warp-uniform arguments.
 
 // 4 bytes per lane; reads only from the period [p0 - d, p0)
-__device__ __noinline__ void lzw_fill_periodic(const LzwView v, uint32_t p0, uint32_t p1, uint32_t d)
+__device__ __forceinline__ void lzw_fill_periodic(const LzwView v, uint32_t p0, uint32_t p1, uint32_t d)
 {
   uint8_t* const base = v.base;
   uint32_t a = (p0 & ~3u) + 4u * v.lane;
@@ -124,8 +124,54 @@ __device__ __noinline__ void lzw_fill_periodic(const LzwView v, uint32_t p0, uin
   }
 }
 
+// The same for fills of 48 bytes and more (runs): 4 bytes per lane; reads only from the period [p0 - d, p0).
+// A short period (d < 16) is widened first: once the first k d - d bytes exist, the fill is just as
+// periodic with k d >= 16, and a word then rarely straddles the end of the period; a word that does
+// is put together from the end and the start of the period (two gathers) instead of byte by byte.
+__device__ __forceinline__ void lzw_fill_periodic_long(const LzwView v, uint32_t p0, uint32_t p1, uint32_t d)
+{
+  uint8_t* const base = v.base;
+  if (d < 16u) {
+    const uint32_t d2 = ((15u + d) / d) * d;   // 16 .. 30
+    const uint32_t pre = d2 - d;               // < 32: one step
+    if (v.lane < pre) base[p0 + v.lane] = base[p0 - d + v.lane % d];
+    __syncwarp();
+    p0 += pre;
+    d = d2;
+  }
+  uint32_t a = (p0 & ~3u) + 4u * v.lane;
+  if (a >= p1) return;
+  // phase of byte a inside the period (a may lie up to 3 bytes before p0: add whole periods first)
+  uint32_t m = (a + 4u * d - p0) % d;
+  const uint32_t step = 128u % d;
+  const uint32_t s0 = p0 - d;
+  for (; a < p1; a += 128u) {
+    const bool full = a >= p0 && a + 4u <= p1;
+    if (full && d >= 4u) {
+      const uint32_t rem = d - m;              // bytes up to the end of the period (>= 1)
+      uint32_t val = lzw_gather(base, s0 + m, rem < 4u ? rem : 4u);
+      if (rem < 4u) {
+        const uint32_t g2 = lzw_gather(base, s0, 4u - rem);
+        val = (val & ~(0xffffffffu << (8u * rem))) | (g2 << (8u * rem));
+      }
+      *reinterpret_cast<uint32_t*>(base + a) = val;
+    } else {
+      uint32_t mb = m;
+#pragma unroll
+      for (uint32_t b = 0; b < 4; ++b) {
+        while (mb >= d) mb -= d;
+        const uint32_t p = a + b;
+        if (p >= p0 && p < p1) base[p] = base[s0 + mb];
+        ++mb;
+      }
+    }
+    m += step;
+    if (m >= d) m -= d;
+  }
+}
+
 // d in {1, 2, 4, 8, 16}: the 16 bytes of every aligned 16-byte slot are the same — build them once
-__device__ __noinline__ void lzw_fill_pattern16(const LzwView v, uint32_t p0, uint32_t p1, uint32_t d)
+__device__ __forceinline__ void lzw_fill_pattern16(const LzwView v, uint32_t p0, uint32_t p1, uint32_t d)
 {
   constexpr unsigned FULL = 0xffffffffu;
   uint8_t* const base = v.base;
@@ -159,7 +205,7 @@ __device__ __noinline__ void lzw_fill_pattern16(const LzwView v, uint32_t p0, ui
 
 // d >= 512: 16 bytes per lane from p - d; a 512-byte iteration only reads what earlier iterations
 // (or earlier matches) wrote
-__device__ __noinline__ void lzw_fill_far(const LzwView v, uint32_t p0, uint32_t p1, uint32_t d)
+__device__ __forceinline__ void lzw_fill_far(const LzwView v, uint32_t p0, uint32_t p1, uint32_t d)
 {
   uint8_t* const base = v.base;
   const uint32_t h16 = (p0 + 15u) & ~15u, t16 = p1 & ~15u;
@@ -183,11 +229,12 @@ __device__ __noinline__ void lzw_fill_far(const LzwView v, uint32_t p0, uint32_t
   if (t16 < p1) lzw_fill_periodic(v, t16, p1, d);
 }
 
-__device__ __forceinline__ void lzw_fill(const LzwView& v, uint32_t p0, uint32_t p1, uint32_t d)
+__device__ __noinline__ void lzw_fill(const LzwView v, uint32_t p0, uint32_t p1, uint32_t d)
 {
   const uint32_t n = p1 - p0;
   if (n >= 48u && d <= 16u && (d & (d - 1u)) == 0u) lzw_fill_pattern16(v, p0, p1, d);
   else if (n >= 48u && d >= 512u) lzw_fill_far(v, p0, p1, d);
+  else if (n >= 48u) lzw_fill_periodic_long(v, p0, p1, d);
   else lzw_fill_periodic(v, p0, p1, d);
   __syncwarp();
 }

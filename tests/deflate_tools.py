@@ -419,7 +419,8 @@ def crafted_lz_streams():
     for lead in (0, 1, 7, 15, 16, 17, 100, 1000, 1023, 1024, 1025):
         for dist, nmax, last in ((1, 3, 100), (1, 40, 0), (2, 5, 3), (3, 4, 257), (4, 2, 50), (5, 3, 0), (8, 33, 258),
                                  (15, 2, 9), (16, 6, 77), (17, 3, 30), (31, 2, 0), (258, 3, 11), (300, 4, 100),
-                                 (511, 2, 3), (512, 5, 200), (513, 35, 17), (4000, 3, 0)):
+                                 (511, 2, 3), (512, 5, 200), (513, 35, 17), (4000, 3, 0),
+                                 (6, 3, 5), (7, 4, 0), (9, 3, 40), (11, 2, 3), (13, 3, 99), (23, 2, 7), (100, 3, 0)):
             w = BitWriter()
             blk = fixed_block(w, True)
             n = max(lead, dist)

@@ -206,6 +206,23 @@ def test_small_table_geometry_with_hand_over(oracle, golden, monkeypatch):
         c.close()
 
 
+@pytest.mark.parametrize("env", [{"SFB200_NO_WIDE": "1"}, {"SFB200_NO_WIDE": "1", "SFB200_NO_STORED": "1", "SFB200_NO_PAIR": "1"}],
+                         ids=["large-geometry", "large-geometry-plain"])
+def test_golden_families_on_the_large_geometry(oracle, golden, monkeypatch, env):
+    """Small batches take the wide table geometry (9/6-bit roots, one CTA per SM) and stored streams
+    the copy kernel: here every golden family goes through the 8/6-bit geometry the full-size
+    batches use, once with and once without the copy kernel and the literal pairing."""
+    import starflate_b200 as S
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    c = S.Context(0)
+    try:
+        for name in golden.families:
+            _check_family(c, oracle, golden, name)
+    finally:
+        c.close()
+
+
 def test_crafted_lz_shapes_and_unaligned_dst_base(ctx, oracle):
     """Runs, short periods, far copies and dense short matches at every chunk phase
     (tests.deflate_tools.crafted_lz_streams), packed back to back, through a dst pointer that is
