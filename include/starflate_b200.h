@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SFB200_ABI_VERSION 4
+#define SFB200_ABI_VERSION 5
 
 /* starflate::DecompressStatus, numeric values preserved (src/decompress.hpp:13-23). */
 enum sfb200_status {
@@ -125,6 +125,30 @@ uint64_t sfb200_staging_bytes(const sfb200_ctx* ctx);
  * DecompressStatus; *written (may be NULL) the bytes produced. */
 int sfb200_decompress(sfb200_ctx* ctx, const uint8_t* src, size_t src_len, uint8_t* dst,
                       size_t dst_cap, uint8_t* status, uint64_t* written);
+
+/* Chunked input for ONE stream (extension; SURVEY.md §8 f3 — the reference anticipates it at
+ * src/decompress.cpp:214): the compressed bytes arrive in pieces, the output leaves in pieces, and
+ * neither has to fit device (or host) memory as a whole.  The unit of progress is the deflate
+ * BLOCK: a call decodes every block that is complete in the input fed so far and that fits `dst`,
+ * and carries to the next call the bytes from the next block header on, the bit offset of that
+ * header and the last 32 KiB of output (the LZ77 window) — all on the device.
+ *   feed(src, src_len, last, dst, dst_cap):  `src` = the next src_len bytes of the stream (host
+ *   memory; 0 is fine: decode more of what is buffered), `last` != 0 = no input comes after these.
+ *   *written = bytes put into dst by this call (they follow what earlier calls returned);
+ *   *finished != 0: the stream has ended and *status is its DecompressStatus — Success after the
+ *   final block, else exactly the status one sfb200_decompress call over the whole input would
+ *   return (with `last` set, input that stops short is an error as it is there; the bytes decoded
+ *   before it are returned).  Running out of room never ends the stream: while *finished == 0,
+ *   *status is SFB200_SUCCESS, or SFB200_DST_TOO_SMALL with *written == 0 when dst cannot hold even
+ *   the next block: nothing is lost, call again with more room (zlib's blocks are tens to hundreds of KiB of output; a block of
+ *   back-to-back maximum-length matches can reach a few MiB).  An error inside a block that is not
+ *   the last chunk cannot be told from input that merely stops short, so it is reported once `last`
+ *   is set.  Synchronous; a stream belongs to the context it was created on (one call at a time). */
+typedef struct sfb200_inflate_stream sfb200_inflate_stream;
+int sfb200_inflate_stream_create(sfb200_ctx* ctx, sfb200_inflate_stream** out);
+void sfb200_inflate_stream_destroy(sfb200_inflate_stream* s);
+int sfb200_inflate_stream_feed(sfb200_inflate_stream* s, const uint8_t* src, size_t src_len, int last, uint8_t* dst,
+                               size_t dst_cap, uint64_t* written, uint8_t* status, int* finished);
 
 /* Size discovery (extension).  The reference's decompress() returns no size and
  * requires the caller to bring a dst that is large enough (src/decompress.hpp:57-64).  This runs

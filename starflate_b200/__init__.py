@@ -245,6 +245,10 @@ class Context:
         self._check(rc, "sfb200_decompress")
         return st.value, d[:dst_cap].tobytes(), wr.value
 
+    def inflate_stream(self) -> "InflateStream":
+        """Chunked input for one stream (sfb200_inflate_stream_*)."""
+        return InflateStream(self)
+
     def staging_bytes(self) -> int:
         """Device memory held for the host-buffer entry points' staging slots."""
         self.lib.sfb200_staging_bytes.argtypes = [C.c_void_p]
@@ -261,3 +265,45 @@ class Context:
         li = _LaunchInfo()
         self._check(self.lib.sfb200_get_launch_info(self.h, C.byref(li)), "sfb200_get_launch_info")
         return {k: getattr(li, k) for k, _ in _LaunchInfo._fields_}
+
+
+class InflateStream:
+    """One stream fed in pieces (sfb200_inflate_stream_*): block-granular progress, the bit offset of
+    the next block header and the last 32 KiB of output are carried on the device."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        lib = ctx.lib
+        lib.sfb200_inflate_stream_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        lib.sfb200_inflate_stream_create.restype = C.c_int
+        lib.sfb200_inflate_stream_destroy.argtypes = [C.c_void_p]
+        lib.sfb200_inflate_stream_destroy.restype = None
+        lib.sfb200_inflate_stream_feed.argtypes = [C.c_void_p, _u8p, C.c_size_t, C.c_int, _u8p, C.c_size_t,
+                                                   C.POINTER(C.c_uint64), C.POINTER(C.c_uint8), C.POINTER(C.c_int)]
+        lib.sfb200_inflate_stream_feed.restype = C.c_int
+        h = C.c_void_p()
+        ctx._check(lib.sfb200_inflate_stream_create(ctx.h, C.byref(h)), "sfb200_inflate_stream_create")
+        self.h = h
+
+    def feed(self, src: bytes, last: bool, dst_cap: int):
+        """-> (status, bytes produced by this call, finished)"""
+        s = np.frombuffer(src, dtype=np.uint8) if len(src) else np.zeros(1, np.uint8)
+        d = np.zeros(max(dst_cap, 1), dtype=np.uint8)
+        wr = C.c_uint64(0)
+        st = C.c_uint8(0)
+        fin = C.c_int(0)
+        rc = self.ctx.lib.sfb200_inflate_stream_feed(self.h, _p(s, _u8p), len(src), int(last), _p(d, _u8p), dst_cap,
+                                                     C.byref(wr), C.byref(st), C.byref(fin))
+        self.ctx._check(rc, "sfb200_inflate_stream_feed")
+        return st.value, d[:wr.value].tobytes(), bool(fin.value)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.sfb200_inflate_stream_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -360,11 +360,39 @@ int sfb200_get_launch_info(sfb200_ctx* ctx, sfb200_launch_info* out)
   return SFB200_RC_OK;
 }
 
+}  // extern "C"
+
+namespace {
+// chunked input (sfb200_inflate_stream_feed): where each stream starts, and where its decode got to
+struct Resume {
+  const uint64_t* start_bit;
+  const uint64_t* start_out;
+  uint64_t* blk_end;
+};
+
+int batch_device_impl(sfb200_ctx* ctx, const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len,
+                      uint8_t* dst_base, uint64_t dst_bytes, const uint64_t* dst_off, const uint64_t* dst_cap,
+                      uint8_t* status, uint64_t* written, uint64_t n, void* cuda_stream, const Resume* resume);
+}  // namespace
+
+extern "C" {
+
 int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
                                    const uint64_t* src_off, const uint64_t* src_len,
                                    uint8_t* dst_base, uint64_t dst_bytes, const uint64_t* dst_off,
                                    const uint64_t* dst_cap, uint8_t* status,
                                    uint64_t* written, uint64_t n, void* cuda_stream)
+{
+  return batch_device_impl(ctx, src_base, src_off, src_len, dst_base, dst_bytes, dst_off, dst_cap, status, written,
+                           n, cuda_stream, nullptr);
+}
+
+}  // extern "C"
+
+namespace {
+int batch_device_impl(sfb200_ctx* ctx, const uint8_t* src_base, const uint64_t* src_off, const uint64_t* src_len,
+                      uint8_t* dst_base, uint64_t dst_bytes, const uint64_t* dst_off, const uint64_t* dst_cap,
+                      uint8_t* status, uint64_t* written, uint64_t n, void* cuda_stream, const Resume* resume)
 {
   if (!ctx) return SFB200_RC_BAD_ARGUMENT;
   if (n == 0) return SFB200_RC_OK;
@@ -407,6 +435,7 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
                                        LaneCfg::WARPS * 32 &&
                      dst_bytes / n >= 32768;
   if (const char* e = std::getenv("SFB200_STREAM_MODE")) stream_mode = e[0] == '1' && ctx->stream_ctas_per_sm > 0;
+  if (resume) stream_mode = false;  // (a decode that continues at a block boundary: the lane kernel only)
   // One stream: pass 2 works on the whole output at once (lz_jump.cuh) instead of one warp walking it
   // (also a FEW large streams, one after the other: sizes are only known on the device, so "large" is
   //  judged by the room the caller gave them)
@@ -519,7 +548,7 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
   SFB_TRY(ctx, cudaMemsetAsync(ctx->d_bits, 0, bits_words * sizeof(uint32_t), st));
   // Order the streams by the type of their first block (see lz_warp.cuh: PrepArgs)
   uint8_t* handled = nullptr;
-  bool sorted = n >= 64 && n < 0xffffffffull && !stream_mode;
+  bool sorted = n >= 64 && n < 0xffffffffull && !stream_mode && !resume;
   if (const char* e = std::getenv("SFB200_NO_SORT"))
     if (e[0] == '1') sorted = false;
   if (sorted) {
@@ -601,6 +630,9 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
     a.todo_count = nullptr;
     a.no_pair = ctx->no_pair;
     a.handled = handled;
+    a.start_bit = resume ? resume->start_bit : nullptr;
+    a.start_out = resume ? resume->start_out : nullptr;
+    a.blk_end = resume ? resume->blk_end : nullptr;
     const uint64_t groups = (cnt + 31) / 32;
     if (stream_mode) {
       sfb::StreamArgs sa;
@@ -816,6 +848,10 @@ int sfb200_decompress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
   return SFB200_RC_OK;
 }
 
+}  // namespace
+
+extern "C" {
+
 int sfb200_decompressed_size_batch_device(sfb200_ctx* ctx, const uint8_t* src_base,
                                           const uint64_t* src_off, const uint64_t* src_len,
                                           uint8_t* status, uint64_t* size, uint64_t n,
@@ -849,6 +885,9 @@ int sfb200_decompressed_size_batch_device(sfb200_ctx* ctx, const uint8_t* src_ba
   a.todo_count = nullptr;
   a.no_pair = ctx->no_pair;
   a.handled = nullptr;
+  a.start_bit = nullptr;
+  a.start_out = nullptr;
+  a.blk_end = nullptr;
   auto kern = sfb::huff_lanes_kernel<LaneCfg, true>;
   if (!ctx->count_configured) {  // (function attributes are per device)
     SFB_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, LaneCfg::SMEM_BYTES));
@@ -1207,6 +1246,171 @@ int sfb200_decompress(sfb200_ctx* ctx, const uint8_t* src, size_t src_len, uint8
   return sfb200_decompress_batch_host(ctx, src, sl, &zero, &sl, dst, dc, &zero, &dc, status,
                                       written, 1);
 }
+
+// ---------------------------------------------------------------------------------------------
+// Chunked input for ONE stream (the reference anticipates it at
+// src/decompress.cpp:214).  The unit of progress is the BLOCK: a call decodes, with the lane kernel,
+// every block that is complete in the input fed so far, keeps what those blocks produced and
+// carries three things to the next call — the bytes from the next block header on (device), the bit
+// offset of that header, and the last 32 KiB of output (the LZ77 window, in front of the output
+// buffer, so that distances reach into it as they would in one call).
+struct sfb200_inflate_stream {
+  sfb200_ctx* ctx = nullptr;
+  uint8_t* d_in[2] = {nullptr, nullptr};   // buffered input (the other one is the target of the next compaction)
+  uint64_t d_in_cap[2] = {0, 0};
+  int cur = 0;
+  uint64_t in_len = 0;     // bytes buffered
+  uint64_t bit = 0;        // bit offset of the next block header inside the buffer (0..7 between calls)
+  uint8_t* d_out = nullptr;   // [32 KiB window | output of one call]
+  uint64_t d_out_cap = 0;
+  uint8_t* d_tmp = nullptr;   // 32 KiB (window moves that overlap)
+  uint64_t hist = 0;       // valid window bytes, right-aligned in the first 32 KiB of d_out
+  uint64_t* d_meta = nullptr;  // src_off, src_len, dst_off, dst_cap, written, start_bit, start_out, blk_end[2], status
+  bool finished = false;
+  uint8_t final_status = 0;
+};
+
+namespace {
+constexpr uint64_t kWindow = 32768;
+int keep_bytes(sfb200_ctx* ctx, uint8_t** p, uint64_t* cap, uint64_t need, uint64_t keep)
+{
+  if (need <= *cap) return SFB200_RC_OK;
+  uint8_t* q = nullptr;
+  const uint64_t want = need + need / 2 + 4096;
+  SFB_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&q), want));
+  if (keep) SFB_TRY(ctx, cudaMemcpy(q, *p, keep, cudaMemcpyDeviceToDevice));
+  if (*p) SFB_TRY(ctx, cudaFree(*p));
+  *p = q;
+  *cap = want;
+  return SFB200_RC_OK;
+}
+}  // namespace
+
+int sfb200_inflate_stream_create(sfb200_ctx* ctx, sfb200_inflate_stream** out)
+{
+  if (!ctx || !out) return SFB200_RC_BAD_ARGUMENT;
+  SFB_ENTER(ctx);
+  sfb200_inflate_stream* s = new (std::nothrow) sfb200_inflate_stream;
+  if (!s) return SFB200_RC_OUT_OF_MEMORY;
+  s->ctx = ctx;
+  if (cudaMalloc(reinterpret_cast<void**>(&s->d_tmp), kWindow) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&s->d_meta), 16 * sizeof(uint64_t)) != cudaSuccess) {
+    cudaFree(s->d_tmp);
+    delete s;
+    cudaGetLastError();
+    return SFB200_RC_OUT_OF_MEMORY;
+  }
+  *out = s;
+  return SFB200_RC_OK;
+}
+
+void sfb200_inflate_stream_destroy(sfb200_inflate_stream* s)
+{
+  if (!s) return;
+  DeviceGuard guard_(s->ctx->device);
+  cudaFree(s->d_in[0]);
+  cudaFree(s->d_in[1]);
+  cudaFree(s->d_out);
+  cudaFree(s->d_tmp);
+  cudaFree(s->d_meta);
+  delete s;
+}
+
+int sfb200_inflate_stream_feed(sfb200_inflate_stream* s, const uint8_t* src, size_t src_len, int last, uint8_t* dst,
+                               size_t dst_cap, uint64_t* written, uint8_t* status, int* finished)
+{
+  if (!s || !status || !written || !finished || (src_len && !src) || (dst_cap && !dst)) return SFB200_RC_BAD_ARGUMENT;
+  sfb200_ctx* const ctx = s->ctx;
+  SFB_ENTER(ctx);
+  *written = 0;
+  if (s->finished) {
+    *status = s->final_status;
+    *finished = 1;
+    return SFB200_RC_OK;
+  }
+  *finished = 0;
+  *status = SFB200_SUCCESS;
+  if (s->in_len + src_len >= 0xffffff00ull || kWindow + dst_cap >= 0xffffff00ull) return SFB200_RC_BAD_ARGUMENT;
+  // the new input goes behind what is buffered
+  int rc = keep_bytes(ctx, &s->d_in[s->cur], &s->d_in_cap[s->cur], s->in_len + src_len + 64, s->in_len);
+  if (rc != SFB200_RC_OK) return rc;
+  if (src_len) SFB_TRY(ctx, cudaMemcpy(s->d_in[s->cur] + s->in_len, src, src_len, cudaMemcpyHostToDevice));
+  s->in_len += src_len;
+  if (dst_cap == 0 && !last) return SFB200_RC_OK;  // (only buffering)
+  rc = keep_bytes(ctx, &s->d_out, &s->d_out_cap, kWindow + dst_cap + 256, s->d_out ? kWindow : 0);
+  if (rc != SFB200_RC_OK) return rc;
+  // one lane-kernel decode from the pending block header, behind the window
+  uint64_t h[16] = {0};
+  h[0] = 0;                        // src_off
+  h[1] = s->in_len;                // src_len
+  h[2] = kWindow - s->hist;        // dst_off
+  h[3] = s->hist + dst_cap;        // dst_cap
+  h[4] = s->hist;                  // written (overwritten)
+  h[5] = s->bit;                   // start_bit
+  h[6] = s->hist;                  // start_out
+  h[7] = s->bit;                   // blk_end: bit, output position (stay like this when no header is reached)
+  h[8] = s->hist;
+  h[9] = SFB200_ERROR;             // status (first byte)
+  SFB_TRY(ctx, cudaMemcpy(s->d_meta, h, sizeof h, cudaMemcpyHostToDevice));
+  Resume rs;
+  rs.start_bit = s->d_meta + 5;
+  rs.start_out = s->d_meta + 6;
+  rs.blk_end = s->d_meta + 7;
+  rc = batch_device_impl(ctx, s->d_in[s->cur], s->d_meta + 0, s->d_meta + 1, s->d_out, kWindow + dst_cap, s->d_meta + 2,
+                         s->d_meta + 3, reinterpret_cast<uint8_t*>(s->d_meta + 9), s->d_meta + 4, 1, nullptr, &rs);
+  if (rc != SFB200_RC_OK) return rc;
+  SFB_TRY(ctx, cudaMemcpy(h, s->d_meta, sizeof h, cudaMemcpyDeviceToHost));
+  const uint8_t st = static_cast<uint8_t>(h[9] & 0xffu);
+  const uint64_t total = h[4], be_bit = h[7], be_out = h[8];
+  uint64_t produced = 0;
+  if (st == SFB200_SUCCESS || (last && st != SFB200_DST_TOO_SMALL)) {
+    // the final block was decoded, or no more input will come: the stream ends as one call would end it
+    produced = total - s->hist;
+    s->finished = true;
+    s->final_status = st;
+    *status = st;
+    *finished = 1;
+  } else if (st == SFB200_DST_TOO_SMALL && be_out == s->hist) {
+    *status = SFB200_DST_TOO_SMALL;  // not even the next block fits dst: call again with more room (nothing is lost)
+    return SFB200_RC_OK;
+  } else {
+    // ran out of input (or of room) inside a block: keep the complete blocks, redo that one next time
+    produced = be_out - s->hist;
+    s->bit = be_bit;
+  }
+  if (produced) SFB_TRY(ctx, cudaMemcpy(dst, s->d_out + kWindow, produced, cudaMemcpyDeviceToHost));
+  *written = produced;
+  if (!s->finished) {
+    // the window: the last 32 KiB of everything produced so far
+    const uint64_t have = s->hist + produced;
+    const uint64_t keep = have < kWindow ? have : kWindow;
+    if (produced) {
+      const uint8_t* from = s->d_out + kWindow + produced - keep;
+      uint8_t* to = s->d_out + kWindow - keep;
+      if (produced >= kWindow) {
+        SFB_TRY(ctx, cudaMemcpy(to, from, keep, cudaMemcpyDeviceToDevice));
+      } else {
+        SFB_TRY(ctx, cudaMemcpy(s->d_tmp, from, keep, cudaMemcpyDeviceToDevice));
+        SFB_TRY(ctx, cudaMemcpy(to, s->d_tmp, keep, cudaMemcpyDeviceToDevice));
+      }
+    }
+    s->hist = keep;
+    // the input: drop the bytes in front of the pending block header
+    const uint64_t drop = s->bit >> 3;
+    if (drop) {
+      const int other = s->cur ^ 1;
+      const uint64_t rest = s->in_len - drop;
+      rc = keep_bytes(ctx, &s->d_in[other], &s->d_in_cap[other], rest + 64, 0);
+      if (rc != SFB200_RC_OK) return rc;
+      if (rest) SFB_TRY(ctx, cudaMemcpy(s->d_in[other], s->d_in[s->cur] + drop, rest, cudaMemcpyDeviceToDevice));
+      s->cur = other;
+      s->in_len = rest;
+      s->bit &= 7u;
+    }
+  }
+  return SFB200_RC_OK;
+}
+
 
 int sfb200_decompress_container_batch_device(sfb200_ctx* ctx, int container, const uint8_t* src_base,
                                              const uint64_t* src_off, const uint64_t* src_len,

@@ -68,6 +68,14 @@ struct BatchArgs {
   const unsigned long long* todo_count;     // in: how many of them (null: n)
   uint32_t no_pair;                         // A/B switch (SFB200_NO_PAIR=1): one token per iteration, as before
   const uint8_t* handled;                   // in (may be null): 1 = stored_streams_kernel finished this stream already
+  // Chunked input (sfb200_inflate_stream_*; all three null otherwise): stream i starts at bit
+  // start_bit[i] of its src — a block header — with start_out[i] bytes of earlier output already
+  // in place at the front of its dst region (they count as written: distances may reach into
+  // them); blk_end[2i] / blk_end[2i+1] receive the bit position and the output position of the last
+  // block boundary the decode passed (what a later call can continue from).
+  const uint64_t* start_bit;
+  const uint64_t* start_out;
+  uint64_t* blk_end;
 };
 
 // ---------------------------------------------------------------------------------------------

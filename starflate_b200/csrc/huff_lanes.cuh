@@ -296,12 +296,20 @@ huff_lanes_kernel(const BatchArgs a)
       } else {
         br.open(a.src_base + a.src_off[idx], static_cast<uint32_t>(slen), ring);
         ow.open(a.dst_base, COUNT ? 0ull : a.dst_off[idx] + a.dst_delta, static_cast<uint32_t>(cap), a.match_bits);
+        if (a.start_bit != nullptr) {  // chunked input: continue at a block header, behind earlier output
+          br.seek_bit(a.start_bit[idx]);
+          ow.jump(static_cast<uint32_t>(a.start_out[idx]));
+        }
         state = S_HEADER;
       }
     }
 
     while (__any_sync(FULL, state != S_DONE)) {
       if (state == S_HEADER) {
+        if (a.blk_end != nullptr) {  // (chunked input) a block boundary: this far a later call need not redo
+          a.blk_end[2 * idx] = static_cast<uint64_t>(br.bitpos());
+          a.blk_end[2 * idx + 1] = ow.written();
+        }
         uint32_t lost = 0;
         state = parse_block_header<C>(br, m, ow.room(), final_block, n_lit, n_dist, copy_src,
                                       copy_left, &status, &lost, lt_lit, lt_dist, tables_fixed);

@@ -99,6 +99,9 @@ extern "C" int emu_decompress_batch(const uint8_t* src, const uint64_t* src_off,
     a.todo_count = nullptr;
     a.no_pair = 0;
     a.handled = nullptr;
+    a.start_bit = nullptr;
+    a.start_out = nullptr;
+    a.blk_end = nullptr;
     threadIdx.x = 0;
     blockIdx.x = 0;
     uint32_t handed[1] = {0xffffffffu};
@@ -158,6 +161,52 @@ extern "C" void emu_decompressed_size(const uint8_t* src, const uint64_t* src_of
     blockIdx.x = 0;
     sfb::huff_lanes_kernel<EmuCfg, true>(a);
   }
+}
+
+// Chunked input (BatchArgs::start_bit / start_out / blk_end): one stream, decoding from bit
+// `start_bit` with `start_out` bytes of earlier output at the front of dst (128-byte aligned here).
+// -> status; written (incl. start_out), the last block boundary passed (bit, output position).
+extern "C" int emu_decompress_resume(const uint8_t* src, uint64_t src_len, uint64_t start_bit, uint8_t* dst,
+                                     uint64_t start_out, uint64_t cap, uint64_t* written, uint64_t* blk_end)
+{
+  std::vector<uint16_t> smem(EmuCfg::SMEM_BYTES / 2 + 64, 0xDEAD);
+  std::vector<uint32_t> lens(sfb::SCRATCH_WORDS * 32, 0xDEADBEEFu);
+  emu_smem = smem.data();
+  blockDim.x = 1;
+  gridDim.x = 1;
+  std::vector<uint8_t> sbuf(src_len + 64, 0xEE);
+  if (src_len) std::memcpy(sbuf.data() + 16, src, src_len);
+  std::vector<uint8_t> dbuf(cap + 512, 0xC3);
+  uint8_t* dbase = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dbuf.data()) + 255) & ~uintptr_t{127});
+  std::memcpy(dbase, dst, cap);
+  std::vector<uint32_t> bits(cap / 32 + 8, 0u);
+  unsigned long long counter = 0;
+  const uint64_t zero = 0;
+  uint8_t st = 0xEE;
+  uint64_t wr = 0;
+  sfb::BatchArgs a{};
+  a.src_base = sbuf.data() + 16;
+  a.src_off = &zero;
+  a.src_len = &src_len;
+  a.dst_base = dbase;
+  a.dst_off = &zero;
+  a.dst_cap = &cap;
+  a.status = &st;
+  a.written = &wr;
+  a.n = 1;
+  a.group_counter = &counter;
+  a.lens_scratch = lens.data();
+  a.match_bits = bits.data();
+  a.start_bit = &start_bit;
+  a.start_out = &start_out;
+  a.blk_end = blk_end;
+  threadIdx.x = 0;
+  blockIdx.x = 0;
+  sfb::huff_lanes_kernel<EmuCfg>(a);
+  scalar_resolve(dbase, 0, wr, bits.data());
+  std::memcpy(dst, dbase, cap);
+  *written = wr;
+  return st;
 }
 
 extern "C" void emu_stats(unsigned long long* out)

@@ -60,6 +60,23 @@ class Emu:
                                        p(sz, _u64p), b.n)
         return st, sz
 
+    def resume(self, src: bytes, start_bit: int, history: bytes, cap: int, fill: int = 0xA5):
+        """Chunked input (BatchArgs.start_bit / start_out / blk_end): decode `src` from bit `start_bit`
+        (a block header) behind `history`. -> (status, bytes after the history, written incl. history,
+        (bit, output position) of the last block boundary passed)"""
+        self.lib.emu_decompress_resume.argtypes = [_u8p, C.c_uint64, C.c_uint64, _u8p, C.c_uint64, C.c_uint64,
+                                                   _u64p, _u64p]
+        s = np.frombuffer(src, dtype=np.uint8) if len(src) else np.zeros(1, np.uint8)
+        total = len(history) + cap
+        d = np.full(max(total, 1), fill, dtype=np.uint8)
+        d[:len(history)] = np.frombuffer(history, dtype=np.uint8)
+        wr = np.zeros(1, np.uint64)
+        be = np.zeros(2, np.uint64)
+        p = lambda a, t: a.ctypes.data_as(t)
+        st = self.lib.emu_decompress_resume(p(s, _u8p), len(src), start_bit, p(d, _u8p), len(history), total,
+                                            p(wr, _u64p), p(be, _u64p))
+        return int(st), d[len(history):total].tobytes(), int(wr[0]), (int(be[0]), int(be[1]))
+
     def stream_decompress(self, src: bytes, cap: int, phase: int = 0, fill: int = 0xA5):
         """One stream through the single-stream pass 1 (huff_stream.cuh, 32 host threads) and the
         real pass 2. -> (status, dst bytes, written)"""

@@ -521,3 +521,73 @@ def test_size_discovery_matches_decode(ctx, oracle, golden):
     assert not st.any() and (wr == b.dst_cap).all()
     for k in (0, 7, 150, 299):
         assert b.dst_slice(dst, k).tobytes() == zlib.decompress(streams[k], -15)
+
+
+def _chunk_plain(seed, n_words, total):
+    rng = np.random.default_rng(seed)
+    words = [bytes(rng.integers(97, 123, int(rng.integers(2, 9))).astype(np.uint8)) for _ in range(n_words)]
+    return b" ".join(words[int(i)] for i in rng.integers(0, n_words, total))
+
+
+@pytest.mark.parametrize("piece,room", [(1 << 10, 1 << 20), (37_777, 1 << 20), (1 << 20, 1 << 21), (5_000, 70_000)])
+def test_chunked_input_stream(ctx, oracle, piece, room):
+    """sfb200_inflate_stream_*: a ~2.5 MB multi-block stream (dynamic, fixed and stored blocks, flush
+    points) fed in pieces, the output taken in pieces — byte-identical to one call over the whole
+    input (the oracle), whatever the piece size; dst too small for a block asks for more room."""
+    plain = _chunk_plain(11, 400, 330_000) + bytes(np.random.default_rng(3).integers(0, 256, 150_000, dtype=np.uint8))
+    plain += b"A" * 300_000 + _chunk_plain(12, 50, 60_000)
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    comp = b""
+    step = 180_000
+    for k in range(0, len(plain), step):
+        comp += co.compress(plain[k:k + step])
+        comp += co.flush([zlib.Z_SYNC_FLUSH, zlib.Z_FULL_FLUSH, zlib.Z_NO_FLUSH][(k // step) % 3]) if k + step < len(plain) else b""
+    comp += co.flush()
+    want_st, want = oracle.decompress(comp, len(plain) + 16)[:2]
+    assert want_st == 0 and bytes(want[:len(plain)]) == plain
+    s = ctx.inflate_stream()
+    try:
+        out = bytearray()
+        pos = 0
+        fin = False
+        guard = 0
+        while not fin:
+            chunk = comp[pos:pos + piece]
+            pos += len(chunk)
+            st, got, fin = s.feed(chunk, pos >= len(comp), room)
+            out += got
+            while not fin and st == 4 and not got:   # the next block does not fit: more room
+                st, got, fin = s.feed(b"", pos >= len(comp), 1 << 21)
+                out += got
+            assert st == 0, (st, pos)
+            guard += 1
+            assert guard < 10_000
+        assert bytes(out) == plain
+        assert s.feed(b"", True, 16) == (0, b"", True)   # after the end: the final status again
+    finally:
+        s.close()
+
+
+def test_chunked_input_stream_errors(ctx, oracle, golden):
+    """Input that stops short, and a corrupt block, end the stream with the status (and the bytes)
+    one call over the same input gives — once `last` says no more input will come."""
+    plain = _chunk_plain(21, 300, 120_000)
+    comp = zlib.compress(plain, 6)[2:-4]
+    for name, data in (("cut", comp[:len(comp) * 2 // 3]), ("flip", comp[:40_000] + bytes([comp[40_000] ^ 0x5A]) + comp[40_001:])):
+        want_st, want, want_wr = oracle.decompress(data, len(plain) + 64)[:3]
+        s = ctx.inflate_stream()
+        try:
+            out = bytearray()
+            fin = False
+            pos = 0
+            while not fin:
+                chunk = data[pos:pos + 9_000]
+                pos += len(chunk)
+                st, got, fin = s.feed(chunk, pos >= len(data), 1 << 20)
+                out += got
+                if not fin:
+                    assert st == 0
+            assert st == want_st, (name, st, want_st)
+            assert bytes(out) == bytes(want[:want_wr]), name
+        finally:
+            s.close()

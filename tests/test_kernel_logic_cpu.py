@@ -283,3 +283,45 @@ def test_container_kernels_in_emulation(emu):
         assert st == want, (kind, want, st)
     st, dst, wr = emu.container(1, z, len(p) - 1)
     assert st == 4  # dst too small: the raw decoder's status stands
+
+
+def test_chunked_input_resumes_at_block_boundaries(emu):
+    """sfb200_inflate_stream_*'s kernel side: a decode that starts at a block header in the middle
+    of the input, behind 32 KiB of earlier output, and reports the last block boundary it passed.
+    The host logic is restated here: feed pieces, keep what the completed blocks produced, carry
+    the bit offset and the window."""
+    import zlib
+    rng = np.random.default_rng(5)
+    words = [bytes(rng.integers(97, 123, int(rng.integers(2, 9))).astype(np.uint8)) for _ in range(300)]
+    plain = b" ".join(words[int(i)] for i in rng.integers(0, 300, 60000))
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    comp = b""
+    for k in range(0, len(plain), 50000):   # several blocks of every type, flush points in between
+        comp += co.compress(plain[k:k + 50000])
+        comp += co.flush(zlib.Z_FULL_FLUSH if (k // 50000) % 2 else zlib.Z_SYNC_FLUSH)
+    comp += co.flush()
+    assert zlib.decompress(comp, -15) == plain
+    for piece in (1000, 7777, 40000):
+        out = b""
+        hist = b""
+        buf = b""
+        base_bit = 0          # bit offset of the next block header inside buf
+        done = False
+        pos = 0
+        while not done:
+            chunk = comp[pos:pos + piece]
+            pos += len(chunk)
+            last = pos >= len(comp)
+            buf += chunk
+            st, got, wr, (be_bit, be_out) = emu.resume(buf, base_bit, hist, 1 << 19)
+            if st == 0 or last:
+                assert st == 0
+                out += got[:wr - len(hist)]
+                done = True
+            else:
+                new = got[:be_out - len(hist)]
+                out += new
+                hist = (hist + new)[-32768:]
+                base_bit = be_bit - 8 * (be_bit // 8)
+                buf = buf[be_bit // 8:]
+        assert out == plain, piece
