@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SFB200_ABI_VERSION 5
+#define SFB200_ABI_VERSION 6
 
 /* starflate::DecompressStatus, numeric values preserved (src/decompress.hpp:13-23). */
 enum sfb200_status {
@@ -149,6 +149,25 @@ int sfb200_inflate_stream_create(sfb200_ctx* ctx, sfb200_inflate_stream** out);
 void sfb200_inflate_stream_destroy(sfb200_inflate_stream* s);
 int sfb200_inflate_stream_feed(sfb200_inflate_stream* s, const uint8_t* src, size_t src_len, int last, uint8_t* dst,
                                size_t dst_cap, uint64_t* written, uint8_t* status, int* finished);
+
+/* Batched COMPRESSION to raw DEFLATE (extension; SURVEY.md §8 f4 — the direction the reference's
+ * README names as not built yet, README.md:5-7; it only has the Huffman-table construction,
+ * huffman/src/table.hpp:246-298).  Stream i = src_base[src_off[i] .. +src_len[i]) is written as one
+ * RFC 1951 stream to dst_base[dst_off[i] .. +dst_cap[i]): LZ77 by hashing (4-byte minimum match,
+ * 32 KiB window, greedy) and ONE fixed-Huffman block, or stored blocks where that is smaller.
+ * status[i] = SFB200_SUCCESS with written[i] bytes, or SFB200_DST_TOO_SMALL (written[i] = 0: neither
+ * form fits; sfb200_compress_bound(src_len) always does), or SFB200_ERROR for src_len[i] >= 2^32 -
+ * 256.  Bytes of the dst region past written[i] may have been used as scratch.  The output decodes
+ * with sfb200_decompress_*, with zlib and with the reference's decompress().  All arrays are
+ * DEVICE pointers; asynchronous on `cuda_stream`. */
+uint64_t sfb200_compress_bound(uint64_t src_len);
+int sfb200_compress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base, const uint64_t* src_off,
+                                 const uint64_t* src_len, uint8_t* dst_base, const uint64_t* dst_off,
+                                 const uint64_t* dst_cap, uint8_t* status, uint64_t* written, uint64_t n,
+                                 void* cuda_stream);
+/* One stream in host memory. */
+int sfb200_compress(sfb200_ctx* ctx, const uint8_t* src, size_t src_len, uint8_t* dst, size_t dst_cap,
+                    uint8_t* status, uint64_t* written);
 
 /* Size discovery (extension).  The reference's decompress() returns no size and
  * requires the caller to bring a dst that is large enough (src/decompress.hpp:57-64).  This runs

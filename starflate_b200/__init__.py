@@ -245,6 +245,39 @@ class Context:
         self._check(rc, "sfb200_decompress")
         return st.value, d[:dst_cap].tobytes(), wr.value
 
+    def compress_batch_device(self, src, src_off, src_len, dst, dst_off, dst_cap, status, written, stream=None):
+        """Batched compression to raw DEFLATE (sfb200_compress_batch_device); torch CUDA tensors."""
+        import torch
+        n = src_off.numel()
+        for t in (src_off, src_len, dst_off, dst_cap, written):
+            assert t.is_cuda and t.dtype == torch.int64 and t.is_contiguous() and t.numel() == n
+        assert src.is_cuda and src.dtype == torch.uint8 and dst.is_cuda and dst.dtype == torch.uint8
+        assert status.is_cuda and status.dtype == torch.uint8 and status.numel() == n
+        if stream is None:
+            stream = torch.cuda.current_stream(src.device).cuda_stream
+        f = self.lib.sfb200_compress_batch_device
+        f.argtypes = [C.c_void_p] * 9 + [C.c_uint64, C.c_void_p]
+        f.restype = C.c_int
+        rc = f(self.h, src.data_ptr(), src_off.data_ptr(), src_len.data_ptr(), dst.data_ptr(), dst_off.data_ptr(),
+               dst_cap.data_ptr(), status.data_ptr(), written.data_ptr(), n, stream)
+        self._check(rc, "sfb200_compress_batch_device")
+
+    def compress(self, src: bytes, dst_cap: int = -1):
+        """One stream in host memory -> (status, raw-DEFLATE bytes)."""
+        self.lib.sfb200_compress_bound.argtypes = [C.c_uint64]
+        self.lib.sfb200_compress_bound.restype = C.c_uint64
+        if dst_cap < 0:
+            dst_cap = int(self.lib.sfb200_compress_bound(len(src)))
+        s = np.frombuffer(src, dtype=np.uint8) if len(src) else np.zeros(1, np.uint8)
+        d = np.zeros(max(dst_cap, 1), dtype=np.uint8)
+        st = C.c_uint8(0)
+        wr = C.c_uint64(0)
+        f = self.lib.sfb200_compress
+        f.argtypes = [C.c_void_p, _u8p, C.c_size_t, _u8p, C.c_size_t, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64)]
+        f.restype = C.c_int
+        self._check(f(self.h, _p(s, _u8p), len(src), _p(d, _u8p), dst_cap, C.byref(st), C.byref(wr)), "sfb200_compress")
+        return st.value, d[:wr.value].tobytes()
+
     def inflate_stream(self) -> "InflateStream":
         """Chunked input for one stream (sfb200_inflate_stream_*)."""
         return InflateStream(self)

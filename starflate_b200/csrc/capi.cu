@@ -9,6 +9,7 @@
 #include "lz_window.cuh"
 #include "lz_jump.cuh"
 #include "container.cuh"
+#include "deflate_compress.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -72,6 +73,8 @@ struct sfb200_ctx {
   int lzw_minb = 5;            // lz_window_kernel instantiation (register budget for 4 / 5 / 6 CTAs per SM;
                                // measured with the long periodic fill in: 5 (48 registers) beats 6 (40, spills
                                // in the chunk loop) on C2 8.5 / 8.9 ms and C4 5.0 / 5.5 ms — SFB200_LZW_CTAS)
+  bool compress_configured = false;
+  int compress_ctas_per_sm = 0;
   bool no_stored = false;      // SFB200_NO_STORED=1: stored streams go through the lane kernel like the others (A/B runs)
   uint32_t no_pair = 0;        // SFB200_NO_PAIR=1: pass 1 takes one token per iteration (A/B runs)
   bool lz_v1 = false;          // SFB200_LZ_V1=1: the first-generation pass 2 (lz_warp.cuh), kept for A/B runs
@@ -1409,6 +1412,86 @@ int sfb200_inflate_stream_feed(sfb200_inflate_stream* s, const uint8_t* src, siz
     }
   }
   return SFB200_RC_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Batched compression (deflate_compress.cuh)
+uint64_t sfb200_compress_bound(uint64_t src_len)
+{
+  // stored blocks are the fallback: 5 header bytes per 65 535 payload bytes
+  return src_len + 5ull * (src_len ? (src_len + 65534ull) / 65535ull : 1ull);
+}
+
+int sfb200_compress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base, const uint64_t* src_off,
+                                 const uint64_t* src_len, uint8_t* dst_base, const uint64_t* dst_off,
+                                 const uint64_t* dst_cap, uint8_t* status, uint64_t* written, uint64_t n,
+                                 void* cuda_stream)
+{
+  if (!ctx) return SFB200_RC_BAD_ARGUMENT;
+  if (n == 0) return SFB200_RC_OK;
+  if (!src_off || !src_len || !dst_off || !dst_cap || !status || !written) return SFB200_RC_BAD_ARGUMENT;
+  SFB_ENTER(ctx);
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (!ctx->compress_configured) {  // (function attributes are per device)
+    SFB_TRY(ctx, cudaFuncSetAttribute(sfb::deflate_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      sfb::CMP_SMEM_BYTES));
+    int per_sm = 0;
+    SFB_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sfb::deflate_compress_kernel,
+                                                               sfb::CMP_WARPS * 32, sfb::CMP_SMEM_BYTES));
+    ctx->compress_ctas_per_sm = per_sm < 1 ? 1 : per_sm;
+    ctx->compress_configured = true;
+  }
+  SFB_TRY(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), st));
+  sfb::CompressArgs a;
+  a.src_base = src_base;
+  a.src_off = src_off;
+  a.src_len = src_len;
+  a.dst_base = dst_base;
+  a.dst_off = dst_off;
+  a.dst_cap = dst_cap;
+  a.status = status;
+  a.written = written;
+  a.n = n;
+  a.counter = ctx->d_counter;
+  const uint64_t want = (n + sfb::CMP_WARPS - 1) / sfb::CMP_WARPS;
+  const uint64_t resident = static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->compress_ctas_per_sm);
+  sfb::deflate_compress_kernel<<<static_cast<unsigned>(want < resident ? want : resident), sfb::CMP_WARPS * 32,
+                                 sfb::CMP_SMEM_BYTES, st>>>(a);
+  SFB_TRY(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  return SFB200_RC_OK;
+}
+
+int sfb200_compress(sfb200_ctx* ctx, const uint8_t* src, size_t src_len, uint8_t* dst, size_t dst_cap,
+                    uint8_t* status, uint64_t* written)
+{
+  if (!ctx || !status || !written || (src_len && !src) || (dst_cap && !dst)) return SFB200_RC_BAD_ARGUMENT;
+  SFB_ENTER(ctx);
+  uint8_t* buf = nullptr;
+  const uint64_t in_pad = (static_cast<uint64_t>(src_len) + 255) & ~255ull;
+  const uint64_t total = in_pad + dst_cap + 256 + 64;
+  SFB_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&buf), total));
+  auto done = [&](int rc) {
+    cudaFree(buf);
+    return rc;
+  };
+  uint64_t h[6] = {0, src_len, 0, dst_cap, 0, 0};
+  uint64_t* meta = reinterpret_cast<uint64_t*>(buf + in_pad + ((dst_cap + 255) & ~255ull));
+  if (src_len && cudaMemcpy(buf, src, src_len, cudaMemcpyHostToDevice) != cudaSuccess)
+    return done(fail(ctx, cudaGetLastError(), "cudaMemcpy(src)"));
+  if (cudaMemcpy(meta, h, sizeof h, cudaMemcpyHostToDevice) != cudaSuccess)
+    return done(fail(ctx, cudaGetLastError(), "cudaMemcpy(meta)"));
+  int rc = sfb200_compress_batch_device(ctx, buf, meta + 0, meta + 1, buf + in_pad, meta + 2, meta + 3,
+                                        reinterpret_cast<uint8_t*>(meta + 5), meta + 4, 1, nullptr);
+  if (rc != SFB200_RC_OK) return done(rc);
+  if (cudaMemcpy(h, meta, sizeof h, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return done(fail(ctx, cudaGetLastError(), "cudaMemcpy(meta back)"));
+  *status = static_cast<uint8_t>(h[5] & 0xffu);
+  *written = h[4];
+  if (h[4] && cudaMemcpy(dst, buf + in_pad, h[4], cudaMemcpyDeviceToHost) != cudaSuccess)
+    return done(fail(ctx, cudaGetLastError(), "cudaMemcpy(dst)"));
+  return done(SFB200_RC_OK);
 }
 
 

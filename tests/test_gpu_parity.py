@@ -591,3 +591,82 @@ def test_chunked_input_stream_errors(ctx, oracle, golden):
             assert bytes(out) == bytes(want[:want_wr]), name
         finally:
             s.close()
+
+
+def test_compress_round_trip_batch(ctx, oracle):
+    """sfb200_compress_batch_device (§8 f4): a ragged batch — text, runs, random bytes, empty and tiny
+    streams, odd alignments — compressed on the GPU, then decoded three ways: by this library's
+    decompressor, by zlib and by the oracle (the reference's algorithm).  All give the input back."""
+    rng = np.random.default_rng(8)
+    words = [bytes(rng.integers(97, 123, int(rng.integers(2, 9))).astype(np.uint8)) for _ in range(500)]
+    plains = []
+    for i in range(300):
+        k = i % 6
+        n = int(rng.integers(0, 70_000)) if i % 7 else int(rng.integers(0, 12))
+        if k == 0:
+            p = b" ".join(words[int(j)] for j in rng.integers(0, 500, n // 6 + 1))[:n]
+        elif k == 1:
+            p = bytes([int(rng.integers(0, 256))]) * n
+        elif k == 2:
+            p = bytes(rng.integers(0, 256, n, dtype=np.uint8))
+        elif k == 3:
+            unit = bytes(rng.integers(0, 256, int(rng.integers(1, 40)), dtype=np.uint8))
+            p = (unit * (n // len(unit) + 1))[:n]
+        elif k == 4:
+            p = bytes(rng.integers(144, 256, n, dtype=np.uint8) if n else b"")
+        else:
+            p = T.text_like(n, 1000 + i) if n else b""
+        plains.append(p)
+    plains.append(_chunk_plain(5, 300, 200_000))   # > 65 535 bytes: the 16-bit position table wraps
+    n = len(plains)
+    lens = np.array([len(p) for p in plains], dtype=np.uint64)
+    src_off = np.zeros(n, np.uint64)
+    src_off[1:] = np.cumsum(lens + np.uint64(3))[:-1]          # odd gaps: every alignment
+    src = np.zeros(int(src_off[-1] + lens[-1]) + 8, np.uint8)
+    for i, p in enumerate(plains):
+        src[int(src_off[i]):int(src_off[i]) + len(p)] = np.frombuffer(p, dtype=np.uint8)
+    caps = lens + lens // np.uint64(8) + np.uint64(64)
+    dst_off = np.zeros(n, np.uint64)
+    dst_off[1:] = np.cumsum(caps + np.uint64(1))[:-1]
+    total = int(dst_off[-1] + caps[-1])
+    dev = torch.device("cuda", ctx.device)
+    as_i64 = lambda a: torch.from_numpy(a.view(np.int64)).to(dev)
+    d_src = torch.from_numpy(src).to(dev)
+    d_dst = torch.full((total,), 0xA5, dtype=torch.uint8, device=dev)
+    d_st = torch.full((n,), 0xEE, dtype=torch.uint8, device=dev)
+    d_wr = torch.zeros(n, dtype=torch.int64, device=dev)
+    ctx.compress_batch_device(d_src, as_i64(src_off), as_i64(lens), d_dst, as_i64(dst_off), as_i64(caps), d_st, d_wr)
+    torch.cuda.synchronize()
+    st = d_st.cpu().numpy()
+    wr = d_wr.cpu().numpy().view(np.uint64)
+    comp_all = d_dst.cpu().numpy()
+    assert (st == 0).all()
+    assert (wr <= caps).all()
+    comps = [comp_all[int(dst_off[i]):int(dst_off[i] + wr[i])].tobytes() for i in range(n)]
+    for i in range(n):
+        assert zlib.decompress(comps[i], -15) == plains[i], i
+        ost, out, owr, ub = oracle.decompress(comps[i], len(plains[i]) + 8)
+        assert (ost, owr, ub) == (0, len(plains[i]), 0) and out[:owr] == plains[i], i
+    # ... and back through this library's own decoder, as one batch
+    b = T.Batch(comps, [len(p) for p in plains])
+    dst_st, dst_wr, dst = gpu_util.run_device(ctx, b)
+    assert (dst_st == 0).all()
+    for i in range(n):
+        assert int(dst_wr[i]) == len(plains[i]) and b.dst_slice(dst, i).tobytes()[:len(plains[i])] == plains[i], i
+    ratio = float(lens.sum()) / float(wr.sum())
+    assert ratio > 1.2
+
+
+def test_compress_single_stream_host_api_and_small_dst(ctx):
+    data = _chunk_plain(9, 200, 20_000)
+    st, comp = ctx.compress(data)
+    assert st == 0 and zlib.decompress(comp, -15) == data and len(comp) < len(data) * 0.7
+    rnd = bytes(np.random.default_rng(4).integers(0, 256, 5000, dtype=np.uint8))
+    st, comp = ctx.compress(rnd)                       # incompressible: stored blocks, inside the bound
+    assert st == 0 and len(comp) == 5005 and zlib.decompress(comp, -15) == rnd
+    st, comp = ctx.compress(rnd, 4000)
+    assert st == 4 and comp == b""
+    st, comp = ctx.compress(b"")
+    assert st == 0 and zlib.decompress(comp, -15) == b""
+    st2, out, wr = ctx.decompress(ctx.compress(data)[1], len(data))
+    assert (st2, wr) == (0, len(data)) and out == data

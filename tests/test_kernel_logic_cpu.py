@@ -325,3 +325,34 @@ def test_chunked_input_resumes_at_block_boundaries(emu):
                 base_bit = be_bit - 8 * (be_bit // 8)
                 buf = buf[be_bit // 8:]
         assert out == plain, piece
+
+
+def test_compression_kernel_round_trips(emu, oracle):
+    """deflate_compress.cuh on 32 host threads: what it writes decodes, with zlib and with the oracle
+    (the reference's algorithm), to the input — text, runs, short periods, random bytes (stored
+    fallback), literals above 143 (9-bit codes), tiny inputs, every source phase; a dst that is too
+    small says so."""
+    import zlib
+    rng = np.random.default_rng(1)
+    words = [bytes(rng.integers(97, 123, int(rng.integers(2, 9))).astype(np.uint8)) for _ in range(200)]
+    cases = {
+        "empty": b"", "one": b"x", "three": b"abc", "four": b"abcd", "abcabc": b"abcabcabcabc",
+        "text": b" ".join(words[int(i)] for i in rng.integers(0, 200, 4000)),
+        "run": b"a" * 5000, "period3": b"abc" * 2000, "period5": b"hello" * 900,
+        "random": bytes(rng.integers(0, 256, 3000, dtype=np.uint8)),
+        "high": bytes(rng.integers(144, 256, 300, dtype=np.uint8)) * 5,
+        "far": bytes(rng.integers(0, 256, 500, dtype=np.uint8)) + bytes(31000) + bytes(rng.integers(0, 256, 500, dtype=np.uint8)),
+    }
+    cases["far"] = cases["far"] + cases["far"][:500]          # a match 31 500 bytes back
+    cases["big"] = cases["text"] * 5                           # > 65 535 bytes: positions wrap the 16-bit table
+    for name, data in cases.items():
+        for phase in ((0, 1, 2, 3) if len(data) < 7000 else (1,)):
+            st, comp = emu.compress(data, len(data) + len(data) // 8 + 64, phase)
+            assert st == 0, name
+            assert zlib.decompress(comp, -15) == data, name
+            ost, out, wr, ub = oracle.decompress(comp, len(data) + 8)
+            assert (ost, wr, ub) == (0, len(data), 0) and out[:wr] == data, name
+    st, comp = emu.compress(cases["random"], 100)
+    assert st == 4 and comp == b""
+    st, comp = emu.compress(cases["run"], 100)                  # fits compressed, would not fit stored
+    assert st == 0 and zlib.decompress(comp, -15) == cases["run"]
