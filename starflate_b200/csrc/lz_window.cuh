@@ -49,9 +49,29 @@ __device__ __forceinline__ uint32_t lzw_popc(uint32_t v)
   return static_cast<uint32_t>(__popc(v));
 #endif
 }
+// CG = loads go to the L2 (ld.global.cg), not through the L1: the variant that runs WHILE pass 1 is
+// still writing other parts of dst and of the bitmap from other SMs (lz_window_queue_kernel) must
+// never see a line its SM cached before those bytes were published.
+template <bool CG>
+__device__ __forceinline__ uint32_t lzw_ld32(const void* p)
+{
+#ifndef SFB_CPU_EMU
+  if constexpr (CG) return __ldcg(reinterpret_cast<const uint32_t*>(p));
+#endif
+  return *reinterpret_cast<const uint32_t*>(p);
+}
+template <bool CG>
+__device__ __forceinline__ uint32_t lzw_ld8(const uint8_t* p)
+{
+#ifndef SFB_CPU_EMU
+  if constexpr (CG) return __ldcg(p);
+#endif
+  return *p;
+}
+template <bool CG>
 __device__ __forceinline__ uint32_t lzw_ldw(const uint8_t* base, uint32_t v)  // v % 4 == 0
 {
-  return *reinterpret_cast<const uint32_t*>(base + v);
+  return lzw_ld32<CG>(base + v);
 }
 __device__ __forceinline__ void lzw_st16(uint8_t* p, uint32_t x, uint32_t y, uint32_t z, uint32_t w)  // p % 16 == 0
 {
@@ -71,20 +91,22 @@ __device__ __forceinline__ void lzw_prefetch(const void* p)
 #endif
 }
 // the 3-byte descriptor at view position h (any alignment; h + 2 is inside the stream)
+template <bool CG>
 __device__ __forceinline__ uint32_t lzw_desc(const uint8_t* base, uint32_t h)
 {
   const uint32_t a = h & ~3u, r = h & 3u;
-  const uint32_t lo = lzw_ldw(base, a);
-  const uint32_t hi = r >= 2u ? lzw_ldw(base, a + 4u) : 0u;
+  const uint32_t lo = lzw_ldw<CG>(base, a);
+  const uint32_t hi = r >= 2u ? lzw_ldw<CG>(base, a + 4u) : 0u;
   return lz_funnel(lo, hi, 8u * r) & 0xffffffu;
 }
 // n source bytes (1 <= n <= 4) starting at view position f, as the low bytes of a word; only aligned
 // words that hold at least one of them are read
+template <bool CG>
 __device__ __forceinline__ uint32_t lzw_gather(const uint8_t* base, uint32_t f, uint32_t n)
 {
   const uint32_t a = f & ~3u, r = f & 3u;
-  const uint32_t lo = lzw_ldw(base, a);
-  const uint32_t hi = r + n > 4u ? lzw_ldw(base, a + 4u) : 0u;
+  const uint32_t lo = lzw_ldw<CG>(base, a);
+  const uint32_t hi = r + n > 4u ? lzw_ldw<CG>(base, a + 4u) : 0u;
   return lz_funnel(lo, hi, 8u * r);
 }
 
@@ -94,6 +116,7 @@ __device__ __forceinline__ uint32_t lzw_gather(const uint8_t* base, uint32_t f, 
 // matches with the same distance).  All bytes below p0 are final.  Warp-uniform arguments.
 
 // 4 bytes per lane; reads only from the period [p0 - d, p0)
+template <bool CG>
 __device__ __forceinline__ void lzw_fill_periodic(const LzwView v, uint32_t p0, uint32_t p1, uint32_t d)
 {
   uint8_t* const base = v.base;
@@ -107,7 +130,7 @@ __device__ __forceinline__ void lzw_fill_periodic(const LzwView v, uint32_t p0, 
     const bool full = a >= p0 && a + 4u <= p1;
     uint32_t val;
     if (full && d >= 4u && m + 3u < d) {  // four consecutive sources
-      val = lzw_gather(base, s0 + m, 4u);
+      val = lzw_gather<CG>(base, s0 + m, 4u);
       *reinterpret_cast<uint32_t*>(base + a) = val;
     } else {
       uint32_t mb = m;
@@ -115,7 +138,7 @@ __device__ __forceinline__ void lzw_fill_periodic(const LzwView v, uint32_t p0, 
       for (uint32_t b = 0; b < 4; ++b) {
         while (mb >= d) mb -= d;
         const uint32_t p = a + b;
-        if (p >= p0 && p < p1) base[p] = base[s0 + mb];
+        if (p >= p0 && p < p1) base[p] = static_cast<uint8_t>(lzw_ld8<CG>(base + s0 + mb));
         ++mb;
       }
     }
@@ -128,13 +151,14 @@ __device__ __forceinline__ void lzw_fill_periodic(const LzwView v, uint32_t p0, 
 // A short period (d < 16) is widened first: once the first k d - d bytes exist, the fill is just as
 // periodic with k d >= 16, and a word then rarely straddles the end of the period; a word that does
 // is put together from the end and the start of the period (two gathers) instead of byte by byte.
+template <bool CG>
 __device__ __forceinline__ void lzw_fill_periodic_long(const LzwView v, uint32_t p0, uint32_t p1, uint32_t d)
 {
   uint8_t* const base = v.base;
   if (d < 16u) {
     const uint32_t d2 = ((15u + d) / d) * d;   // 16 .. 30
     const uint32_t pre = d2 - d;               // < 32: one step
-    if (v.lane < pre) base[p0 + v.lane] = base[p0 - d + v.lane % d];
+    if (v.lane < pre) base[p0 + v.lane] = static_cast<uint8_t>(lzw_ld8<CG>(base + p0 - d + v.lane % d));
     __syncwarp();
     p0 += pre;
     d = d2;
@@ -149,9 +173,9 @@ __device__ __forceinline__ void lzw_fill_periodic_long(const LzwView v, uint32_t
     const bool full = a >= p0 && a + 4u <= p1;
     if (full && d >= 4u) {
       const uint32_t rem = d - m;              // bytes up to the end of the period (>= 1)
-      uint32_t val = lzw_gather(base, s0 + m, rem < 4u ? rem : 4u);
+      uint32_t val = lzw_gather<CG>(base, s0 + m, rem < 4u ? rem : 4u);
       if (rem < 4u) {
-        const uint32_t g2 = lzw_gather(base, s0, 4u - rem);
+        const uint32_t g2 = lzw_gather<CG>(base, s0, 4u - rem);
         val = (val & ~(0xffffffffu << (8u * rem))) | (g2 << (8u * rem));
       }
       *reinterpret_cast<uint32_t*>(base + a) = val;
@@ -161,7 +185,7 @@ __device__ __forceinline__ void lzw_fill_periodic_long(const LzwView v, uint32_t
       for (uint32_t b = 0; b < 4; ++b) {
         while (mb >= d) mb -= d;
         const uint32_t p = a + b;
-        if (p >= p0 && p < p1) base[p] = base[s0 + mb];
+        if (p >= p0 && p < p1) base[p] = static_cast<uint8_t>(lzw_ld8<CG>(base + s0 + mb));
         ++mb;
       }
     }
@@ -171,6 +195,7 @@ __device__ __forceinline__ void lzw_fill_periodic_long(const LzwView v, uint32_t
 }
 
 // d in {1, 2, 4, 8, 16}: the 16 bytes of every aligned 16-byte slot are the same — build them once
+template <bool CG>
 __device__ __forceinline__ void lzw_fill_pattern16(const LzwView v, uint32_t p0, uint32_t p1, uint32_t d)
 {
   constexpr unsigned FULL = 0xffffffffu;
@@ -183,7 +208,7 @@ __device__ __forceinline__ void lzw_fill_pattern16(const LzwView v, uint32_t p0,
 #pragma unroll
     for (uint32_t j = 0; j < 4; ++j) {
       const uint32_t t = 4u * k + j;
-      w |= static_cast<uint32_t>(base[p0 - d + ((t - r) & (d - 1u))]) << (8u * j);
+      w |= lzw_ld8<CG>(base + p0 - d + ((t - r) & (d - 1u))) << (8u * j);
     }
   }
   const uint32_t r0 = __shfl_sync(FULL, w, 0), r1 = __shfl_sync(FULL, w, 1), r2 = __shfl_sync(FULL, w, 2),
@@ -205,37 +230,39 @@ __device__ __forceinline__ void lzw_fill_pattern16(const LzwView v, uint32_t p0,
 
 // d >= 512: 16 bytes per lane from p - d; a 512-byte iteration only reads what earlier iterations
 // (or earlier matches) wrote
+template <bool CG>
 __device__ __forceinline__ void lzw_fill_far(const LzwView v, uint32_t p0, uint32_t p1, uint32_t d)
 {
   uint8_t* const base = v.base;
   const uint32_t h16 = (p0 + 15u) & ~15u, t16 = p1 & ~15u;
   if (h16 >= t16) {
-    lzw_fill_periodic(v, p0, p1, d);
+    lzw_fill_periodic<CG>(v, p0, p1, d);
     return;
   }
-  if (p0 < h16) lzw_fill_periodic(v, p0, h16, d);  // (reads [p0 - d, p0) only)
+  if (p0 < h16) lzw_fill_periodic<CG>(v, p0, h16, d);  // (reads [p0 - d, p0) only)
   __syncwarp();
   for (uint32_t a0 = h16; a0 < t16; a0 += 512u) {
     const uint32_t a = a0 + 16u * v.lane;
     if (a < t16) {
       const uint32_t s = a - d, sa = s & ~3u, sh = 8u * (s & 3u);
-      const uint32_t w0 = lzw_ldw(base, sa), w1 = lzw_ldw(base, sa + 4u), w2 = lzw_ldw(base, sa + 8u),
-                     w3 = lzw_ldw(base, sa + 12u);
-      const uint32_t w4 = sh ? lzw_ldw(base, sa + 16u) : 0u;
+      const uint32_t w0 = lzw_ldw<CG>(base, sa), w1 = lzw_ldw<CG>(base, sa + 4u), w2 = lzw_ldw<CG>(base, sa + 8u),
+                     w3 = lzw_ldw<CG>(base, sa + 12u);
+      const uint32_t w4 = sh ? lzw_ldw<CG>(base, sa + 16u) : 0u;
       lzw_st16(base + a, lz_funnel(w0, w1, sh), lz_funnel(w1, w2, sh), lz_funnel(w2, w3, sh), lz_funnel(w3, w4, sh));
     }
     __syncwarp();
   }
-  if (t16 < p1) lzw_fill_periodic(v, t16, p1, d);
+  if (t16 < p1) lzw_fill_periodic<CG>(v, t16, p1, d);
 }
 
+template <bool CG>
 __device__ __noinline__ void lzw_fill(const LzwView v, uint32_t p0, uint32_t p1, uint32_t d)
 {
   const uint32_t n = p1 - p0;
-  if (n >= 48u && d <= 16u && (d & (d - 1u)) == 0u) lzw_fill_pattern16(v, p0, p1, d);
-  else if (n >= 48u && d >= 512u) lzw_fill_far(v, p0, p1, d);
-  else if (n >= 48u) lzw_fill_periodic_long(v, p0, p1, d);
-  else lzw_fill_periodic(v, p0, p1, d);
+  if (n >= 48u && d <= 16u && (d & (d - 1u)) == 0u) lzw_fill_pattern16<CG>(v, p0, p1, d);
+  else if (n >= 48u && d >= 512u) lzw_fill_far<CG>(v, p0, p1, d);
+  else if (n >= 48u) lzw_fill_periodic_long<CG>(v, p0, p1, d);
+  else lzw_fill_periodic<CG>(v, p0, p1, d);
   __syncwarp();
 }
 
@@ -243,7 +270,7 @@ __device__ __noinline__ void lzw_fill(const LzwView v, uint32_t p0, uint32_t p1,
 // One 128-byte chunk of a dense window.  `lo`/`hi`: only bytes in [lo, hi) are this call's to
 // produce (stream edges; bytes a fill has already produced).  EDGE = the chunk is not wholly
 // inside [lo, hi).  c_*: the most recent match seen so far (in/out).
-template <bool EDGE>
+template <bool EDGE, bool CG>
 __device__ __forceinline__ void lzw_chunk(const LzwView& v, uint32_t P, uint32_t lo, uint32_t hi, uint32_t cw,
                                           uint32_t ncw, uint32_t hb4, uint32_t& c_o, uint32_t& c_end,
                                           uint32_t& c_d)
@@ -313,10 +340,10 @@ __device__ __forceinline__ void lzw_chunk(const LzwView& v, uint32_t P, uint32_t
     uint32_t res = cw;
     const bool dep = (pendA && lastA >= P) || (pendB && lastB >= P);
     if (!__any_sync(FULL, dep)) {  // every source lies before the chunk: one shot
-      const uint32_t a0 = pendA ? *reinterpret_cast<const uint32_t*>(pA) : 0u;
-      const uint32_t a1 = (pendA && hiA) ? *reinterpret_cast<const uint32_t*>(pA + 4) : 0u;
-      const uint32_t b0 = pendB ? *reinterpret_cast<const uint32_t*>(pB) : 0u;
-      const uint32_t b1 = (pendB && hiB) ? *reinterpret_cast<const uint32_t*>(pB + 4) : 0u;
+      const uint32_t a0 = pendA ? lzw_ld32<CG>(pA) : 0u;
+      const uint32_t a1 = (pendA && hiA) ? lzw_ld32<CG>(pA + 4) : 0u;
+      const uint32_t b0 = pendB ? lzw_ld32<CG>(pB) : 0u;
+      const uint32_t b1 = (pendB && hiB) ? lzw_ld32<CG>(pB + 4) : 0u;
       const uint32_t gA = lz_funnel(a0, a1, 8u * rA), gB = lz_funnel(b0, b1, 8u * rB) << shB;
       if (pendA) res = (res & ~mA) | (gA & mA);
       if (pendB) res = (res & ~mB) | (gB & mB);
@@ -331,10 +358,10 @@ __device__ __forceinline__ void lzw_chunk(const LzwView& v, uint32_t P, uint32_t
       if (bal == 0) break;
       const uint32_t F = __shfl_sync(FULL, first, __ffs(static_cast<int>(bal)) - 1);
       const bool doA = pendA && lastA < F, doB = pendB && lastB < F;
-      const uint32_t a0 = doA ? *reinterpret_cast<const uint32_t*>(pA) : 0u;
-      const uint32_t a1 = (doA && hiA) ? *reinterpret_cast<const uint32_t*>(pA + 4) : 0u;
-      const uint32_t b0 = doB ? *reinterpret_cast<const uint32_t*>(pB) : 0u;
-      const uint32_t b1 = (doB && hiB) ? *reinterpret_cast<const uint32_t*>(pB + 4) : 0u;
+      const uint32_t a0 = doA ? lzw_ld32<CG>(pA) : 0u;
+      const uint32_t a1 = (doA && hiA) ? lzw_ld32<CG>(pA + 4) : 0u;
+      const uint32_t b0 = doB ? lzw_ld32<CG>(pB) : 0u;
+      const uint32_t b1 = (doB && hiB) ? lzw_ld32<CG>(pB + 4) : 0u;
       const uint32_t gA = lz_funnel(a0, a1, 8u * rA), gB = lz_funnel(b0, b1, 8u * rB) << shB;
       if (doA) res = (res & ~mA) | (gA & mA);
       if (doB) res = (res & ~mB) | (gB & mB);
@@ -369,7 +396,7 @@ __device__ __forceinline__ void lzw_chunk(const LzwView& v, uint32_t P, uint32_t
 #pragma unroll
     for (uint32_t b = 0; b < 4; ++b) {
       if (((pend >> b) & 1u) && src[b] < F) {
-        const uint32_t byte = base[src[b]];
+        const uint32_t byte = lzw_ld8<CG>(base + src[b]);
         res = lz_prmt(res, byte, 0x3210u ^ ((0x4u ^ b) << (4u * b)));  // byte b <- `byte`
         pend &= ~(1u << b);
       }
@@ -386,11 +413,12 @@ __device__ __forceinline__ void lzw_chunk(const LzwView& v, uint32_t P, uint32_t
 }
 
 // this lane's bitmap word of window W, restricted to the stream's own bytes
+template <bool CG>
 __device__ __forceinline__ uint32_t lzw_window_bits(const LzwView& v, uint32_t W)
 {
   const uint32_t pos0 = W + 32u * v.lane;
   if (pos0 >= v.end || pos0 + 32u <= v.q) return 0u;
-  uint32_t w = v.bits[pos0 >> 5];
+  uint32_t w = lzw_ld32<CG>(v.bits + (pos0 >> 5));
   if (pos0 < v.q) w &= 0xffffffffu << (v.q - pos0);
   if (pos0 + 32u > v.end) w &= 0xffffffffu >> (pos0 + 32u - v.end);
   return w;
