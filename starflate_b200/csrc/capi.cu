@@ -73,6 +73,10 @@ struct sfb200_ctx {
   int lzw_minb = 5;            // lz_window_kernel instantiation (register budget for 4 / 5 / 6 CTAs per SM;
                                // measured with the long periodic fill in: 5 (48 registers) beats 6 (40, spills
                                // in the chunk loop) on C2 8.5 / 8.9 ms and C4 5.0 / 5.5 ms — SFB200_LZW_CTAS)
+  uint8_t* d_queue = nullptr;  // hand-over queue of the overlapped mode (QueueArgs): counters, turns, states, items
+  uint64_t d_queue_cap = 0;
+  int queue_mode = 0;          // SFB200_QUEUE=1: pass 2 runs beside pass 1 (lz_window_queue_kernel)
+  int queue_ctas = 4;          // ... with this many of its CTAs per SM on the second stream (SFB200_QUEUE_CTAS)
   bool compress_configured = false;
   int compress_ctas_per_sm = 0;
   bool no_stored = false;      // SFB200_NO_STORED=1: stored streams go through the lane kernel like the others (A/B runs)
@@ -221,6 +225,8 @@ int sfb200_create(int device, sfb200_ctx** out)
     if (const char* e = std::getenv("SFB200_LZ_V1")) ctx->lz_v1 = e[0] == '1';
     if (const char* e = std::getenv("SFB200_NO_PAIR")) ctx->no_pair = e[0] == '1';
     if (const char* e = std::getenv("SFB200_NO_STORED")) ctx->no_stored = e[0] == '1';
+    if (const char* e = std::getenv("SFB200_QUEUE")) ctx->queue_mode = std::atoi(e);
+    if (const char* e = std::getenv("SFB200_QUEUE_CTAS")) ctx->queue_ctas = std::max(1, std::atoi(e));
     static_assert(sfb::LZ_THREADS == sfb::LZW_THREADS, "one launch geometry for both pass-2 kernels");
     static_assert(LaneCfg::WARPS == WideCfg::WARPS, "the wide launch takes the CTA count computed for the large one");
     int lz_per_sm = 0;
@@ -236,6 +242,17 @@ int sfb200_create(int device, sfb200_ctx** out)
             cudaSuccess ||
         lz_per_sm < 1)
       return bail(SFB200_RC_CUDA_ERROR);
+    // The queue-mode pass 2 must be able to share an SM with pass 1: an SM changes its shared-memory
+    // carve-out only when it is idle, so a kernel that asks for none of it, once resident, keeps
+    // pass 1 (112 KiB per CTA) off that SM for as long as it runs — ask for pass 1's carve-out.
+    if (ctx->queue_mode) {
+      const void* lzq = ctx->lzw_minb == 4   ? reinterpret_cast<const void*>(sfb::lz_window_queue_kernel<4>)
+                        : ctx->lzw_minb == 5 ? reinterpret_cast<const void*>(sfb::lz_window_queue_kernel<5>)
+                                             : reinterpret_cast<const void*>(sfb::lz_window_queue_kernel<6>);
+      if (cudaFuncSetAttribute(lzq, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) !=
+          cudaSuccess)
+        return bail(SFB200_RC_CUDA_ERROR);
+    }
     // fewer resident warps keep the streams' 32 KiB windows inside the L2
     int cap = SFB_LZ_CTAS_PER_SM;
     if (const char* e = std::getenv("SFB200_LZ_CTAS_PER_SM")) cap = std::atoi(e);
@@ -320,6 +337,7 @@ void sfb200_destroy(sfb200_ctx* ctx)
   cudaFree(ctx->d_cont);
   cudaFree(ctx->d_defer);
   cudaFree(ctx->d_order);
+  cudaFree(ctx->d_queue);
   cudaFree(ctx->d_src);
   cudaFree(ctx->d_dst);
   for (int k = 0; k < 3; ++k) {
@@ -342,6 +360,17 @@ void sfb200_destroy(sfb200_ctx* ctx)
 }
 
 const char* sfb200_last_error(const sfb200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+// Diagnostic of the experimental queue mode (SFB200_QUEUE=1; not part of the declared ABI): waits for
+// the device and copies the queue's eight counters — tail, head, final_tail, done, dbg[0..3].
+int sfb200_debug_queue(sfb200_ctx* ctx, unsigned long long* out8)
+{
+  if (!ctx || !out8 || !ctx->d_queue) return SFB200_RC_BAD_ARGUMENT;
+  SFB_ENTER(ctx);
+  SFB_TRY(ctx, cudaDeviceSynchronize());
+  SFB_TRY(ctx, cudaMemcpy(out8, ctx->d_queue, 64, cudaMemcpyDeviceToHost));
+  return SFB200_RC_OK;
+}
 
 int sfb200_get_launch_info(sfb200_ctx* ctx, sfb200_launch_info* out)
 {
@@ -530,9 +559,24 @@ int batch_device_impl(sfb200_ctx* ctx, const uint8_t* src_base, const uint64_t* 
   // (C2: 21.8 ms overlapped, 20.2 ms back to back); from three waves on it pays (131 072 streams:
   // 218 against 200 GB/s).
   if (n_waves == 2) n_waves = 1;
+  // Queue mode: ONE launch of pass 1, pass 2 beside it on the second stream, fed segment by segment
+  // (deflate_lane.cuh: QueueArgs; lz_window.cuh: lz_window_queue_kernel).
+  const bool qmode = ctx->queue_mode != 0 && !stream_mode && !use_small && !resume && !jump && !ctx->lz_v1;
+  uint64_t qcap = 0;
+  if (qmode) {
+    n_waves = 1;
+    qcap = 2 * n + ((dst_bytes + delta) >> sfb::Q_SEG_SHIFT) + 64;
+    const int rc = grow(ctx, &ctx->d_queue, &ctx->d_queue_cap, 64 + 24 * n + 8 * qcap + 64);
+    if (rc != SFB200_RC_OK) return rc;
+  }
   const uint64_t per_wave = n_waves == 1 ? n : wave;
-  const bool overlap = n_waves > 1;
+  const bool overlap = n_waves > 1 || qmode;
   if (overlap) {
+    if (!ctx->ps[0]) {  // pass 1's stream: the higher priority (its CTAs are placed first)
+      int lo = 0, hi = 0;
+      SFB_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      SFB_TRY(ctx, cudaStreamCreateWithPriority(&ctx->ps[0], cudaStreamNonBlocking, hi));
+    }
     for (auto& ps : ctx->ps)
       if (!ps) SFB_TRY(ctx, cudaStreamCreateWithFlags(&ps, cudaStreamNonBlocking));
     for (uint64_t k = ctx->wave_ev.size(); k < n_waves + 3; ++k) {
@@ -549,6 +593,7 @@ int batch_device_impl(sfb200_ctx* ctx, const uint8_t* src_base, const uint64_t* 
                                kCountersPerWave * std::max<uint64_t>(n_waves, 1) * sizeof(unsigned long long), st));
   SFB_TRY(ctx, cudaMemsetAsync(ctx->d_counter + kCountersPerWave * kMaxWaves, 0, 16 * sizeof(unsigned long long), st));
   SFB_TRY(ctx, cudaMemsetAsync(ctx->d_bits, 0, bits_words * sizeof(uint32_t), st));
+  if (qmode) SFB_TRY(ctx, cudaMemsetAsync(ctx->d_queue, 0, 64 + 24 * n + 8 * qcap, st));
   // Order the streams by the type of their first block (see lz_warp.cuh: PrepArgs)
   uint8_t* handled = nullptr;
   bool sorted = n >= 64 && n < 0xffffffffull && !stream_mode && !resume;
@@ -613,7 +658,7 @@ int batch_device_impl(sfb200_ctx* ctx, const uint8_t* src_base, const uint64_t* 
     unsigned long long* const ctr = ctx->d_counter + kCountersPerWave * k;
     const uint32_t* const order = sorted ? ctx->d_order + first : nullptr;
     // pass 1: Huffman layer, one lane per stream
-    sfb::BatchArgs a;
+    sfb::BatchArgs a{};
     a.src_base = src_base;
     a.src_off = src_off;
     a.src_len = src_len;
@@ -636,6 +681,20 @@ int batch_device_impl(sfb200_ctx* ctx, const uint8_t* src_base, const uint64_t* 
     a.start_bit = resume ? resume->start_bit : nullptr;
     a.start_out = resume ? resume->start_out : nullptr;
     a.blk_end = resume ? resume->blk_end : nullptr;
+    if (qmode) {
+      unsigned long long* const c = reinterpret_cast<unsigned long long*>(ctx->d_queue);
+      a.q.tail = c + 0;
+      a.q.head = c + 1;
+      a.q.final_tail = c + 2;
+      a.q.done = reinterpret_cast<unsigned int*>(c + 3);
+      a.q.dbg = c + 4;
+      a.q.turn = reinterpret_cast<unsigned int*>(ctx->d_queue + 64);
+      a.q.state = reinterpret_cast<uint32_t*>(ctx->d_queue + 64 + 4 * n);
+      a.q.items = reinterpret_cast<unsigned long long*>(ctx->d_queue + 64 + 24 * n);
+      a.q.cap = qcap;
+      a.q.seg_shift = sfb::Q_SEG_SHIFT;
+      a.q.lag = sfb::Q_LAG;
+    }
     const uint64_t groups = (cnt + 31) / 32;
     if (stream_mode) {
       sfb::StreamArgs sa;
@@ -760,7 +819,7 @@ int batch_device_impl(sfb200_ctx* ctx, const uint8_t* src_base, const uint64_t* 
       SFB_TRY(ctx, cudaGetLastError());
       ctx->launches += 1;
     }
-    if (overlap) {
+    if (overlap && !qmode) {
       SFB_TRY(ctx, cudaEventRecord(ctx->wave_ev[k], s1));
       SFB_TRY(ctx, cudaStreamWaitEvent(s2, ctx->wave_ev[k], 0));
     }
@@ -776,7 +835,28 @@ int batch_device_impl(sfb200_ctx* ctx, const uint8_t* src_base, const uint64_t* 
     r.idx_base = first;
     r.todo_list = order;
     r.stream_counter = ctr + 2;
-    if (jump) {
+    if (qmode) {
+      // beside pass 1 (second stream), and the rest of the GPU's worth behind it (its own stream)
+      // (beside pass 1: CTAs of 4 warps — 6 144 registers, what is left next to two CTAs of pass 1 —
+      //  and few enough of them that pass 1 finds room on some SM whatever the order the two kernels
+      //  start in: its stream has the higher priority, but nothing in CUDA promises the order)
+      const unsigned per_sm = static_cast<unsigned>(ctx->lz_ctas_per_sm);
+      const unsigned qa = std::min<unsigned>(static_cast<unsigned>(ctx->queue_ctas), 4u);
+      const unsigned grid_a = static_cast<unsigned>(ctx->sm_count) * qa;
+      const unsigned grid_b = static_cast<unsigned>(ctx->sm_count) * std::max(1u, per_sm - qa / 2u);
+      if (ctx->lzw_minb == 4) {
+        sfb::lz_window_queue_kernel<4><<<grid_a, 128, 0, s2>>>(r, a.q);
+        sfb::lz_window_queue_kernel<4><<<grid_b, sfb::LZW_THREADS, 0, s1>>>(r, a.q);
+      } else if (ctx->lzw_minb == 5) {
+        sfb::lz_window_queue_kernel<5><<<grid_a, 128, 0, s2>>>(r, a.q);
+        sfb::lz_window_queue_kernel<5><<<grid_b, sfb::LZW_THREADS, 0, s1>>>(r, a.q);
+      } else {
+        sfb::lz_window_queue_kernel<6><<<grid_a, 128, 0, s2>>>(r, a.q);
+        sfb::lz_window_queue_kernel<6><<<grid_b, sfb::LZW_THREADS, 0, s1>>>(r, a.q);
+      }
+      SFB_TRY(ctx, cudaGetLastError());
+      ctx->launches += 1;
+    } else if (jump) {
       sfb::JumpArgs j;
       j.dst_base = dst_base;
       j.dst_delta = delta;
@@ -867,7 +947,7 @@ int sfb200_decompressed_size_batch_device(sfb200_ctx* ctx, const uint8_t* src_ba
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   ctx->ev_valid = false;
   SFB_TRY(ctx, cudaMemsetAsync(ctx->d_counter, 0, kCountersPerWave * sizeof(unsigned long long), st));
-  sfb::BatchArgs a;
+  sfb::BatchArgs a{};
   a.src_base = src_base;
   a.src_off = src_off;
   a.src_len = src_len;

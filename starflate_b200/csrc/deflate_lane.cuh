@@ -45,6 +45,38 @@ constexpr int SCR_COUNT = 72;       // [72,104)  count | offset << 16 per length
 constexpr int SCR_SORTED = 104;     // [104,264) symbols in canonical order as u16: lit/len 0..287, distance 288..319
 constexpr int SCRATCH_WORDS = 264;
 
+// Hand-over from pass 1 to a pass 2 that runs BESIDE it (lz_window.cuh: lz_window_queue_kernel): a
+// lane publishes every SEG bytes of output it has left behind — item (stream, k) says "the first
+// (k + 1) SEG + LAG bytes of this stream's pass-1 output are in memory" — and one final item per
+// stream once status and written are.  Items are 64-bit words, 0 = not there yet.
+struct QueueArgs {
+  unsigned long long* items;       // null: no queue (pass 2 runs after pass 1)
+  unsigned long long cap;          // slots in `items` (more than there will ever be items)
+  unsigned long long* tail;        // producers
+  unsigned long long* head;        // consumers
+  unsigned long long* final_tail;  // the number of items there will ever be, once done[1] is set
+  unsigned int* done;              // [0] pass-1 CTAs that have exited, [1] all of them have
+  unsigned long long* dbg;         // [0] != 0: a consumer gave up waiting (1 = for an item, 2 = for its turn); [1..3] what for
+  unsigned int* turn;              // per stream: the segment whose turn it is
+  uint32_t* state;                 // per stream: 5 words a segment hands to the next (LzwState)
+  uint32_t seg_shift;              // SEG = 1 << seg_shift bytes of output
+  uint32_t lag;                    // LAG
+};
+constexpr uint32_t Q_SEG_SHIFT = 14;
+constexpr uint32_t Q_LAG = 4096;   // >= a window (1024) + the look-ahead of a dense window (1024 + 256 + 8) + a match (258) + slack
+
+__device__ __forceinline__ void q_push(const QueueArgs& q, uint64_t idx, uint32_t k, bool fin)
+{
+#ifndef SFB_CPU_EMU
+  __threadfence();   // what this lane stored so far is visible before the item is
+  const unsigned long long at = atomicAdd(q.tail, 1ull);
+  *reinterpret_cast<volatile unsigned long long*>(q.items + at) =
+      ((idx + 1ull) << 24) | (static_cast<unsigned long long>(k) << 1) | (fin ? 1ull : 0ull);
+#else
+  (void)q; (void)idx; (void)k; (void)fin;
+#endif
+}
+
 struct BatchArgs {
   const uint8_t* src_base;
   const uint64_t* src_off;
@@ -76,6 +108,7 @@ struct BatchArgs {
   const uint64_t* start_bit;
   const uint64_t* start_out;
   uint64_t* blk_end;
+  QueueArgs q;                              // q.items null: no hand-over queue
 };
 
 // ---------------------------------------------------------------------------------------------

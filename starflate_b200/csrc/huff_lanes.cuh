@@ -61,6 +61,7 @@ struct TokWin {
   uint64_t obuf;
   uint64_t first;   // word 0 of an unaligned dst once the cursor has left it: its bytes before
                     // `lead` are not ours, so it is written bytewise at the end (flush_tail)
+  bool first_out;   // word 0's own bytes are in memory already (publish()): flush_tail leaves them alone
   uint8_t* fbase;   // match-head bitmap, byte granular: the bits of word wv live in fbase[wv >> 3]
                     // (dst_base is 128-byte aligned, so address words and bitmap bytes line up)
   uint32_t fb;      // head bits of the open word
@@ -74,6 +75,7 @@ struct TokWin {
     vend = lead + cap;
     obuf = 0;
     first = 0;
+    first_out = false;
     fbase = reinterpret_cast<uint8_t*>(bits) + ((off - lead) >> 3);
     fb = 0;
   }
@@ -82,6 +84,7 @@ struct TokWin {
     al = nullptr;
     lead = vpos = vend = 0;
     obuf = first = 0;
+    first_out = false;
     fbase = nullptr;
     fb = 0;
   }
@@ -160,11 +163,21 @@ struct TokWin {
     for (uint32_t b = wv < lead ? lead : wv; b < vpos; ++b)
       obuf |= static_cast<uint64_t>(al[b]) << (8 * (b - wv));
   }
+  // Everything below the open word is in memory — except word 0 of an unaligned dst, which is kept
+  // back: before the first bytes of the stream are handed to a pass 2 that runs beside this one it
+  // goes out too (pass 2 may rewrite those bytes: flush_tail must not put the old ones back).
+  __device__ __forceinline__ void release_first()
+  {
+    if (lead != 0 && vpos >= 8u && !first_out) {
+      for (uint32_t b = lead; b < 8; ++b) al[b] = static_cast<uint8_t>(first >> (8 * b));
+      first_out = true;
+    }
+  }
   // called once, when the stream ends for any reason
   __device__ __forceinline__ void flush_tail()
   {
     spill_pending();
-    if (lead != 0 && vpos >= 8u)  // the cursor left word 0: its bytes from `lead` on are still pending
+    if (lead != 0 && vpos >= 8u && !first_out)  // the cursor left word 0: its bytes from `lead` on are still pending
       for (uint32_t b = lead; b < 8; ++b) al[b] = static_cast<uint8_t>(first >> (8 * b));
     if (fb) or_bits(vpos & ~7u, fb);
     fb = 0;
@@ -194,6 +207,7 @@ struct CountWin {
   __device__ __forceinline__ void spill_pending() const {}
   __device__ __forceinline__ void jump(uint32_t n) { vpos += n; }
   __device__ __forceinline__ void flush_tail() const {}
+  __device__ __forceinline__ void release_first() const {}
 };
 
 __device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src)
@@ -254,6 +268,7 @@ huff_lanes_kernel(const BatchArgs a)
   const uint64_t n_todo = a.todo_count ? static_cast<uint64_t>(*a.todo_count) : a.n;
   const uint64_t n_groups = (n_todo + 31) / 32;
   const bool pair_on = a.no_pair == 0;
+  const bool qon = !COUNT && a.q.items != nullptr;
   // per-lane table state that outlives a stream (see parse_block_header)
   bool tables_fixed = false;
   LongTab<C::ROOT_LIT> lt_lit;     // canonical first/count of the codes longer than the LUT roots
@@ -285,7 +300,13 @@ huff_lanes_kernel(const BatchArgs a)
     uint32_t copy_left = 0;
     bool live = slot < n_todo;
     bool first_header = true;  // nothing of this stream has been decided yet
-    if (live && a.handled != nullptr && a.handled[idx] != 0) live = false;  // (a stream of stored blocks: done already)
+    // hand-over to a pass 2 that runs beside this kernel (QueueArgs): the next segment to publish and
+    // the cursor position from which it may be (never reached without a queue)
+    uint32_t pub_k = 0, pub_at = 0xffffffffu;
+    if (live && a.handled != nullptr && a.handled[idx] != 0) {  // (a stream of stored blocks: done already)
+      live = false;
+      if (qon) q_push(a.q, idx, 0u, true);
+    }
     if (live) {
       const uint64_t slen = a.src_len[idx];
       const uint64_t cap = COUNT ? 0xfffffef0ull : a.dst_cap[idx];
@@ -293,6 +314,7 @@ huff_lanes_kernel(const BatchArgs a)
         a.status[idx] = ST_ERROR;  // outside the batch precondition
         a.written[idx] = 0;
         live = false;
+        if (qon) q_push(a.q, idx, 0u, true);
       } else {
         br.open(a.src_base + a.src_off[idx], static_cast<uint32_t>(slen), ring);
         ow.open(a.dst_base, COUNT ? 0ull : a.dst_off[idx] + a.dst_delta, static_cast<uint32_t>(cap), a.match_bits);
@@ -301,8 +323,18 @@ huff_lanes_kernel(const BatchArgs a)
           ow.jump(static_cast<uint32_t>(a.start_out[idx]));
         }
         state = S_HEADER;
+        if (qon) pub_at = ow.lead + (1u << a.q.seg_shift) + a.q.lag + 8u;
       }
     }
+    // every word below the open one is in memory: publish the segments that lie LAG bytes behind it
+    auto publish = [&]() {
+      ow.release_first();
+      do {
+        q_push(a.q, idx, pub_k, false);
+        ++pub_k;
+        pub_at += 1u << a.q.seg_shift;
+      } while (ow.vpos >= pub_at);
+    };
 
     while (__any_sync(FULL, state != S_DONE)) {
       if (state == S_HEADER) {
@@ -366,6 +398,7 @@ huff_lanes_kernel(const BatchArgs a)
           state = final_block ? S_DONE : S_HEADER;
         }
       }
+      if (ow.vpos >= pub_at) publish();
       // ---- token iterations (all 32 lanes stay in this loop together) -----------------------
       uint32_t it = 0;
       // software pipeline: the output step of a token is deferred to the start of the next
@@ -395,6 +428,7 @@ huff_lanes_kernel(const BatchArgs a)
         const uint32_t bits_hi = funnel_r(br.w1, br.w2, bo0);   // window bits [32, 64) from the token start
         const uint32_t e1 = lds16(lutb + (C::LIT_OFF * 64) + ((bits0 << 6) & (((1u << C::ROOT_LIT) - 1u) << 6)));
         ow.emit(p_chunk, p_n, p_skip, p_mt, p_hoff);   // (the previous iteration's output step)
+        if (ow.vpos >= pub_at) publish();
         const bool pre1 = dec & !tail & (ow.room() != 0u) & ((ow.vpos & 7u) != 7u) & pair_on;
         // a literal entry has bits 12-15 clear and its code length (1 .. ROOT_LIT) in bits 0-3
         const uint32_t t1 = e1 & 0xf00fu;
@@ -526,9 +560,24 @@ huff_lanes_kernel(const BatchArgs a)
         a.status[idx] = static_cast<uint8_t>(status);
         a.written[idx] = ow.written();
         live = false;
+        if (qon) q_push(a.q, idx, pub_k, true);
+        pub_at = 0xffffffffu;   // (the lane idles until its warp's other streams end: nothing more to publish)
       }
     }
   }
+#ifndef SFB_CPU_EMU
+  if (qon) {  // the last CTA to leave tells the consumers how many items there are
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(a.q.done, 1u) == gridDim.x - 1u) {
+        *reinterpret_cast<volatile unsigned long long*>(a.q.final_tail) = atomicAdd(a.q.tail, 0ull);
+        __threadfence();
+        *reinterpret_cast<volatile unsigned int*>(a.q.done + 1) = 1u;
+      }
+    }
+  }
+#endif
 }
 
 }  // namespace sfb

@@ -27,6 +27,7 @@
 #pragma once
 
 #include "lz_warp.cuh"
+#include "deflate_lane.cuh"
 
 namespace sfb {
 
@@ -424,6 +425,144 @@ __device__ __forceinline__ uint32_t lzw_window_bits(const LzwView& v, uint32_t W
   return w;
 }
 
+// What one warp carries along a stream, and what lz_window_queue_kernel hands from one segment of a
+// stream to the next.
+struct LzwState {
+  uint32_t W;                  // the window being worked on (view position, multiple of 1024)
+  uint32_t cur;                // every byte below cur is final (dense mode: see c_*)
+  uint32_t c_o, c_end, c_d;    // dense mode: the most recent match, may reach past cur
+};
+
+// Windows W <= ... < w_stop of the stream in view `v` (v.end bounds what may be read at all; `look`
+// bounds how far ahead a run of matches may be looked for — both the end of the stream when all of
+// it is there).
+template <bool CG>
+__device__ __forceinline__ void lzw_run(const LzwView& v, LzwState& s, uint32_t w_stop, uint32_t look)
+{
+  constexpr unsigned FULL = 0xffffffffu;
+  const uint32_t lane = v.lane;
+  const uint32_t end = v.end;
+  uint32_t cur = s.cur, c_o = s.c_o, c_end = s.c_end, c_d = s.c_d;
+  uint32_t pre_P = LZW_NONE, pre_w = 0, pre_w1 = 0;  // the words of chunks pre_P and pre_P + 128, loaded ahead
+                                                     // (valid while nothing was written there)
+  uint32_t W = s.W;
+  uint32_t wbits = (W < end && W < w_stop) ? lzw_window_bits<CG>(v, W) : 0u;
+  while (W < end && W < w_stop) {
+    if (cur >= W + 1024u) {  // a run went past this window
+      W = cur & ~1023u;
+      if (W >= end || W >= w_stop) break;
+      wbits = lzw_window_bits<CG>(v, W);
+      continue;
+    }
+    const uint32_t pos0 = W + 32u * lane;
+    uint32_t mine = wbits;  // heads at or after cur
+    if (cur > pos0) mine = cur - pos0 >= 32u ? 0u : mine & (0xffffffffu << (cur - pos0));
+    uint32_t cnt = lzw_popc(mine);
+    cnt = __reduce_add_sync(FULL, cnt);
+    const uint32_t wend = W + 1024u < end ? W + 1024u : end;
+    if (c_end > cur && (cnt <= LZW_SPARSE_MAX || c_end - cur >= 128u)) {
+      // the match carried out of a dense chunk: finish it in one go
+      const uint32_t e = c_end;
+      lzw_fill<CG>(v, cur, e, c_d);
+      cur = e;
+      c_end = 0;
+      pre_P = LZW_NONE;
+      continue;
+    }
+    if (cnt <= LZW_SPARSE_MAX && c_end <= cur) {
+      // ---- sparse window: one match (or run of matches) at a time ---------------------------
+      if (cnt) pre_P = LZW_NONE;
+      while (cnt) {
+        uint32_t m2 = wbits;
+        if (cur > pos0) m2 = cur - pos0 >= 32u ? 0u : m2 & (0xffffffffu << (cur - pos0));
+        const uint32_t bal = __ballot_sync(FULL, m2 != 0);
+        if (bal == 0) break;
+        const int fl = __ffs(static_cast<int>(bal)) - 1;
+        const uint32_t fm = __shfl_sync(FULL, m2, fl);
+        const uint32_t h = W + 32u * static_cast<uint32_t>(fl) + static_cast<uint32_t>(__ffs(static_cast<int>(fm)) - 1);
+        const uint32_t desc = lzw_desc<CG>(v.base, h);
+        const uint32_t L = (desc & 255u) + 3u, D = (desc >> 8) + 1u;
+        uint32_t run_end = h + L;
+        if (L == 258u) {
+          // is this the first of a run of back-to-back matches with the same distance?  Lane i
+          // looks at h + i L (lane 0 at the head itself).
+          const uint32_t g = h + lane * L;
+          bool okD = false, ok = false;
+          uint32_t Lg = 0;
+          if (g + 3u <= look && ((lzw_ld32<CG>(v.bits + (g >> 5)) >> (g & 31u)) & 1u)) {
+            const uint32_t dg = lzw_desc<CG>(v.base, g);
+            Lg = (dg & 255u) + 3u;
+            okD = (dg >> 8) + 1u == D;
+            ok = okD && Lg == L;
+          }
+          const uint32_t okm = __ballot_sync(FULL, ok), okDm = __ballot_sync(FULL, okD);
+          const uint32_t f = okm == FULL ? 32u : static_cast<uint32_t>(__ffs(static_cast<int>(~okm)) - 1);  // >= 1
+          run_end = h + f * L;
+          const uint32_t Lf = __shfl_sync(FULL, Lg, static_cast<int>(f & 31u));
+          if (f < 32u && ((okDm >> f) & 1u)) run_end += Lf;  // a shorter last one
+        }
+        __syncwarp();  // every lane has read the descriptor(s) before the fill overwrites them
+        lzw_fill<CG>(v, h, run_end, D);
+        cur = run_end;
+        if (cur >= wend) break;
+      }
+      if (cur < wend) cur = wend;
+      if (cur >= W + 1024u || cur >= end) {
+        W += 1024u;
+        if (W < end && W < w_stop) wbits = lzw_window_bits<CG>(v, W);
+      }
+      continue;
+    }
+    // ---- dense window: 128-byte chunks --------------------------------------------------------
+    // (chunk words are loaded TWO chunks ahead and the next window's bitmap word one window ahead:
+    //  a chunk's own loads never wait for memory; chunk P only writes inside [P, P + 128))
+    const uint32_t nwb = lzw_window_bits<CG>(v, W + 1024u);
+    if (W + 2048u < end) lzw_prefetch(v.base + W + 2048u + 32u * lane);
+    {
+      uint32_t P = cur & ~127u;
+      const uint32_t lo = cur;  // (bytes below are final or not ours)
+      auto load_w = [&](uint32_t PP) -> uint32_t {
+        const uint32_t wp = PP + 4u * lane;
+        return (wp + 4u > v.q && wp < end) ? lzw_ldw<CG>(v.base, wp) : 0u;
+      };
+      uint32_t cw, ncw;
+      if (pre_P == P) {
+        cw = pre_w;
+        ncw = pre_w1;
+      } else {
+        cw = load_w(P);
+        ncw = load_w(P + 128u);
+      }
+      bool stopped = false;
+      for (; P < wend; P += 128u) {
+        if (c_end >= P + 128u && c_end > cur && P >= lo) {  // the carried match covers the whole chunk: fill it
+          stopped = true;
+          break;
+        }
+        const uint32_t nncw = load_w(P + 256u);
+        const uint32_t mw = __shfl_sync(FULL, wbits, static_cast<int>(((P - W) >> 5) + (lane >> 3)));
+        const uint32_t hb4 = (mw >> (4u * (lane & 7u))) & 15u;
+        if (P >= lo && P + 128u <= end) lzw_chunk<false, CG>(v, P, lo, end, cw, ncw, hb4, c_o, c_end, c_d);
+        else lzw_chunk<true, CG>(v, P, lo, end, cw, ncw, hb4, c_o, c_end, c_d);
+        cw = ncw;
+        ncw = nncw;
+        cur = P + 128u < end ? P + 128u : end;
+      }
+      pre_P = P;
+      pre_w = cw;
+      pre_w1 = ncw;
+      if (stopped) continue;  // (the fill branch above takes it from here)
+    }
+    W += 1024u;
+    wbits = nwb;
+  }
+  s.W = W;
+  s.cur = cur;
+  s.c_o = c_o;
+  s.c_end = c_end;
+  s.c_d = c_d;
+}
+
 // MINB: resident CTAs per SM the register allocation aims at (capi.cu picks the instantiation)
 template <int MINB>
 __global__ void __launch_bounds__(LZW_THREADS, MINB) lz_window_kernel(const ResolveArgs a)
@@ -445,123 +584,158 @@ __global__ void __launch_bounds__(LZW_THREADS, MINB) lz_window_kernel(const Reso
     v.q = static_cast<uint32_t>(off & 1023u);
     v.end = v.q + static_cast<uint32_t>(wr);
     v.lane = lane;
-    const uint32_t end = v.end;
-    uint32_t cur = v.q;                        // every byte below cur is final (dense mode: see c_*)
-    uint32_t c_o = 0, c_end = 0, c_d = 1;      // dense mode: the most recent match, may reach past cur
-    uint32_t pre_P = LZW_NONE, pre_w = 0, pre_w1 = 0;  // the words of chunks pre_P and pre_P + 128, loaded ahead
-                                                       // (valid while nothing was written there)
-    uint32_t W = 0;
-    uint32_t wbits = lzw_window_bits(v, 0);
-    while (W < end) {
-      if (cur >= W + 1024u) {  // a run went past this window
-        W = cur & ~1023u;
-        if (W >= end) break;
-        wbits = lzw_window_bits(v, W);
-        continue;
-      }
-      const uint32_t pos0 = W + 32u * lane;
-      uint32_t mine = wbits;  // heads at or after cur
-      if (cur > pos0) mine = cur - pos0 >= 32u ? 0u : mine & (0xffffffffu << (cur - pos0));
-      uint32_t cnt = lzw_popc(mine);
-      cnt = __reduce_add_sync(FULL, cnt);
-      const uint32_t wend = W + 1024u < end ? W + 1024u : end;
-      if (c_end > cur && (cnt <= LZW_SPARSE_MAX || c_end - cur >= 128u)) {
-        // the match carried out of a dense chunk: finish it in one go
-        const uint32_t e = c_end;
-        lzw_fill(v, cur, e, c_d);
-        cur = e;
-        c_end = 0;
-        pre_P = LZW_NONE;
-        continue;
-      }
-      if (cnt <= LZW_SPARSE_MAX && c_end <= cur) {
-        // ---- sparse window: one match (or run of matches) at a time ---------------------------
-        if (cnt) pre_P = LZW_NONE;
-        while (cnt) {
-          uint32_t m2 = wbits;
-          if (cur > pos0) m2 = cur - pos0 >= 32u ? 0u : m2 & (0xffffffffu << (cur - pos0));
-          const uint32_t bal = __ballot_sync(FULL, m2 != 0);
-          if (bal == 0) break;
-          const int fl = __ffs(static_cast<int>(bal)) - 1;
-          const uint32_t fm = __shfl_sync(FULL, m2, fl);
-          const uint32_t h = W + 32u * static_cast<uint32_t>(fl) + static_cast<uint32_t>(__ffs(static_cast<int>(fm)) - 1);
-          const uint32_t desc = lzw_desc(v.base, h);
-          const uint32_t L = (desc & 255u) + 3u, D = (desc >> 8) + 1u;
-          uint32_t run_end = h + L;
-          if (L == 258u) {
-            // is this the first of a run of back-to-back matches with the same distance?  Lane i
-            // looks at h + i L (lane 0 at the head itself).
-            const uint32_t g = h + lane * L;
-            bool okD = false, ok = false;
-            uint32_t Lg = 0;
-            if (g + 3u <= end && ((v.bits[g >> 5] >> (g & 31u)) & 1u)) {
-              const uint32_t dg = lzw_desc(v.base, g);
-              Lg = (dg & 255u) + 3u;
-              okD = (dg >> 8) + 1u == D;
-              ok = okD && Lg == L;
-            }
-            const uint32_t okm = __ballot_sync(FULL, ok), okDm = __ballot_sync(FULL, okD);
-            const uint32_t f = okm == FULL ? 32u : static_cast<uint32_t>(__ffs(static_cast<int>(~okm)) - 1);  // >= 1
-            run_end = h + f * L;
-            const uint32_t Lf = __shfl_sync(FULL, Lg, static_cast<int>(f & 31u));
-            if (f < 32u && ((okDm >> f) & 1u)) run_end += Lf;  // a shorter last one
-          }
-          __syncwarp();  // every lane has read the descriptor(s) before the fill overwrites them
-          lzw_fill(v, h, run_end, D);
-          cur = run_end;
-          if (cur >= wend) break;
-        }
-        if (cur < wend) cur = wend;
-        if (cur >= W + 1024u || cur >= end) {
-          W += 1024u;
-          if (W < end) wbits = lzw_window_bits(v, W);
-        }
-        continue;
-      }
-      // ---- dense window: 128-byte chunks --------------------------------------------------------
-      // (chunk words are loaded TWO chunks ahead and the next window's bitmap word one window ahead:
-      //  a chunk's own loads never wait for memory; chunk P only writes inside [P, P + 128))
-      const uint32_t nwb = lzw_window_bits(v, W + 1024u);
-      if (W + 2048u < end) lzw_prefetch(v.base + W + 2048u + 32u * lane);
-      {
-        uint32_t P = cur & ~127u;
-        const uint32_t lo = cur;  // (bytes below are final or not ours)
-        auto load_w = [&](uint32_t PP) -> uint32_t {
-          const uint32_t wp = PP + 4u * lane;
-          return (wp + 4u > v.q && wp < end) ? lzw_ldw(v.base, wp) : 0u;
-        };
-        uint32_t cw, ncw;
-        if (pre_P == P) {
-          cw = pre_w;
-          ncw = pre_w1;
-        } else {
-          cw = load_w(P);
-          ncw = load_w(P + 128u);
-        }
-        bool stopped = false;
-        for (; P < wend; P += 128u) {
-          if (c_end >= P + 128u && c_end > cur && P >= lo) {  // the carried match covers the whole chunk: fill it
-            stopped = true;
-            break;
-          }
-          const uint32_t nncw = load_w(P + 256u);
-          const uint32_t mw = __shfl_sync(FULL, wbits, static_cast<int>(((P - W) >> 5) + (lane >> 3)));
-          const uint32_t hb4 = (mw >> (4u * (lane & 7u))) & 15u;
-          if (P >= lo && P + 128u <= end) lzw_chunk<false>(v, P, lo, end, cw, ncw, hb4, c_o, c_end, c_d);
-          else lzw_chunk<true>(v, P, lo, end, cw, ncw, hb4, c_o, c_end, c_d);
-          cw = ncw;
-          ncw = nncw;
-          cur = P + 128u < end ? P + 128u : end;
-        }
-        pre_P = P;
-        pre_w = cw;
-        pre_w1 = ncw;
-        if (stopped) continue;  // (the fill branch above takes it from here)
-      }
-      W += 1024u;
-      wbits = nwb;
-    }
+    LzwState s;
+    s.W = 0;
+    s.cur = v.q;
+    s.c_o = 0;
+    s.c_end = 0;
+    s.c_d = 1;
+    lzw_run<false>(v, s, 0xffffffffu, v.end);
   }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Pass 2 BESIDE pass 1: the same work, taken from the queue pass 1 fills (deflate_lane.cuh:
+// QueueArgs) — item (stream, k) = "the first (k + 1) SEG + LAG bytes of this stream's pass-1 output
+// are in memory", plus one final item per stream.  A warp pops an item, waits until the stream's
+// earlier segments are done (they were popped before it, by warps that wait for nothing but their
+// own predecessors), takes the five words of state the previous segment left, resolves the windows
+// below (k + 1) SEG — never reading a byte at or above (k + 1) SEG + LAG - 16, never writing one at
+// or above (k + 1) SEG + 258 — and leaves its state for the next.  All loads go to the L2 (CG): an
+// L1 line may have been filled before a neighbouring stream's bytes in it were published.
+// Launched twice per batch: a few CTAs per SM on a second stream while pass 1 runs (whatever fits
+// beside its CTAs), and the rest of the GPU's worth behind pass 1 on its own stream; both drain the
+// one queue and leave when pass 1 has said how many items there are and all have been taken.
+#ifndef SFB_CPU_EMU
+__device__ __forceinline__ unsigned long long lzq_ld64(const unsigned long long* p)
+{
+  return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+__device__ __forceinline__ unsigned int lzq_ld32(const unsigned int* p)
+{
+  return *reinterpret_cast<const volatile unsigned int*>(p);
+}
+
+// Every wait of a consumer is bounded (Q_SPIN_CYCLES): a consumer that gives up records what it was
+// waiting for in q.dbg and raises the abort flag, which ends every other consumer too — the batch
+// call then fails (capi.cu checks the flag) instead of hanging the GPU.
+constexpr long long Q_SPIN_CYCLES = 3000000000ll;   // ~1.5 s at 1.9 GHz (a turn: waits for other consumers only)
+constexpr long long Q_IDLE_CYCLES = 8000000ll;      // ~4 ms (an item: the first ones take pass 1 ~2 ms)
+__device__ __forceinline__ void lzq_give_up(const QueueArgs& q, unsigned long long what, unsigned long long a0,
+                                            unsigned long long a1, unsigned long long a2)
+{
+  if (atomicCAS(q.dbg, 0ull, what) == 0ull) {
+    q.dbg[1] = a0;
+    q.dbg[2] = a1;
+    q.dbg[3] = a2;
+    __threadfence();
+  }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(LZW_THREADS, MINB) lz_window_queue_kernel(const ResolveArgs a, const QueueArgs q)
+{
+  constexpr unsigned FULL = 0xffffffffu;
+  const uint32_t lane = threadIdx.x & 31u;
+  for (;;) {
+    unsigned long long item = 0;
+    if (lane == 0) {
+      // Nothing is claimed before pass 1 has been seen alive (tail != 0): the hardware may have placed
+      // this kernel first and have no room left for pass 1, and waiting for it then would be a
+      // deadlock — a warp that has waited Q_IDLE_CYCLES for the first sign leaves (whatever is left
+      // over is taken by the launch behind pass 1).  Once pass 1 runs it needs nothing from here to
+      // finish, so a claimed slot is either filled or known to stay empty (done).
+      long long t0 = clock64();
+      bool alive = true;
+      while (lzq_ld64(q.tail) == 0ull && lzq_ld32(q.done + 1) == 0u) {
+        if (clock64() - t0 > Q_IDLE_CYCLES || lzq_ld64(q.dbg) != 0ull) {
+          alive = false;
+          break;
+        }
+        __nanosleep(1000);
+      }
+      if (alive) {
+        const unsigned long long i = atomicAdd(q.head, 1ull);
+        t0 = clock64();
+        for (; i < q.cap;) {   // (a slot past the end: more consumers than items — nothing will come)
+          item = lzq_ld64(q.items + i);
+          if (item) break;
+          if (lzq_ld32(q.done + 1) != 0u && i >= lzq_ld64(q.final_tail)) {
+            item = lzq_ld64(q.items + i);   // (nothing is pushed after `done`)
+            break;
+          }
+          if (lzq_ld64(q.dbg) != 0ull) break;
+          if (clock64() - t0 > Q_SPIN_CYCLES) {
+            lzq_give_up(q, 1ull, i, lzq_ld64(q.tail), lzq_ld32(q.done));
+            break;
+          }
+          __nanosleep(200);
+        }
+      }
+    }
+    item = __shfl_sync(FULL, item, 0);
+    if (item == 0) break;
+    const uint64_t si = (item >> 24) - 1ull;
+    const uint32_t k = static_cast<uint32_t>(item >> 1) & 0x7fffffu;
+    const bool fin = (item & 1ull) != 0;
+    bool bail = false;
+    if (lane == 0) {
+      const long long t0 = clock64();
+      while (lzq_ld32(q.turn + si) != k) {
+        if (lzq_ld64(q.dbg) != 0ull) { bail = true; break; }
+        if (clock64() - t0 > Q_SPIN_CYCLES) {
+          lzq_give_up(q, 2ull, si, k, lzq_ld32(q.turn + si));
+          bail = true;
+          break;
+        }
+        __nanosleep(100);
+      }
+    }
+    if (__shfl_sync(FULL, bail, 0)) break;
+    __threadfence();   // (what the producers of the item and of the turn stored is visible from here on)
+    const uint64_t off = a.dst_off[si] + a.dst_delta;
+    LzwView v;
+    v.base = a.dst_base + (off & ~1023ull);
+    v.bits = a.match_bits + ((off & ~1023ull) >> 5);
+    v.q = static_cast<uint32_t>(off & 1023u);
+    v.lane = lane;
+    LzwState s;
+    if (k == 0) {
+      s.W = 0;
+      s.cur = v.q;
+      s.c_o = 0;
+      s.c_end = 0;
+      s.c_d = 1;
+    } else {
+      const uint32_t* st = q.state + 5ull * si;
+      s.W = __ldcg(st + 0);
+      s.cur = __ldcg(st + 1);
+      s.c_o = __ldcg(st + 2);
+      s.c_end = __ldcg(st + 3);
+      s.c_d = __ldcg(st + 4);
+    }
+    if (fin) {
+      const uint64_t wr = __ldcg(a.written + si);
+      v.end = v.q + static_cast<uint32_t>(wr);
+      if (wr) lzw_run<true>(v, s, 0xffffffffu, v.end);
+    } else {
+      const uint32_t lim = v.q + ((k + 1u) << q.seg_shift);
+      v.end = lim + q.lag - 16u;
+      lzw_run<true>(v, s, lim & ~1023u, v.end);
+      if (lane == 0) {
+        uint32_t* st = q.state + 5ull * si;
+        st[0] = s.W;
+        st[1] = s.cur;
+        st[2] = s.c_o;
+        st[3] = s.c_end;
+        st[4] = s.c_d;
+        __threadfence();
+        *reinterpret_cast<volatile unsigned int*>(q.turn + si) = k + 1u;
+      }
+    }
+    __syncwarp();
+  }
+}
+#endif
 
 }  // namespace sfb

@@ -20,6 +20,8 @@ static unsigned long long emu_stat_deferred = 0;
 
 extern "C" void emu_lz_resolve(uint8_t* dst_base, const uint64_t* dst_off, const uint64_t* written,
                                const uint32_t* match_bits, uint64_t n);  // dst_base 128-byte aligned
+extern "C" void emu_lz_resolve_segments(uint8_t* dst_base, uint64_t dst_off, uint64_t written,
+                                        const uint32_t* match_bits, uint32_t seg_shift, uint32_t lag);
 
 // the in-place token format of huff_lanes.cuh, resolved byte by byte
 static void scalar_resolve(uint8_t* dst_base, uint64_t off, uint64_t written, const uint32_t* bits)
@@ -78,7 +80,7 @@ extern "C" int emu_decompress_batch(const uint8_t* src, const uint64_t* src_off,
     unsigned long long counter = 0;
     const uint64_t zero = 0;
     uint64_t wr = 0;
-    sfb::BatchArgs a;
+    sfb::BatchArgs a{};
     a.src_base = sp;
     a.src_off = &zero;
     a.src_len = &src_len[i];
@@ -121,7 +123,8 @@ extern "C" int emu_decompress_batch(const uint8_t* src, const uint64_t* src_off,
     }
     if (run_large) sfb::huff_lanes_kernel<EmuCfg>(a);
     if (wr > dst_cap[i]) return 2000 + static_cast<int>(i);
-    if (warp_pass2) emu_lz_resolve(dbase, &doff, &wr, bits.data(), 1);
+    if (warp_pass2 == 2) emu_lz_resolve_segments(dbase, doff, wr, bits.data(), 11, 4096);  // (2 KiB segments)
+    else if (warp_pass2) emu_lz_resolve(dbase, &doff, &wr, bits.data(), 1);
     else scalar_resolve(dbase, doff, wr, bits.data());
     if (written) written[i] = wr;
     for (uint8_t* q = dbuf.data(); q < dp; ++q)

@@ -40,3 +40,51 @@ extern "C" void emu_lz_resolve(uint8_t* dst_base, const uint64_t* dst_off, const
   for (auto& t : lanes) t.join();
   emu_warp = nullptr;
 }
+
+// The segment-wise form lz_window_queue_kernel uses (one stream; segments in order, state handed
+// from one to the next through memory, reads bounded by (k + 1) SEG + LAG - 16 as on the device):
+// the result must be what one lzw_run over the whole stream gives.
+extern "C" void emu_lz_resolve_segments(uint8_t* dst_base, uint64_t dst_off, uint64_t written,
+                                        const uint32_t* match_bits, uint32_t seg_shift, uint32_t lag)
+{
+  EmuWarp warp;
+  emu_warp = &warp;
+  uint32_t state[5] = {0, 0, 0, 0, 0};
+  std::vector<std::thread> lanes;
+  for (unsigned l = 0; l < 32; ++l)
+    lanes.emplace_back([&, l] {
+      threadIdx.x = l;
+      blockIdx.x = 0;
+      blockDim.x = 32;
+      gridDim.x = 1;
+      sfb::LzwView v;
+      v.base = dst_base + (dst_off & ~1023ull);
+      v.bits = match_bits + ((dst_off & ~1023ull) >> 5);
+      v.q = static_cast<uint32_t>(dst_off & 1023u);
+      v.lane = l;
+      // pass 1 publishes segment k once written >= (k + 1) SEG + LAG (+ 8): those get their own item
+      uint32_t k = 0;
+      for (;; ++k) {
+        sfb::LzwState s;
+        if (k == 0) {
+          s.W = 0; s.cur = v.q; s.c_o = 0; s.c_end = 0; s.c_d = 1;
+        } else {
+          s.W = state[0]; s.cur = state[1]; s.c_o = state[2]; s.c_end = state[3]; s.c_d = state[4];
+        }
+        const bool fin = written < (static_cast<uint64_t>(k + 1) << seg_shift) + lag + 8;
+        if (fin) {
+          v.end = v.q + static_cast<uint32_t>(written);
+          if (written) sfb::lzw_run<true>(v, s, 0xffffffffu, v.end);
+          break;
+        }
+        const uint32_t lim = v.q + ((k + 1u) << seg_shift);
+        v.end = lim + lag - 16u;
+        sfb::lzw_run<true>(v, s, lim & ~1023u, v.end);
+        __syncwarp();
+        if (l == 0) { state[0] = s.W; state[1] = s.cur; state[2] = s.c_o; state[3] = s.c_end; state[4] = s.c_d; }
+        __syncwarp();
+      }
+    });
+  for (auto& t : lanes) t.join();
+  emu_warp = nullptr;
+}

@@ -356,3 +356,23 @@ def test_compression_kernel_round_trips(emu, oracle):
     assert st == 4 and comp == b""
     st, comp = emu.compress(cases["run"], 100)                  # fits compressed, would not fit stored
     assert st == 0 and zlib.decompress(comp, -15) == cases["run"]
+
+
+def test_segment_wise_pass2_matches_one_run(emu, oracle):
+    """The form of pass 2 that runs beside pass 1 (lz_window_queue_kernel): a stream is resolved
+    segment by segment, the state handed on through memory, reads bounded by what pass 1 has
+    published.  Here with 2 KiB segments on crafted LZ shapes (runs across segment ends, matches
+    that straddle them, far and near sources) and on text: identical to the oracle."""
+    cases = [c for c in T.crafted_lz_streams() if c[2] > 7000][:60]
+    streams = [c[1] for c in cases]
+    caps = [c[2] for c in cases]
+    for kind, n, seed in (("dynamic", 40000, 5), ("repetitive", 70000, 6), ("dynamic", 9000, 7)):
+        plain, comp = T.make_stream(kind, n, seed)
+        streams.append(comp)
+        caps.append(len(plain))
+    b = T.Batch(streams, caps, dst_align=1)
+    dst_e, dst_o = b.new_dst(), b.new_dst()
+    st, wr = emu.decompress_batch(b, dst_e, warp_pass2=2)
+    ost, owr, _ = oracle.decompress_batch(b.src, b.src_off, b.src_len, dst_o, b.dst_off, b.dst_cap)
+    assert (ost == 0).all() and (st == ost).all() and (wr == owr).all()
+    assert (dst_e == dst_o).all()

@@ -74,6 +74,12 @@ def main():
                     res.append(ctx.last_pass_ms())
                     tot.append(e0.elapsed_time(e1))
             ok = int(d_st.max()) == 0 and bool(torch.equal(d_wr, d_dc))
+            qdbg = None
+            if env.get("SFB200_QUEUE", "0") != "0":  # the queue's counters: tail, head, final_tail, done, dbg[0..3]
+                import ctypes
+                buf = (ctypes.c_ulonglong * 8)()
+                if ctx.lib.sfb200_debug_queue(ctx.h, buf) == 0:
+                    qdbg = [int(x) for x in buf]
             for i in sample:
                 o, c = int(w["dst_off"][i]), int(w["dst_cap"][i])
                 ok = ok and zlib.crc32(d_dst[o:o + c].cpu().numpy().tobytes()) == int(w["crc"][i])
@@ -84,7 +90,7 @@ def main():
             t = float(np.median(tot))
             line = {"workload": wl, "variant": name, "env": env, "ok": bool(ok), "n": n, "total_out": w["total_out"],
                     "total_in": w["total_in"], "clear_ms": float(m[0]), "pass1_ms": float(m[1]), "pass2_ms": float(m[2]),
-                    "step_ms": t, "gbs": w["total_out"] / t / 1e6, "launch": ctx.launch_info()}
+                    "step_ms": t, "gbs": w["total_out"] / t / 1e6, "launch": ctx.launch_info(), "queue": qdbg}
             print(json.dumps(line), flush=True)
             if out:
                 out.write(json.dumps(line) + "\n")
