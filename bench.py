@@ -349,7 +349,7 @@ def main():
         except Exception:
             return None
 
-    def measure(name, w, steps, warmup, want_e2e, streams_total=None):
+    def measure(name, w, steps, warmup, want_e2e, streams_total=None, min_region_ms=0.0):
         """One workload on this rank's GPU: device-timed steps (CUDA events, max over ranks), the
         correctness gate, per-pass times, optionally the end-to-end number through host buffers."""
         n = w["n"]
@@ -390,6 +390,20 @@ def main():
             o, c = int(w["dst_off"][i]), int(w["dst_cap"][i])
             assert zlib.crc32(d_dst[o:o + c].cpu().numpy().tobytes()) == int(w["crc"][i]), f"stream {i}"
 
+        # the clock sampler must be up before the timed region starts (nvidia-smi takes ~0.1-0.5 s),
+        # and a secondary shape's region is stretched to several sampling periods (more steps — the
+        # headline keeps exactly the K steps it was asked for)
+        t_wait = time.time()
+        while sampler.proc is not None and not sampler.samples and time.time() - t_wait < 3.0:
+            time.sleep(0.01)
+        if min_region_ms > 0:
+            ew0, ew1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ew0.record()
+            step()
+            ew1.record()
+            torch.cuda.synchronize(dev)
+            est = max(sharding.max_over_ranks(ew0.elapsed_time(ew1), dev), 0.05)
+            steps = int(min(400, max(steps, np.ceil(min_region_ms / est))))
         launches0 = ctx.launch_info()["kernel_launches"]
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
@@ -526,10 +540,10 @@ def main():
         count = total * (rank + 1) // world - first
         ws = make_workload("c3", count, 65536, rank, first=first, shared_seeds=True)
         tot = {"total_out": total * 4096}
-        r = measure("c3", ws, max(3, min(args.steps, 5)), 3, False, streams_total=tot)
+        r = measure("c3", ws, max(3, min(args.steps, 5)), 3, False, streams_total=tot, min_region_ms=120.0)
         line["sharded"] = {"workload": f"c3: {total} x 4096 B pages (stored / fixed / dynamic by turns), ONE batch cut "
                                        f"into {world} contiguous shard(s), one per GPU, no collective",
-                           "scaling": "strong", "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"],
+                           "scaling": "strong", "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "steps": r["steps"],
                            "streams_total": total, "streams_this_rank": count, "roofline_frac": r["roofline"]["frac"],
                            "passes_ms": r["roofline"]["passes_ms"], "clocks": r["clocks"]}
         del ws
@@ -538,7 +552,7 @@ def main():
         shapes = {}
         for nm, ns, uq, st in (("c1", 1, 1, 5), ("c4", 16384, 128, 3), ("c5", 1, 1, 3)):
             wsh = make_workload(nm, ns, uq, rank)
-            r = measure(nm, wsh, st, 3, False)
+            r = measure(nm, wsh, st, 3, False, min_region_ms=120.0)
             shapes[nm] = {k: r[k] for k in ("workload", "value", "ms_per_step", "steps", "clocks", "gpu_launches", "l2")}
             shapes[nm]["unit"] = UNIT
             shapes[nm]["roofline"] = {k: r["roofline"][k] for k in ("achieved", "peak", "frac", "passes_ms", "algorithmic_bytes")}

@@ -238,7 +238,7 @@ constexpr uint32_t LANES = 32;
 // COUNT = true is the size-discovery mode (the reference returns no size and asks
 // the caller to know it): the same decode with a writer that stores nothing and no capacity
 // limit; status[i] / written[i] are what a decode into a large enough dst would return.
-template <class C, bool COUNT = false>
+template <class C, bool COUNT = false, bool QUEUE = false>   // QUEUE: publish segments to a pass 2 that runs beside (QueueArgs)
 __global__ void __launch_bounds__(C::WARPS * 32, C::CTAS)
 huff_lanes_kernel(const BatchArgs a)
 {
@@ -268,7 +268,7 @@ huff_lanes_kernel(const BatchArgs a)
   const uint64_t n_todo = a.todo_count ? static_cast<uint64_t>(*a.todo_count) : a.n;
   const uint64_t n_groups = (n_todo + 31) / 32;
   const bool pair_on = a.no_pair == 0;
-  const bool qon = !COUNT && a.q.items != nullptr;
+  constexpr bool qon = QUEUE && !COUNT;
   // per-lane table state that outlives a stream (see parse_block_header)
   bool tables_fixed = false;
   LongTab<C::ROOT_LIT> lt_lit;     // canonical first/count of the codes longer than the LUT roots
@@ -398,7 +398,7 @@ huff_lanes_kernel(const BatchArgs a)
           state = final_block ? S_DONE : S_HEADER;
         }
       }
-      if (ow.vpos >= pub_at) publish();
+      if constexpr (qon) { if (ow.vpos >= pub_at) publish(); }
       // ---- token iterations (all 32 lanes stay in this loop together) -----------------------
       uint32_t it = 0;
       // software pipeline: the output step of a token is deferred to the start of the next
@@ -428,7 +428,7 @@ huff_lanes_kernel(const BatchArgs a)
         const uint32_t bits_hi = funnel_r(br.w1, br.w2, bo0);   // window bits [32, 64) from the token start
         const uint32_t e1 = lds16(lutb + (C::LIT_OFF * 64) + ((bits0 << 6) & (((1u << C::ROOT_LIT) - 1u) << 6)));
         ow.emit(p_chunk, p_n, p_skip, p_mt, p_hoff);   // (the previous iteration's output step)
-        if (ow.vpos >= pub_at) publish();
+        if constexpr (qon) { if (ow.vpos >= pub_at) publish(); }
         const bool pre1 = dec & !tail & (ow.room() != 0u) & ((ow.vpos & 7u) != 7u) & pair_on;
         // a literal entry has bits 12-15 clear and its code length (1 .. ROOT_LIT) in bits 0-3
         const uint32_t t1 = e1 & 0xf00fu;

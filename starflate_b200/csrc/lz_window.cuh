@@ -34,6 +34,7 @@ namespace sfb {
 constexpr int LZW_THREADS = 256;
 constexpr uint32_t LZW_SPARSE_MAX = 6;
 constexpr uint32_t LZW_NONE = 0xffffffffu;
+constexpr uint32_t LZW_PF_MIN = 1024u;   // sources nearer than this are not prefetched (lzw_run<.., PF>)
 
 struct LzwView {
   uint8_t* base;          // view byte v lives at base[v]; base is 128-byte aligned, windows start at v % 1024 == 0
@@ -436,7 +437,11 @@ struct LzwState {
 // Windows W <= ... < w_stop of the stream in view `v` (v.end bounds what may be read at all; `look`
 // bounds how far ahead a run of matches may be looked for — both the end of the stream when all of
 // it is there).
-template <bool CG>
+// PF: in dense windows every head lane asks the L2 for the line its match's SOURCE starts in one
+// chunk before the chunk is worked on (the descriptors of a stream are all there before pass 2
+// starts, only the source bytes may not be final yet — a prefetch does not care).  Half of this
+// kernel's stall samples on text are gathers that miss the L2.
+template <bool CG, bool PF = false>
 __device__ __forceinline__ void lzw_run(const LzwView& v, LzwState& s, uint32_t w_stop, uint32_t look)
 {
   constexpr unsigned FULL = 0xffffffffu;
@@ -542,6 +547,21 @@ __device__ __forceinline__ void lzw_run(const LzwView& v, LzwState& s, uint32_t 
         const uint32_t nncw = load_w(P + 256u);
         const uint32_t mw = __shfl_sync(FULL, wbits, static_cast<int>(((P - W) >> 5) + (lane >> 3)));
         const uint32_t hb4 = (mw >> (4u * (lane & 7u))) & 15u;
+        if constexpr (PF) {
+          // the last head in my word of the NEXT chunk (its words are in ncw, the bitmap bits in
+          // this window's word or the next one's): far sources only, near ones are in the L1 / L2
+          const uint32_t P1 = P + 128u;
+          const uint32_t mw1 = __shfl_sync(FULL, P1 < W + 1024u ? wbits : nwb,
+                                           static_cast<int>((((P1 - W) >> 5) & 31u) + (lane >> 3)));
+          const uint32_t hb1 = (mw1 >> (4u * (lane & 7u))) & 15u;
+          const uint32_t nx1 = __shfl_sync(FULL, lane == 0u ? nncw : ncw, static_cast<int>((lane + 1u) & 31u));
+          const uint32_t hl1 = 31u - static_cast<uint32_t>(__clz(static_cast<int>(hb1 | 1u)));
+          const uint32_t d1 = (lz_funnel(ncw, nx1, 8u * hl1) >> 8) & 0xffffu;   // distance - 1
+          const uint32_t h1 = P1 + 4u * lane + hl1;
+          // (a word that is not a descriptor any more — a fill went over it — gives some d1: the
+          //  source is only asked for when it lies inside the stream)
+          if (hb1 != 0u && d1 >= LZW_PF_MIN && d1 < h1 - v.q && h1 < end) lzw_prefetch(v.base + h1 - d1 - 1u);
+        }
         if (P >= lo && P + 128u <= end) lzw_chunk<false, CG>(v, P, lo, end, cw, ncw, hb4, c_o, c_end, c_d);
         else lzw_chunk<true, CG>(v, P, lo, end, cw, ncw, hb4, c_o, c_end, c_d);
         cw = ncw;
@@ -564,7 +584,7 @@ __device__ __forceinline__ void lzw_run(const LzwView& v, LzwState& s, uint32_t 
 }
 
 // MINB: resident CTAs per SM the register allocation aims at (capi.cu picks the instantiation)
-template <int MINB>
+template <int MINB, bool PF = true>
 __global__ void __launch_bounds__(LZW_THREADS, MINB) lz_window_kernel(const ResolveArgs a)
 {
   constexpr unsigned FULL = 0xffffffffu;
@@ -590,7 +610,7 @@ __global__ void __launch_bounds__(LZW_THREADS, MINB) lz_window_kernel(const Reso
     s.c_o = 0;
     s.c_end = 0;
     s.c_d = 1;
-    lzw_run<false>(v, s, 0xffffffffu, v.end);
+    lzw_run<false, PF>(v, s, 0xffffffffu, v.end);
   }
 }
 

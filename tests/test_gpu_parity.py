@@ -206,12 +206,14 @@ def test_small_table_geometry_with_hand_over(oracle, golden, monkeypatch):
         c.close()
 
 
-@pytest.mark.parametrize("env", [{"SFB200_NO_WIDE": "1"}, {"SFB200_NO_WIDE": "1", "SFB200_NO_STORED": "1", "SFB200_NO_PAIR": "1"}],
-                         ids=["large-geometry", "large-geometry-plain"])
+@pytest.mark.parametrize("env", [{"SFB200_NO_WIDE": "1"}, {"SFB200_NO_WIDE": "1", "SFB200_NO_STORED": "1", "SFB200_NO_PAIR": "1"},
+                                 {"SFB200_NO_WIDE": "1", "SFB200_QUEUE": "1"}],
+                         ids=["large-geometry", "large-geometry-plain", "queue-mode"])
 def test_golden_families_on_the_large_geometry(oracle, golden, monkeypatch, env):
     """Small batches take the wide table geometry (9/6-bit roots, one CTA per SM) and stored streams
     the copy kernel: here every golden family goes through the 8/6-bit geometry the full-size
-    batches use, once with and once without the copy kernel and the literal pairing."""
+    batches use, once with and once without the copy kernel and the literal pairing, and once with
+    pass 2 running beside pass 1 (the experimental hand-over queue: 16 KiB segments)."""
     import starflate_b200 as S
     for k, v in env.items():
         monkeypatch.setenv(k, v)
