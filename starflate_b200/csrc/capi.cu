@@ -73,7 +73,7 @@ struct sfb200_ctx {
   int lzw_minb = 5;            // lz_window_kernel instantiation (register budget for 4 / 5 / 6 CTAs per SM;
                                // measured with the long periodic fill in: 5 (48 registers) beats 6 (40, spills
                                // in the chunk loop) on C2 8.5 / 8.9 ms and C4 5.0 / 5.5 ms — SFB200_LZW_CTAS)
-  bool lzw_no_pf = false;      // SFB200_LZW_PF=0: lz_window_kernel without the source prefetch (A/B runs; 5 CTAs per SM only)
+  bool lzw_pf = false;         // SFB200_LZW_PF=1: lz_window_kernel with the source prefetch (measured slower; 5 CTAs per SM only)
   uint8_t* d_queue = nullptr;  // hand-over queue of the overlapped mode (QueueArgs): counters, turns, states, items
   uint64_t d_queue_cap = 0;
   int queue_mode = 0;          // SFB200_QUEUE=1: pass 2 runs beside pass 1 (lz_window_queue_kernel)
@@ -227,7 +227,7 @@ int sfb200_create(int device, sfb200_ctx** out)
     if (const char* e = std::getenv("SFB200_NO_PAIR")) ctx->no_pair = e[0] == '1';
     if (const char* e = std::getenv("SFB200_NO_STORED")) ctx->no_stored = e[0] == '1';
     if (const char* e = std::getenv("SFB200_QUEUE")) ctx->queue_mode = std::atoi(e);
-    if (const char* e = std::getenv("SFB200_LZW_PF")) ctx->lzw_no_pf = e[0] == '0';
+    if (const char* e = std::getenv("SFB200_LZW_PF")) ctx->lzw_pf = e[0] == '1';
     if (const char* e = std::getenv("SFB200_QUEUE_CTAS")) ctx->queue_ctas = std::max(1, std::atoi(e));
     static_assert(sfb::LZ_THREADS == sfb::LZW_THREADS, "one launch geometry for both pass-2 kernels");
     static_assert(LaneCfg::WARPS == WideCfg::WARPS, "the wide launch takes the CTA count computed for the large one");
@@ -923,7 +923,7 @@ int batch_device_impl(sfb200_ctx* ctx, const uint8_t* src_base, const uint64_t* 
       const unsigned grid = static_cast<unsigned>(want < resident ? want : resident);
       if (ctx->lz_v1) sfb::lz_resolve_kernel<<<grid, sfb::LZ_THREADS, 0, s2>>>(r);
       else if (ctx->lzw_minb == 4) sfb::lz_window_kernel<4><<<grid, sfb::LZW_THREADS, 0, s2>>>(r);
-      else if (ctx->lzw_minb == 5 && ctx->lzw_no_pf) sfb::lz_window_kernel<5, false><<<grid, sfb::LZW_THREADS, 0, s2>>>(r);
+      else if (ctx->lzw_minb == 5 && ctx->lzw_pf) sfb::lz_window_kernel<5, true><<<grid, sfb::LZW_THREADS, 0, s2>>>(r);
       else if (ctx->lzw_minb == 5) sfb::lz_window_kernel<5><<<grid, sfb::LZW_THREADS, 0, s2>>>(r);
       else sfb::lz_window_kernel<6><<<grid, sfb::LZW_THREADS, 0, s2>>>(r);
       SFB_TRY(ctx, cudaGetLastError());

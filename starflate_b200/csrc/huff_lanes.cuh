@@ -452,11 +452,15 @@ huff_lanes_kernel(const BatchArgs a)
         // anything that is not a plain literal / length+distance — end of block included — is
         // redone exactly, from the same 64 window bits
         // (near the end of the input the token must also fit into the real bits that are left)
-        // (the last few tokens of a stream — `tail` — all go the exact way, whether they fit or not:
-        //  cheaper than asking every token of the stream whether it fits)
+        // (`tail`: a window word reaches past the end of the stream — the bits there are zeros, not
+        //  input.  A plain token that ends inside the real bits is still exactly what the reference
+        //  decodes bit by bit; one that does not goes the exact way, which names the status.  4 KiB
+        //  pages spend their last ~10 tokens here: taking all of them the exact way, one lane at a
+        //  time, was a fifth of pass 1 on BASELINE config 3.)
         const bool odd = (L == 0) | (is_match & (dL == 0));
-        if (dec & !lit1 & (odd | tail)) {
-          const int32_t left32 = static_cast<int32_t>(br.ebits - 32u * br.rp - bo0);
+        const int32_t left32 = static_cast<int32_t>(br.ebits - 32u * br.rp - bo0);   // real bits left (valid in `tail`)
+        const bool past_end = tail & (static_cast<int32_t>(used) > left32);
+        if (dec & !lit1 & (odd | past_end)) {
           // (a) a valid code longer than the tables hold: canonical decode in registers
           bool done = false;
           if (lt_lit.usable & lt_dist.usable) {

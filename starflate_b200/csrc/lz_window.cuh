@@ -437,10 +437,12 @@ struct LzwState {
 // Windows W <= ... < w_stop of the stream in view `v` (v.end bounds what may be read at all; `look`
 // bounds how far ahead a run of matches may be looked for — both the end of the stream when all of
 // it is there).
-// PF: in dense windows every head lane asks the L2 for the line its match's SOURCE starts in one
-// chunk before the chunk is worked on (the descriptors of a stream are all there before pass 2
-// starts, only the source bytes may not be final yet — a prefetch does not care).  Half of this
-// kernel's stall samples on text are gathers that miss the L2.
+// PF (EXPERIMENT, measured slower, off unless SFB200_LZW_PF=1): in dense windows every head lane
+// asks the L2 for the line its match's SOURCE starts in one chunk before the chunk is worked on (the
+// descriptors of a stream are all there before pass 2 starts, only the source bytes may not be
+// final yet — a prefetch does not care).  Half of this kernel's stall samples on text are gathers
+// that miss the L2, but the kernel is also issue-bound and moves 2.9 TB/s of DRAM
+// traffic: C2 pass 2 10.3 ms with the prefetch against 8.5 ms without (gpurun_out/r02_ab_pf1.jsonl).
 template <bool CG, bool PF = false>
 __device__ __forceinline__ void lzw_run(const LzwView& v, LzwState& s, uint32_t w_stop, uint32_t look)
 {
@@ -584,7 +586,7 @@ __device__ __forceinline__ void lzw_run(const LzwView& v, LzwState& s, uint32_t 
 }
 
 // MINB: resident CTAs per SM the register allocation aims at (capi.cu picks the instantiation)
-template <int MINB, bool PF = true>
+template <int MINB, bool PF = false>
 __global__ void __launch_bounds__(LZW_THREADS, MINB) lz_window_kernel(const ResolveArgs a)
 {
   constexpr unsigned FULL = 0xffffffffu;
