@@ -555,7 +555,11 @@ int batch_device_impl(sfb200_ctx* ctx, const uint8_t* src_base, const uint64_t* 
   //  inside a launch warps pull groups dynamically, which evens out unequal streams and lets a
   //  lane keep its fixed-Huffman tables from one stream to the next)
   const uint64_t lanes = use_small ? small_lanes : big_lanes;
-  const uint64_t wave = lanes * std::max<uint64_t>(1, (n + 8 * lanes - 1) / (8 * lanes));
+  uint64_t wave = lanes * std::max<uint64_t>(1, (n + 8 * lanes - 1) / (8 * lanes));
+  if (const char* e = std::getenv("SFB200_WAVE_STREAMS")) {  // (experiments: the size of a wave)
+    const uint64_t v = std::strtoull(e, nullptr, 10);
+    if (v >= 1024) wave = v;
+  }
   uint64_t n_waves = (n + wave - 1) / wave;
   if (const char* e = std::getenv("SFB200_NO_OVERLAP"))
     if (e[0] == '1') n_waves = 1;
@@ -565,7 +569,9 @@ int batch_device_impl(sfb200_ctx* ctx, const uint8_t* src_base, const uint64_t* 
   // the issue slots and pass 1, which is latency-bound, slows down by more than pass 2 gains
   // (C2: 21.8 ms overlapped, 20.2 ms back to back); from three waves on it pays (131 072 streams:
   // 218 against 200 GB/s).
-  if (n_waves == 2) n_waves = 1;
+  bool two_waves = false;
+  if (const char* e = std::getenv("SFB200_TWO_WAVES")) two_waves = e[0] == '1';
+  if (n_waves == 2 && !two_waves) n_waves = 1;
   // Queue mode: ONE launch of pass 1, pass 2 beside it on the second stream, fed segment by segment
   // (deflate_lane.cuh: QueueArgs; lz_window.cuh: lz_window_queue_kernel).
   const bool qmode = ctx->queue_mode != 0 && !stream_mode && !use_small && !resume && !jump && !ctx->lz_v1;
