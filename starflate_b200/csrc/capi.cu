@@ -901,10 +901,12 @@ int batch_device_impl(sfb200_ctx* ctx, const uint8_t* src_base, const uint64_t* 
         };
         j.round = 0;
         sfb::lz_jump_init_kernel<<<set_stripe(0), sfb::JUMP_THREADS, 0, s2>>>(j);
+        ctx->launches += 1;
         for (uint64_t sp = 0; sp < stripes; ++sp) {
           if (sp + 1 < stripes) {
             j.round = 0;
             sfb::lz_jump_init_kernel<<<set_stripe(sp + 1), sfb::JUMP_THREADS, 0, s2>>>(j);
+            ctx->launches += 1;
           }
           const unsigned grid = set_stripe(sp);
           // a chain inside a stripe has fewer hops than the stripe has bytes, and a round divides
@@ -916,11 +918,11 @@ int batch_device_impl(sfb200_ctx* ctx, const uint8_t* src_base, const uint64_t* 
           for (int r = 1; r <= max_rounds; ++r) {
             j.round = static_cast<uint32_t>(r);
             sfb::lz_jump_round_kernel<<<grid, sfb::JUMP_THREADS, 0, s2>>>(j);
+            ctx->launches += 1;
           }
           SFB_TRY(ctx, cudaGetLastError());
         }
       }
-      ctx->launches += (sfb::JUMP_MAX_ROUNDS + 1) * cnt * stripes;
     } else {
       constexpr uint64_t wpc = sfb::LZ_THREADS / 32;
       const uint64_t resident =
@@ -934,7 +936,7 @@ int batch_device_impl(sfb200_ctx* ctx, const uint8_t* src_base, const uint64_t* 
       else sfb::lz_window_kernel<6><<<grid, sfb::LZW_THREADS, 0, s2>>>(r);
       SFB_TRY(ctx, cudaGetLastError());
     }
-    ctx->launches += 1;
+    if (qmode || !jump) ctx->launches += 1;   // (the jump route counted its launches one by one)
   }
   if (overlap) {
     SFB_TRY(ctx, cudaEventRecord(ctx->wave_ev[n_waves + 1], s1));
