@@ -154,7 +154,9 @@ int sfb200_inflate_stream_feed(sfb200_inflate_stream* s, const uint8_t* src, siz
  * README names as not built yet, README.md:5-7; it only has the Huffman-table construction,
  * huffman/src/table.hpp:246-298).  Stream i = src_base[src_off[i] .. +src_len[i]) is written as one
  * RFC 1951 stream to dst_base[dst_off[i] .. +dst_cap[i]): LZ77 by hashing (4-byte minimum match,
- * 32 KiB window, greedy) and ONE fixed-Huffman block, or stored blocks where that is smaller.
+ * 32 KiB window, greedy) and ONE Huffman block — dynamic (code lengths derived on the device from
+ * the stream's own symbol counts) where that is smaller, else fixed — or stored blocks where
+ * neither beats the input.
  * status[i] = SFB200_SUCCESS with written[i] bytes, or SFB200_DST_TOO_SMALL (written[i] = 0: neither
  * form fits; sfb200_compress_bound(src_len) always does), or SFB200_ERROR for src_len[i] >= 2^32 -
  * 256.  Bytes of the dst region past written[i] may have been used as scratch.  The output decodes

@@ -1552,6 +1552,8 @@ int sfb200_compress_batch_device(sfb200_ctx* ctx, const uint8_t* src_base, const
   a.written = written;
   a.n = n;
   a.counter = ctx->d_counter;
+  a.fixed_only = 0;   // SFB200_COMPRESS_FIXED=1: the first generation (one pass, fixed-Huffman blocks only) for A/B runs
+  if (const char* e = std::getenv("SFB200_COMPRESS_FIXED")) a.fixed_only = e[0] == '1';
   const uint64_t want = (n + sfb::CMP_WARPS - 1) / sfb::CMP_WARPS;
   const uint64_t resident = static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->compress_ctas_per_sm);
   sfb::deflate_compress_kernel<<<static_cast<unsigned>(want < resident ? want : resident), sfb::CMP_WARPS * 32,

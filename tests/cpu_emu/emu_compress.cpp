@@ -3,6 +3,7 @@
 #define SFB_CPU_EMU 1
 #include "cuda_shim_warp.h"
 
+#include <cstdlib>
 #include <thread>
 #include <vector>
 
@@ -37,6 +38,7 @@ extern "C" int emu_compress(const uint8_t* src, uint64_t src_len, uint8_t* dst, 
   a.written = written;
   a.n = 1;
   a.counter = &counter;
+  a.fixed_only = std::getenv("SFB200_COMPRESS_FIXED") != nullptr;
   std::vector<std::thread> lanes;
   for (unsigned l = 0; l < 32; ++l)
     lanes.emplace_back([&a, l] {

@@ -657,6 +657,14 @@ def test_compress_round_trip_batch(ctx, oracle):
         assert int(dst_wr[i]) == len(plains[i]) and b.dst_slice(dst, i).tobytes()[:len(plains[i])] == plains[i], i
     ratio = float(lens.sum()) / float(wr.sum())
     assert ratio > 1.2
+    # text of some length gets a dynamic-Huffman block (BTYPE 10), random bytes stored ones (00)
+    kinds = [(comps[i][0] >> 1) & 3 for i in range(n)]
+    assert all(kinds[i] == 2 for i in range(n) if i % 6 in (0, 5) and len(plains[i]) > 2000)
+    assert all(kinds[i] == 0 for i in range(n) if i % 6 == 2 and len(plains[i]) > 2000)
+    text_in = sum(len(plains[i]) for i in range(n) if i % 6 == 5)
+    text_out = sum(len(comps[i]) for i in range(n) if i % 6 == 5)
+    text_z = sum(len(zlib.compress(plains[i], 6)) for i in range(n) if i % 6 == 5)
+    assert text_out < 1.25 * text_z, (text_in, text_out, text_z)   # within a quarter of zlib level 6 on text
 
 
 def test_compress_single_stream_host_api_and_small_dst(ctx):

@@ -5,6 +5,8 @@ warp-cooperative LZ77 resolve in the GPU-less container; the real parity tests a
 ones through the C ABI."""
 import zlib
 
+import os
+
 import numpy as np
 import pytest
 
@@ -352,6 +354,29 @@ def test_compression_kernel_round_trips(emu, oracle):
             assert zlib.decompress(comp, -15) == data, name
             ost, out, wr, ub = oracle.decompress(comp, len(data) + 8)
             assert (ost, wr, ub) == (0, len(data), 0) and out[:wr] == data, name
+    # dynamic-Huffman blocks: taken where they are smaller, complete codes (zlib refuses others), the
+    # Kraft loops in both directions
+    skew = np.minimum(rng.geometric(0.5, 120000) - 1, 40).astype(np.uint8).tobytes()   # rare symbols, > 2^15 tokens: the 15-bit clamp
+    dyn_cases = {
+        "text": cases["text"], "skew": skew, "all256": bytes(range(256)) * 40,
+        "literals_only": bytes(rng.permutation(256).astype(np.uint8)) + bytes(rng.integers(0, 7, 3000, dtype=np.uint8) * 37),
+        "two_symbols": b"ab" * 3 + b"a", "run": cases["run"],
+    }
+    for name, data in dyn_cases.items():
+        st, comp = emu.compress(data, len(data) + len(data) // 8 + 64, 1)
+        assert st == 0, name
+        assert zlib.decompress(comp, -15) == data, name
+        ost, out, wr, ub = oracle.decompress(comp, len(data) + 8)
+        assert (ost, wr, ub) == (0, len(data), 0) and out[:wr] == data, name
+        os.environ["SFB200_COMPRESS_FIXED"] = "1"
+        try:
+            st, comp_fixed = emu.compress(data, len(data) + len(data) // 8 + 64, 1)
+        finally:
+            del os.environ["SFB200_COMPRESS_FIXED"]
+        assert st == 0 and zlib.decompress(comp_fixed, -15) == data, name
+        assert len(comp) <= len(comp_fixed), name
+        if name in ("text", "skew"):
+            assert (comp[0] >> 1) & 3 == 2 and len(comp) < 0.85 * len(comp_fixed), name
     st, comp = emu.compress(cases["random"], 100)
     assert st == 4 and comp == b""
     st, comp = emu.compress(cases["run"], 100)                  # fits compressed, would not fit stored
