@@ -499,9 +499,8 @@ def main():
                          "dominant_kernel": k1 if p1_ms >= p2_ms else k2, "step_ms": k_ms,
                          "algorithmic_bytes": algo_bytes,
                          "note": "achieved = (compressed read + decompressed written) / device time of the "
-                                 "WHOLE step, not of the dominant kernel alone; with more than two waves of "
-                                 "streams the passes overlap on two internal streams: passes_ms then gives "
-                                 "clear | start of pass 1 .. end of its last wave | the part of pass 2 after that",
+                                 "WHOLE step, not of the dominant kernel alone; the two passes run back to back "
+                                 "(one launch each), passes_ms = clear and batch preparation | pass 1 | pass 2",
                          "passes_ms": {"clear": clear_ms, k1.split(" (")[0]: p1_ms, k2.split(" (")[0]: p2_ms},
                          "frac_of_nominal_8TBs": achieved / 8000.0},
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "wall_s_timed_region": t_wall,

@@ -252,8 +252,8 @@ int sfb200_get_launch_info(sfb200_ctx* ctx, sfb200_launch_info* out);
  *   out3[1] pass 1, the Huffman layer (huff_lanes_kernel; one stream or a few large ones:
  *           find / verify candidates, huff_stream_kernel counting and writing, the chain),
  *   out3[2] pass 2, the LZ77 back-references (lz_window_kernel; single-stream route: lz_jump_*).
- * With more than two waves of streams the passes overlap: out3[1] then runs to the end of the last
- * wave of pass 1 and out3[2] is what remains of pass 2 after that. */
+ * (With SFB200_OVERLAP=1 — the experimental wave form — the passes overlap: out3[1] then runs to
+ * the end of the last wave of pass 1 and out3[2] is what remains of pass 2 after that.) */
 int sfb200_last_pass_ms(sfb200_ctx* ctx, float* out3);
 
 #ifdef __cplusplus

@@ -542,11 +542,13 @@ int batch_device_impl(sfb200_ctx* ctx, const uint8_t* src_base, const uint64_t* 
     SFB_TRY(ctx, cudaMalloc(reinterpret_cast<void**>(&ctx->d_defer), want * sizeof(uint32_t)));
     ctx->d_defer_n = want;
   }
-  // Waves.  Pass 1 runs one wave of streams (as many as there are resident lanes) at a time
-  // and is latency-bound (about half of the issue slots stay idle); pass 2 needs no shared
-  // memory and few registers.  With more than one wave, pass 1 of wave k+1 and pass 2 of wave
-  // k are put on two internal streams so that they share the SMs; a single wave runs on the
-  // caller's stream directly.
+  // Waves.  The two passes run BACK TO BACK over the whole batch: one launch each, inside which
+  // warps pull groups of streams dynamically.  Cutting the batch into waves and running pass 2 of
+  // wave k beside pass 1 of wave k+1 on two internal streams is kept for experiments
+  // (SFB200_OVERLAP=1; wave size SFB200_WAVE_STREAMS) — measured at the end of round 2 it loses on
+  // every shape: 65 536 x 64 KiB 19.4 against 18.6 ms, 131 072 x 64 KiB 39.7 against 37.0 ms,
+  // 1 048 576 x 4 KiB 18.5 against 18.1 ms: pass 1 is latency-bound and slows down
+  // by more than pass 2 gains when it shares its SMs.
   const uint64_t big_lanes = static_cast<uint64_t>(ctx->sm_count) * static_cast<uint64_t>(ctx->ctas_per_sm) *
                              LaneCfg::WARPS * 32;
   const uint64_t small_lanes = static_cast<uint64_t>(ctx->sm_count) *
@@ -561,17 +563,11 @@ int batch_device_impl(sfb200_ctx* ctx, const uint8_t* src_base, const uint64_t* 
     if (v >= 1024) wave = v;
   }
   uint64_t n_waves = (n + wave - 1) / wave;
-  if (const char* e = std::getenv("SFB200_NO_OVERLAP"))
-    if (e[0] == '1') n_waves = 1;
+  bool overlap_waves = false;
+  if (const char* e = std::getenv("SFB200_OVERLAP")) overlap_waves = e[0] == '1';
+  if (!overlap_waves) n_waves = 1;
   if (n_waves > kMaxWaves) n_waves = 1;  // (counters are a fixed array: enormous batches run unsplit)
   if (stream_mode) n_waves = 1;
-  // With two waves the overlapped part (pass 1 of the second, pass 2 of the first) wants ~95 % of
-  // the issue slots and pass 1, which is latency-bound, slows down by more than pass 2 gains
-  // (C2: 21.8 ms overlapped, 20.2 ms back to back); from three waves on it pays (131 072 streams:
-  // 218 against 200 GB/s).
-  bool two_waves = false;
-  if (const char* e = std::getenv("SFB200_TWO_WAVES")) two_waves = e[0] == '1';
-  if (n_waves == 2 && !two_waves) n_waves = 1;
   // Queue mode: ONE launch of pass 1, pass 2 beside it on the second stream, fed segment by segment
   // (deflate_lane.cuh: QueueArgs; lz_window.cuh: lz_window_queue_kernel).
   const bool qmode = ctx->queue_mode != 0 && !stream_mode && !use_small && !resume && !jump && !ctx->lz_v1;

@@ -5,6 +5,8 @@ import hashlib
 
 import zlib
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -433,6 +435,25 @@ def test_full_size_checksum_of_checksums(ctx, shape):
     ctx.checksum_batch_device(dst, dst_off, written, out)
     torch.cuda.synchronize(dev)
     assert (out.cpu().numpy().view(np.uint64) == want).all()
+    if shape == "C3":
+        # the wave form (pass 2 of wave k beside pass 1 of wave k+1 on two internal streams; an
+        # experiment since the end of round 2, SFB200_OVERLAP=1) gives the same bytes
+        import starflate_b200 as S
+        os.environ["SFB200_OVERLAP"] = "1"
+        try:
+            c2 = S.Context(ctx.device)
+        finally:
+            del os.environ["SFB200_OVERLAP"]
+        try:
+            dst.fill_(0x5A)
+            os.environ["SFB200_OVERLAP"] = "1"   # (read per call)
+            c2.decompress_batch_device(src, src_off, src_len, dst, dst_off, cap, status, written)
+            c2.checksum_batch_device(dst, dst_off, written, out)
+            torch.cuda.synchronize(dev)
+            assert int(status.max()) == 0 and (out.cpu().numpy().view(np.uint64) == want).all()
+        finally:
+            os.environ.pop("SFB200_OVERLAP", None)
+            c2.close()
 
 
 @pytest.mark.parametrize("shape,size", [("C1", 1 << 20), ("C5", 1 << 30)])
