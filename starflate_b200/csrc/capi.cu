@@ -1089,12 +1089,18 @@ int sfb200_decompress_batch_host(sfb200_ctx* ctx, const uint8_t* src, uint64_t s
     uint64_t first, count, src_lo, src_hi, dst_lo, dst_hi;
   };
   std::vector<Sub> subs;
+  // (the first sub-batches are an eighth, a quarter and a half of a slot: the download — the slower
+  //  PCIe direction, which bounds the call — starts after the upload and the kernels of 1/8 of a
+  //  slot instead of a whole one, and from then on never waits: a sub-batch's kernels take a
+  //  quarter of the time its predecessor's download does even when it is twice as large)
   for (uint64_t i = 0; i < n;) {
     Sub sb{i, 0, ~0ull, 0, ~0ull, 0};
+    const uint64_t ramp = subs.size() == 0 ? 8 : subs.size() == 1 ? 4 : subs.size() == 2 ? 2 : 1;
+    const uint64_t lim_src = slot_src / ramp, lim_dst = slot_dst / ramp;
     while (i < n && sb.count < want_n) {
       const uint64_t slo = std::min(sb.src_lo, src_off[i]), shi = std::max(sb.src_hi, src_off[i] + src_len[i]);
       const uint64_t dlo = std::min(sb.dst_lo, dst_off[i]) & ~127ull, dhi = std::max(sb.dst_hi, dst_off[i] + dst_cap[i]);
-      if (sb.count && (shi - slo > slot_src || dhi - dlo > slot_dst)) break;
+      if (sb.count && (shi - slo > lim_src || dhi - dlo > lim_dst)) break;
       sb.src_lo = slo;
       sb.src_hi = shi;
       sb.dst_lo = dlo;  // (128-byte aligned: keeps the windows' alignment and the bitmap phase of the caller's layout)
