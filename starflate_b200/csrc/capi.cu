@@ -836,7 +836,7 @@ int batch_device_impl(sfb200_ctx* ctx, const uint8_t* src_base, const uint64_t* 
     }
     if (k + 1 == n_waves) SFB_TRY(ctx, cudaEventRecord(ctx->ev[2], s1));  // end of all of pass 1
     // pass 2: LZ77 back-references, one warp per stream
-    sfb::ResolveArgs r;
+    sfb::ResolveArgs r{};
     r.dst_base = dst_base;
     r.dst_delta = delta;
     r.dst_off = dst_off;

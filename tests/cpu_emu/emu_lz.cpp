@@ -17,7 +17,7 @@ extern "C" void emu_lz_resolve(uint8_t* dst_base, const uint64_t* dst_off, const
   EmuWarp warp;
   emu_warp = &warp;
   unsigned long long counter = 0;
-  sfb::ResolveArgs a;
+  sfb::ResolveArgs a{};
   a.dst_base = dst_base;
   a.dst_delta = 0;
   a.dst_off = dst_off;
