@@ -547,17 +547,22 @@ def main():
                            "passes_ms": r["roofline"]["passes_ms"], "clocks": r["clocks"]}
         del ws
     # ---- the other named shapes, 1 GPU (north_star: "each named shape is reported") ---------------
-    if not args.no_shapes and world == 1 and args.workload == "c2" and args.container == "raw":
+    # (N > 1: every rank runs its own copy — weak scaling for the batch C4, independent replicas for
+    #  the single streams C1 / C5, which do not shard; value = all ranks' bytes / the slowest rank's time;
+    #  roofline is one GPU's)
+    if not args.no_shapes and args.workload == "c2" and args.container == "raw":
         shapes = {}
         for nm, ns, uq, st in (("c1", 1, 1, 5), ("c4", 16384, 128, 3), ("c5", 1, 1, 3)):
             wsh = make_workload(nm, ns, uq, rank)
             r = measure(nm, wsh, st, 3, False, min_region_ms=120.0)
             shapes[nm] = {k: r[k] for k in ("workload", "value", "ms_per_step", "steps", "clocks", "gpu_launches", "l2")}
             shapes[nm]["unit"] = UNIT
+            shapes[nm]["n_gpus"] = world
+            shapes[nm]["scaling"] = "weak" if nm == "c4" else "replicas only (one stream does not shard)"
             shapes[nm]["roofline"] = {k: r["roofline"][k] for k in ("achieved", "peak", "frac", "passes_ms", "algorithmic_bytes")}
             del wsh
         if "sharded" in line:
-            shapes["c3"] = {"see": "sharded (the same workload; at 1 GPU the shard is the whole batch)",
+            shapes["c3"] = {"see": "sharded (the same workload; at 1 GPU the shard is the whole batch)", "n_gpus": world, "scaling": "strong",
                             "value": line["sharded"]["value"], "ms_per_step": line["sharded"]["ms_per_step"],
                             "unit": UNIT, "roofline": {"frac": line["sharded"]["roofline_frac"]},
                             "clocks": line["sharded"]["clocks"]}
