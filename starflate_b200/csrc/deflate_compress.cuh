@@ -69,6 +69,10 @@ constexpr int CMP_WARP_BYTES = (1 << CMP_HASH_BITS) * 2 + CMP_STAGE_WORDS * 4 + 
                                (CMP_NLL + CMP_ND + CMP_NCL) + CMP_NSEQ * 2;
 constexpr int CMP_SMEM_BYTES = CMP_WARPS * CMP_WARP_BYTES;
 constexpr uint32_t CMP_MIN_MATCH = 4;
+#ifndef SFB_CMP_LAZY
+#define SFB_CMP_LAZY 1
+#endif
+constexpr bool CMP_LAZY = SFB_CMP_LAZY != 0;
 constexpr uint32_t CMP_MAX_MATCH = 258;
 constexpr uint32_t CMP_MAX_DIST = 32768;
 
@@ -431,14 +435,22 @@ __device__ __forceinline__ void cmp_parse(const uint8_t* s, uint32_t n, uint16_t
         }
       }
     }
-    // greedy parse of the 32 positions, by the whole warp
-    bool start = false;
+    // parse of the 32 positions, front to back, by the whole warp: greedy with one step of
+    // laziness — a match gives way to a literal when the next position has a longer one (what
+    // zlib's deflate_slow does; the next position's candidate is already there, so it costs a shuffle)
+    bool start = false, as_lit = false;
     uint32_t t = 0;
     while (t < 32u && c + t < n) {
       const uint32_t L = __shfl_sync(FULL, mlen, static_cast<int>(t));
-      if (lane == t) start = true;
-      t += L ? L : 1u;
+      const uint32_t Ln = __shfl_sync(FULL, mlen, static_cast<int>((t + 1u) & 31u));
+      const bool defer = CMP_LAZY && L != 0u && t + 1u < 32u && Ln > L;
+      if (lane == t) {
+        start = true;
+        as_lit = defer;
+      }
+      t += (L != 0u && !defer) ? L : 1u;
     }
+    if (as_lit) mlen = 0;
     if constexpr (MODE == 0) {
       if (start) {
         if (mlen) {
