@@ -16,7 +16,10 @@ _u64p = C.POINTER(C.c_uint64)
 
 
 def build(root_lit=8, root_dist=6, pool=96) -> str:
-    out = os.path.join(HERE, "cpu_emu", f"libemu_{root_lit}_{root_dist}_{pool}.so")
+    # SFB_EMU_ASAN=1: the kernels' sources under AddressSanitizer + UBSan (run pytest with
+    # LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0)
+    asan = os.environ.get("SFB_EMU_ASAN") == "1"
+    out = os.path.join(HERE, "cpu_emu", f"libemu_{root_lit}_{root_dist}_{pool}{'_asan' if asan else ''}.so")
     emu = os.path.join(HERE, "cpu_emu")
     csrc = os.path.join(ROOT, "starflate_b200", "csrc")
     srcs = [os.path.join(emu, "emu.cpp"), os.path.join(emu, "emu_lz.cpp"), os.path.join(emu, "emu_stream.cpp"), os.path.join(emu, "emu_compress.cpp"),
@@ -26,7 +29,8 @@ def build(root_lit=8, root_dist=6, pool=96) -> str:
             os.path.join(csrc, "lz_warp.cuh"), os.path.join(csrc, "lz_window.cuh"), os.path.join(csrc, "huff_stream.cuh"),
             os.path.join(csrc, "block_finder.cuh"), os.path.join(csrc, "container.cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
-        subprocess.check_call(["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-pthread",
+        opt = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer"] if asan else ["-O2"]
+        subprocess.check_call(["g++", "-std=c++20", *opt, "-fPIC", "-shared", "-pthread",
                                f"-DSFB_EMU_ROOT_LIT={root_lit}", f"-DSFB_EMU_ROOT_DIST={root_dist}",
                                f"-DSFB_EMU_POOL={pool}", "-o", out, srcs[0], srcs[1], srcs[2], srcs[3]])
     return out
