@@ -438,18 +438,32 @@ __device__ __forceinline__ void cmp_parse(const uint8_t* s, uint32_t n, uint16_t
     // parse of the 32 positions, front to back, by the whole warp: greedy with one step of
     // laziness — a match gives way to a literal when the next position has a longer one (what
     // zlib's deflate_slow does; the next position's candidate is already there, so it costs a shuffle)
-    bool start = false, as_lit = false;
+    // (the loop runs once per MATCH taken: the literals between two matches are found with the
+    //  ballot of the positions that have one)
+    const uint32_t lim = n - c < 32u ? n - c : 32u;
+    const uint32_t mm = __ballot_sync(FULL, mlen != 0u);
+    uint32_t start_mask = 0, lit_mask = 0;
     uint32_t t = 0;
-    while (t < 32u && c + t < n) {
-      const uint32_t L = __shfl_sync(FULL, mlen, static_cast<int>(t));
-      const uint32_t Ln = __shfl_sync(FULL, mlen, static_cast<int>((t + 1u) & 31u));
-      const bool defer = CMP_LAZY && L != 0u && t + 1u < 32u && Ln > L;
-      if (lane == t) {
-        start = true;
-        as_lit = defer;
+    while (t < lim) {
+      const uint32_t rest = mm & (0xffffffffu << t);                         // matches at or after t ..
+      const uint32_t p = rest ? cmp_ctz(rest) : 32u;                         // .. the first of them
+      if (p >= lim) {                                                        // literals to the end of the step
+        start_mask |= (0xffffffffu << t) & (0xffffffffu >> (32u - lim));
+        t = lim;
+        break;
       }
-      t += (L != 0u && !defer) ? L : 1u;
+      start_mask |= (0xffffffffu << t) & (0xffffffffu >> (31u - p));         // literals [t, p) and the token at p
+      const uint32_t L = __shfl_sync(FULL, mlen, static_cast<int>(p));
+      const uint32_t Ln = __shfl_sync(FULL, mlen, static_cast<int>((p + 1u) & 31u));
+      const bool defer = CMP_LAZY && p + 1u < 32u && Ln > L;
+      if (defer) {
+        lit_mask |= 1u << p;
+        t = p + 1u;
+      } else {
+        t = p + L;
+      }
     }
+    const bool start = ((start_mask >> lane) & 1u) != 0u, as_lit = ((lit_mask >> lane) & 1u) != 0u;
     if (as_lit) mlen = 0;
     if constexpr (MODE == 0) {
       if (start) {
