@@ -442,7 +442,7 @@ struct LzwState {
 // descriptors of a stream are all there before pass 2 starts, only the source bytes may not be
 // final yet — a prefetch does not care).  Half of this kernel's stall samples on text are gathers
 // that miss the L2, but the kernel is also issue-bound and moves 2.9 TB/s of DRAM
-// traffic: C2 pass 2 10.3 ms with the prefetch against 8.5 ms without (gpurun_out/r02_ab_pf1.jsonl).
+// traffic: C2 pass 2 10.3 ms with the prefetch against 8.5 ms without (profiles/ab/r02_ab_pf1.jsonl).
 template <bool CG, bool PF = false>
 __device__ __forceinline__ void lzw_run(const LzwView& v, LzwState& s, uint32_t w_stop, uint32_t look)
 {
