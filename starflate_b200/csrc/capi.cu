@@ -942,6 +942,18 @@ int batch_device_impl(sfb200_ctx* ctx, const uint8_t* src_base, const uint64_t* 
   }
   SFB_TRY(ctx, cudaEventRecord(ctx->ev[3], st));
   ctx->ev_valid = true;
+  if (qmode) {
+    // (experimental mode: synchronous, so that a consumer that gave up waiting — lz_window.cuh:
+    //  lzq_give_up — fails the call instead of leaving matches unresolved behind a success)
+    unsigned long long q8[8] = {0};
+    SFB_TRY(ctx, cudaStreamSynchronize(st));
+    SFB_TRY(ctx, cudaMemcpy(q8, ctx->d_queue, sizeof(q8), cudaMemcpyDeviceToHost));
+    if (q8[4] != 0ull) {
+      ctx->err = "queue mode: a pass-2 consumer gave up waiting (" + std::string(q8[4] == 1ull ? "for an item" : "for its turn") +
+                 ", " + std::to_string(q8[5]) + " / " + std::to_string(q8[6]) + " / " + std::to_string(q8[7]) + ")";
+      return SFB200_RC_CUDA_ERROR;
+    }
+  }
   return SFB200_RC_OK;
 }
 
