@@ -8,6 +8,10 @@ judged without GPU time.
 The loop is found as the address range between the first instruction attributed to the loop
 condition line and the last backward branch to it; the rare paths inside it (exact slow path, long
 codes) are excluded by source line.
+NOTE (end of round 2): the rare-path line ranges below (deflate_lane.cuh 560-590, the markers in
+huff_lanes.cuh) have not followed the last source changes: the total it prints includes the inlined
+exact path.  The per-line execution counts of an ncu capture (tools/ncu_src_hot.py ... inst) are
+what DESIGN.md's per-iteration figures come from.
 """
 from __future__ import annotations
 
@@ -40,7 +44,7 @@ def main():
     src_lines = open(os.path.join(ROOT, "starflate_b200", "csrc", "huff_lanes.cuh")).read().splitlines()
     loop_line = next(i + 1 for i, l in enumerate(src_lines) if "while (__any_sync(FULL, state == S_DECODE))" in l)
     rare_lo = next(i + 1 for i, l in enumerate(src_lines) if "// (a) a valid code longer than the tables hold" in l) - 1
-    rare_hi = next(i + 1 for i, l in enumerate(src_lines) if "if (dec) br.skip(used);" in l) - 1
+    rare_hi = next(i + 1 for i, l in enumerate(src_lines) if "if (t.status == ST_SUCCESS) br.skip(used);" in l) - 1
     ins = []
     cur, infn = None, False
     for l in txt.splitlines():
@@ -59,7 +63,7 @@ def main():
         raise SystemExit("kernel not found")
     # the token loop: the address range spanned by the instructions attributed to the loop's own
     # source lines (the callees are inlined: their instructions lie in between)
-    body_lo = loop_line
+    body_lo = loop_line + 1   # (the condition's own line also has instructions in front of the loop)
     body_hi = next(i + 1 for i, l in enumerate(src_lines) if "p_skip = mt ? value - 3u : 0u;" in l)
     own = [a for a, t, s in ins if s and s[0] == "huff_lanes.cuh" and body_lo <= s[1] <= body_hi and not (rare_lo <= s[1] <= rare_hi)]
     start, end = min(own), max(own)
